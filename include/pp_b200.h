@@ -1,0 +1,167 @@
+/*
+ * pp_b200.h -- C ABI of libpp_b200.so: the B200 (sm_100a) replacement for the
+ * data-parallel hot path of yifita/pytorch_points.
+ *
+ * Each entry point replaces one function of the reference's pybind11 extension
+ * modules `pytorch_points._ext.losses` / `pytorch_points._ext.sampling` (cited
+ * per function, paths relative to /root/reference/pytorch_points/).  No torch
+ * types cross this boundary: plain device pointers, sizes, a device ordinal and
+ * a CUDA stream handle (`void*` == cudaStream_t; NULL = legacy default stream).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major memory on
+ *     `device`; the library never allocates, frees or retains caller memory;
+ *   - all launches are asynchronous on `stream`;
+ *   - return value: PP_OK (0) on success, a negative PP_E* code for argument
+ *     errors, or a positive cudaError_t; pp_last_error_string() describes the
+ *     last failure on the calling thread.  Nothing ever calls exit() (the
+ *     reference does: _ext/sampling_cuda.cu:40-44) or prints-and-continues
+ *     (_ext/nmdistance_cuda.cu:132-137);
+ *   - indices are int32 like the reference's IntTensor outputs.
+ */
+#ifndef PP_B200_H
+#define PP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_OK 0
+#define PP_EINVAL (-22)   /* bad size / null pointer / unsupported shape */
+#define PP_ENOSPC (-28)   /* workspace too small */
+
+/* Library / ABI version (bumped when a signature changes). */
+int pp_version(void);
+/* Human-readable description of the last error on this thread ("" if none). */
+const char *pp_last_error_string(void);
+
+/* ------------------------------------------------------------------ losses */
+
+/* Scratch bytes pp_chamfer_fwd needs for (B,N,M). */
+size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M);
+
+/*
+ * Chamfer / nndistance forward.  Replaces losses.nmdistance_forward
+ * (_ext/nmdistance.cpp:13-15,31 -> _ext/nmdistance_cuda.cu:118-140, kernel :8-49).
+ *   xyz1 (B,N,c) xyz2 (B,M,c) fp32 -> dist1 (B,N) dist2 (B,M) squared distances,
+ *   idx1 (B,N) idx2 (B,M) int32 argmin, lowest index on ties.
+ *   sums: optional (may be NULL) 2 floats receiving [sum(dist1), sum(dist2)]
+ *   (fused reduction for the loss mean / NCCL all-reduce input).
+ *   workspace: >= pp_chamfer_fwd_workspace_bytes(B,N,M) bytes, 8-byte aligned.
+ */
+int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
+                   float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,
+                   void *workspace, size_t workspace_bytes, int device, void *stream);
+
+/*
+ * Labeled Chamfer forward.  Replaces losses.labeled_nmdistance_forward
+ * (_ext/nmdistance.cpp:17-20,32 -> _ext/nmdistance_cuda.cu:56-115,142-166).
+ *   label1 (B,N) label2 (B,M) fp32 (the reference casts labels to the point dtype,
+ *   network/model_loss.py:452-453); unmatched points get idx -1, dist 0.
+ */
+int pp_chamfer_labeled_fwd(const float *xyz1, const float *xyz2, const float *label1,
+                           const float *label2, int B, int N, int M, int c, float *dist1,
+                           float *dist2, int32_t *idx1, int32_t *idx2, int device, void *stream);
+
+/*
+ * Chamfer backward.  Replaces losses.nmdistance_backward
+ * (_ext/nmdistance.cpp:23-27,33 -> _ext/nmdistance_cuda.cu:169-221).
+ *   gradxyz1 (B,N,c) / gradxyz2 (B,M,c) are fully overwritten (no pre-zeroing needed);
+ *   entries with idx < 0 contribute nothing (:175).
+ */
+int pp_chamfer_bwd(const float *xyz1, const float *xyz2, const float *graddist1,
+                   const float *graddist2, const int32_t *idx1, const int32_t *idx2, int B, int N,
+                   int M, int c, float *gradxyz1, float *gradxyz2, int device, void *stream);
+
+/* ---------------------------------------------------------------- sampling */
+
+/*
+ * Farthest point sampling.  Replaces sampling.furthest_sampling
+ * (_ext/sampling.cpp:68-80,207 -> _ext/sampling_cuda.cu:162-325).
+ *   xyz (B,N,3); temp (B,N) caller-filled with 1e10 (network/geo_operations.py:33), on
+ *   return it holds the final running minima; idx (B,m) int32, idx[:,0] = seed.
+ *   Tie-break is the reference's (k mod bs, k) key, bs = min(2^floor(log2 N), 512).
+ */
+int pp_fps(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
+           int device, void *stream);
+
+/*
+ * gather_points forward / backward.  Replace sampling.gather_forward / gather_backward
+ * (_ext/sampling.cpp:19-41,208-209 -> _ext/sampling_cuda.cu:9-84).
+ *   points (B,C,N), idx (B,npoint) -> out (B,C,npoint);
+ *   backward ACCUMULATES into grad_points (B,C,N) (caller zero-fills, as
+ *   network/operations.py:76-77 does).
+ */
+int pp_gather_fwd(const float *points, const int32_t *idx, int B, int C, int N, int npoint,
+                  float *out, int device, void *stream);
+int pp_gather_bwd(const float *grad_out, const int32_t *idx, int B, int C, int N, int npoint,
+                  float *grad_points, int device, void *stream);
+
+/*
+ * ball_query.  Replaces sampling.ball_query
+ * (_ext/sampling.cpp:85-104,210 -> _ext/sampling_cuda.cu:340-398).
+ *   new_xyz (B,M,3) centres, xyz (B,N,3) -> idx (B,M,nsample) int32: first nsample
+ *   points (ascending index) with d^2 < radius^2, padded with the first hit, all 0 when
+ *   the ball is empty.  Every output slot is written (no pre-zeroing needed).
+ */
+int pp_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
+                  int nsample, int32_t *idx, int device, void *stream);
+
+/*
+ * group_points forward / backward ("next" row N1).  Replace sampling.group_points /
+ * group_points_grad (_ext/sampling.cpp:113-161,211-212 -> _ext/sampling_cuda.cu:447-514).
+ *   points (B,C,N), idx (B,npoint,nsample) -> out (B,C,npoint,nsample);
+ *   backward ACCUMULATES into grad_points (B,C,N).
+ */
+int pp_group_fwd(const float *points, const int32_t *idx, int B, int C, int N, int npoint,
+                 int nsample, float *out, int device, void *stream);
+int pp_group_bwd(const float *grad_out, const int32_t *idx, int B, int C, int N, int npoint,
+                 int nsample, float *grad_points, int device, void *stream);
+
+/* --------------------------------------------------------------------- knn */
+
+/* Scratch bytes pp_knn needs. */
+size_t pp_knn_workspace_bytes(int B, int M, int N, int c, int k);
+
+/*
+ * group_knn core: k nearest neighbours of every query among `points`.
+ * The reference snapshot names the op (README.md:12) but ships no implementation; its
+ * callers use pytorch3d.ops.knn_points (network/layers.py:52, network/geo_operations.py:112,139,
+ * network/model_loss.py:120,147,378).  Contract (defined by this repo):
+ *   query (B,M,c), points (B,N,c), 1 <= k <= min(N, PP_KNN_MAX_K) ->
+ *   dist (B,M,k) squared L2 in the Chamfer op order, idx (B,M,k) int32,
+ *   sorted ascending by (distance, index).
+ */
+#define PP_KNN_MAX_K 64
+int pp_knn(const float *query, const float *points, int B, int M, int N, int c, int k,
+           float *dist, int32_t *idx, void *workspace, size_t workspace_bytes, int device,
+           void *stream);
+
+/*
+ * three_nn ("next" row N3).  Replaces sampling.three_nn
+ * (_ext/sampling.cpp:163-176,213 -> _ext/interpolate_gpu.cu:9-75).
+ *   unknown (B,N,3), known (B,M,3) -> dist2 (B,N,3) squared, idx (B,N,3) int32.
+ */
+int pp_three_nn(const float *unknown, const float *known, int B, int N, int M, float *dist2,
+                int32_t *idx, int device, void *stream);
+
+/* ------------------------------------------------------------- diagnostics */
+
+/*
+ * Micro-benchmarks used to measure the roofline denominators that
+ * MEASURED_PEAKS.json lacks (FP32 pipe, shared memory, L2).  `which` selects the
+ * probe, `iters` its length; returns elapsed milliseconds in *ms and the work
+ * (flop or bytes) in *work.  Not part of the reference surface.
+ */
+int pp_microbench(int which, int iters, float *ms, double *work, int device);
+
+/* Tuning knob for experiments: selects a kernel variant (0 = default). */
+int pp_set_option(const char *name, int value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PP_B200_H */

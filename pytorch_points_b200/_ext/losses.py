@@ -1,0 +1,83 @@
+"""Mirror of `pytorch_points._ext.losses` (_ext/nmdistance.cpp:30-34).
+
+Caller allocates every output, exactly like the reference; functions return 1 on success
+(the reference returns 1 / 0 and prints on failure -- here failures raise instead)."""
+import torch
+
+from .. import _C
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes):
+    """Per-device scratch buffer, grown on demand (the packed (distance, granule) keys of the
+    one-pass Chamfer kernel).  Stream-ordered reuse: callers on one stream never overlap."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _check_f32(*ts):
+    for t in ts:
+        if t.dtype != torch.float32:
+            raise RuntimeError("pytorch_points_b200: only float32 point clouds are supported, got %s" % t.dtype)
+
+
+def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None):
+    """losses.nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2) -> int
+    (_ext/nmdistance.cpp:13-15).  `sums` (optional, 2 floats) is an extension: fused
+    [sum(dist1), sum(dist2)]."""
+    dev = _C.require_cuda(xyz1, xyz2, dist1, dist2, idx1, idx2)
+    _C.require_contiguous(xyz1, xyz2, dist1, dist2, idx1, idx2)
+    _check_f32(xyz1, xyz2, dist1, dist2)
+    B, N, c = xyz1.shape
+    M = xyz2.shape[1]
+    if xyz2.shape[0] != B or xyz2.shape[2] != c:
+        raise RuntimeError("nmdistance_forward: xyz1 %s and xyz2 %s disagree" % (tuple(xyz1.shape), tuple(xyz2.shape)))
+    if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
+        raise RuntimeError("nmdistance_forward: idx tensors must be int32")
+    nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
+    ws = _workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_chamfer_fwd(_C.ptr(xyz1), _C.ptr(xyz2), B, N, M, c, _C.ptr(dist1), _C.ptr(dist2),
+                                   _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums), _C.ptr(ws), ws.numel(),
+                                   dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_chamfer_fwd")
+    return 1
+
+
+def labeled_nmdistance_forward(xyz1, xyz2, label1, label2, dist1, dist2, idx1, idx2):
+    """losses.labeled_nmdistance_forward (_ext/nmdistance.cpp:17-20)."""
+    dev = _C.require_cuda(xyz1, xyz2, label1, label2, dist1, dist2, idx1, idx2)
+    label1 = label1.to(dtype=xyz1.dtype).contiguous()  # nmdistance_cuda.cu:153 (toType)
+    label2 = label2.to(dtype=xyz1.dtype).contiguous()
+    _C.require_contiguous(xyz1, xyz2, dist1, dist2, idx1, idx2)
+    _check_f32(xyz1, xyz2, dist1, dist2)
+    B, N, c = xyz1.shape
+    M = xyz2.shape[1]
+    if label1.numel() != B * N or label2.numel() != B * M:
+        raise RuntimeError("labeled_nmdistance_forward: labels must be (B,N[,1]) and (B,M[,1])")
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_chamfer_labeled_fwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(label1), _C.ptr(label2), B, N, M, c,
+                                           _C.ptr(dist1), _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2),
+                                           dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_chamfer_labeled_fwd")
+    return 1
+
+
+def nmdistance_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2):
+    """losses.nmdistance_backward (_ext/nmdistance.cpp:23-27).  gradxyz1/2 are overwritten."""
+    dev = _C.require_cuda(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2)
+    _C.require_contiguous(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2)
+    _check_f32(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2)
+    B, N, c = xyz1.shape
+    M = xyz2.shape[1]
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_chamfer_bwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(graddist1), _C.ptr(graddist2),
+                                   _C.ptr(idx1), _C.ptr(idx2), B, N, M, c, _C.ptr(gradxyz1), _C.ptr(gradxyz2),
+                                   dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_chamfer_bwd")
+    return 1

@@ -1,0 +1,142 @@
+"""Mirror of `pytorch_points._ext.sampling` (_ext/sampling.cpp:205-216)."""
+import torch
+
+from .. import _C
+
+
+def _check(cond, msg):
+    if not cond:
+        raise RuntimeError("pytorch_points_b200: " + msg)
+
+
+def furthest_sampling(m, seedIdx, input, temp, idx):
+    """sampling.furthest_sampling(m, seedIdx, input, temp, idx) -> idx (_ext/sampling.cpp:68-80)."""
+    dev = _C.require_cuda(input, temp, idx)
+    _C.require_contiguous(input, temp, idx)
+    _check(input.dtype == torch.float32 and temp.dtype == torch.float32, "furthest_sampling: float32 only")
+    _check(idx.dtype == torch.int32, "furthest_sampling: idx must be int32")
+    B, N, c = input.shape
+    _check(c == 3, "furthest sampling is implemented for 3D points")
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_fps(_C.ptr(input), B, N, int(m), int(seedIdx), _C.ptr(temp), _C.ptr(idx), dev.index,
+                           _C.stream_of(dev))
+    _C.check(rc, "pp_fps")
+    return idx
+
+
+def gather_forward(b, c, n, npoints, points, idx, out):
+    """sampling.gather_forward (_ext/sampling.cpp:19-28)."""
+    dev = _C.require_cuda(points, idx, out)
+    _C.require_contiguous(points, idx, out)
+    _check(points.dtype == torch.float32 and idx.dtype == torch.int32, "gather_forward: float32 points, int32 idx")
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_gather_fwd(_C.ptr(points), _C.ptr(idx), b, c, n, npoints, _C.ptr(out), dev.index,
+                                  _C.stream_of(dev))
+    _C.check(rc, "pp_gather_fwd")
+    return 1
+
+
+def gather_backward(b, c, n, npoints, grad_out, idx, grad_points):
+    """sampling.gather_backward (_ext/sampling.cpp:31-41); accumulates into grad_points."""
+    dev = _C.require_cuda(grad_out, idx, grad_points)
+    _C.require_contiguous(grad_out, idx, grad_points)
+    _check(grad_out.dtype == torch.float32 and idx.dtype == torch.int32, "gather_backward: float32 grads, int32 idx")
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_gather_bwd(_C.ptr(grad_out), _C.ptr(idx), b, c, n, npoints, _C.ptr(grad_points), dev.index,
+                                  _C.stream_of(dev))
+    _C.check(rc, "pp_gather_bwd")
+    return 1
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    """sampling.ball_query(new_xyz, xyz, radius, nsample) -> idx (B,M,nsample) int32
+    (_ext/sampling.cpp:85-104; the callee allocates the output there too)."""
+    dev = _C.require_cuda(new_xyz, xyz)
+    _C.require_contiguous(new_xyz, xyz)  # CHECK_INPUT in the reference
+    _check(new_xyz.dtype == torch.float32 and xyz.dtype == torch.float32, "ball_query: float32 only")
+    B, M, _ = new_xyz.shape
+    N = xyz.shape[1]
+    idx = torch.empty(B, M, int(nsample), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_ball_query(_C.ptr(new_xyz), _C.ptr(xyz), B, N, M, float(radius), int(nsample), _C.ptr(idx),
+                                  dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_ball_query")
+    return idx
+
+
+def group_points(points, idx):
+    """sampling.group_points(points (B,C,N), idx (B,npoint,nsample)) -> (B,C,npoint,nsample)
+    (_ext/sampling.cpp:113-136)."""
+    dev = _C.require_cuda(points, idx)
+    _C.require_contiguous(points, idx)
+    _check(points.dtype == torch.float32, "points must be a float tensor")
+    _check(idx.dtype == torch.int32, "idx must be an int tensor")
+    B, C, N = points.shape
+    _, npoint, nsample = idx.shape
+    out = torch.empty(B, C, npoint, nsample, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_group_fwd(_C.ptr(points), _C.ptr(idx), B, C, N, npoint, nsample, _C.ptr(out), dev.index,
+                                 _C.stream_of(dev))
+    _C.check(rc, "pp_group_fwd")
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    """sampling.group_points_grad(grad_out (B,C,npoint,nsample), idx, n) -> (B,C,n)
+    (_ext/sampling.cpp:138-161)."""
+    dev = _C.require_cuda(grad_out, idx)
+    _C.require_contiguous(grad_out, idx)
+    _check(grad_out.dtype == torch.float32, "grad_out must be a float tensor")
+    _check(idx.dtype == torch.int32, "idx must be an int tensor")
+    B, C, npoint, nsample = grad_out.shape
+    g = torch.zeros(B, C, int(n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_group_bwd(_C.ptr(grad_out), _C.ptr(idx), B, C, int(n), npoint, nsample, _C.ptr(g), dev.index,
+                                 _C.stream_of(dev))
+    _C.check(rc, "pp_group_bwd")
+    return g
+
+
+def three_nn(unknown, known):
+    """sampling.three_nn(unknown (B,N,3), known (B,M,3)) -> (dist2 (B,N,3), idx (B,N,3))
+    (_ext/sampling.cpp:163-176)."""
+    dev = _C.require_cuda(unknown, known)
+    _C.require_contiguous(unknown, known)
+    B, N, _ = unknown.shape
+    M = known.shape[1]
+    dist2 = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
+    idx = torch.empty(B, N, 3, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_three_nn(_C.ptr(unknown), _C.ptr(known), B, N, M, _C.ptr(dist2), _C.ptr(idx), dev.index,
+                                _C.stream_of(dev))
+    _C.check(rc, "pp_three_nn")
+    return dist2, idx
+
+
+def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
+    """sampling.three_nn_wrapper(b, n, m, unknown, known, dist2, idx) with caller-allocated outputs,
+    the exact pybind signature of the reference (_ext/sampling.cpp:163-173,213)."""
+    dev = _C.require_cuda(unknown, known, dist2, idx)
+    _C.require_contiguous(unknown, known, dist2, idx)
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_three_nn(_C.ptr(unknown), _C.ptr(known), b, n, m, _C.ptr(dist2), _C.ptr(idx), dev.index,
+                                _C.stream_of(dev))
+    _C.check(rc, "pp_three_nn")
+
+
+def knn(k, query, points):
+    """group_knn core (no reference counterpart): query (B,M,c), points (B,N,c)
+    -> dist (B,M,k) ascending squared distances, idx (B,M,k) int32."""
+    dev = _C.require_cuda(query, points)
+    _C.require_contiguous(query, points)
+    _check(query.dtype == torch.float32 and points.dtype == torch.float32, "knn: float32 only")
+    B, M, c = query.shape
+    N = points.shape[1]
+    _check(points.shape[0] == B and points.shape[2] == c, "knn: query/points shapes disagree")
+    dist = torch.empty(B, M, int(k), dtype=torch.float32, device=dev)
+    idx = torch.empty(B, M, int(k), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_knn(_C.ptr(query), _C.ptr(points), B, M, N, c, int(k), _C.ptr(dist), _C.ptr(idx),
+                           _C.ptr(None), 0, dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_knn")
+    return dist, idx

@@ -1,0 +1,156 @@
+// pp_common.cuh -- shared helpers for the sm_100a kernels of libpp_b200.so.
+// No torch headers anywhere in csrc/: the library is a plain C-ABI CUDA .so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pp_b200.h"
+
+namespace pp {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int NUM_SMS_B200 = 148;
+
+void set_error(const char *fmt, ...);
+int get_option(const char *name, int dflt);
+
+// RAII device switch: every entry point runs on the device the caller names and
+// restores the previous one, so a mismatched "current device" can never send a
+// launch to the wrong GPU (the reference has no device guard).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) {
+            err = cudaSetDevice(device);
+            changed = (err == cudaSuccess);
+        }
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+
+#define PP_REQUIRE(cond, ...)                  \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::pp::set_error(__VA_ARGS__);      \
+            return PP_EINVAL;                  \
+        }                                      \
+    } while (0)
+
+#define PP_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ::pp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                     \
+            return (int)_e;                                                                \
+        }                                                                                  \
+    } while (0)
+
+#define PP_LAUNCH_CHECK()                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            ::pp::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, \
+                            __LINE__);                                                        \
+            return (int)_e;                                                                   \
+        }                                                                                     \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------
+// fp32 building blocks with the rounding order pinned by explicit intrinsics /
+// PTX (never left to the compiler's contraction), SURVEY.md D4 + Appendix A.
+// ---------------------------------------------------------------------------
+
+// Chamfer / KNN order (_ext/nmdistance_cuda.cu:31-35): t = ref - query,
+// d = fma(tz,tz, fma(ty,ty, rn(tx*tx))).
+__device__ __forceinline__ float sqdist_xyz(float rx, float ry, float rz, float qx, float qy,
+                                            float qz) {
+    const float tx = __fsub_rn(rx, qx), ty = __fsub_rn(ry, qy), tz = __fsub_rn(rz, qz);
+    return __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, __fmul_rn(tx, tx)));
+}
+
+// FPS / ball_query / three_nn order (_ext/sampling_cuda.cu:202,364; interpolate_gpu.cu:36):
+// the 3-term expression contracts to fma(dz,dz, fma(dx,dx, rn(dy*dy))) -- y first.
+__device__ __forceinline__ float sqdist_yxz(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// Packed fp32x2 (Blackwell FADD2/FMUL2/FFMA2): two Chamfer-order distances per
+// instruction stream.  (rx,ry,rz) hold two reference points, nq* the NEGATED query
+// coordinate: rn(r + (-q)) == rn(r - q) bit for bit.  ptxas folds the {nq,nq}
+// pair into the .F32 broadcast operand of FADD2.
+__device__ __forceinline__ float2 sqdist2_xyz(float2 rx, float2 ry, float2 rz, float nqx, float nqy,
+                                              float nqz) {
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 bx, by, bz, qx, qy, qz, tx, ty, tz, dd;\n\t"
+        "mov.b64 bx, {%2, %3};\n\t"
+        "mov.b64 by, {%4, %5};\n\t"
+        "mov.b64 bz, {%6, %7};\n\t"
+        "mov.b64 qx, {%8, %8};\n\t"
+        "mov.b64 qy, {%9, %9};\n\t"
+        "mov.b64 qz, {%10, %10};\n\t"
+        "add.rn.f32x2 tx, bx, qx;\n\t"
+        "add.rn.f32x2 ty, by, qy;\n\t"
+        "add.rn.f32x2 tz, bz, qz;\n\t"
+        "mul.rn.f32x2 dd, tx, tx;\n\t"
+        "fma.rn.f32x2 dd, ty, ty, dd;\n\t"
+        "fma.rn.f32x2 dd, tz, tz, dd;\n\t"
+        "mov.b64 {%0, %1}, dd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(rx.x), "f"(rx.y), "f"(ry.x), "f"(ry.y), "f"(rz.x), "f"(rz.y), "f"(nqx), "f"(nqy),
+          "f"(nqz));
+    return d;
+}
+
+// Same but in the FPS / ball_query order (y first): d = fma(tz,tz, fma(tx,tx, rn(ty*ty))).
+__device__ __forceinline__ float2 sqdist2_yxz(float2 rx, float2 ry, float2 rz, float nqx, float nqy,
+                                              float nqz) {
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 bx, by, bz, qx, qy, qz, tx, ty, tz, dd;\n\t"
+        "mov.b64 bx, {%2, %3};\n\t"
+        "mov.b64 by, {%4, %5};\n\t"
+        "mov.b64 bz, {%6, %7};\n\t"
+        "mov.b64 qx, {%8, %8};\n\t"
+        "mov.b64 qy, {%9, %9};\n\t"
+        "mov.b64 qz, {%10, %10};\n\t"
+        "add.rn.f32x2 tx, bx, qx;\n\t"
+        "add.rn.f32x2 ty, by, qy;\n\t"
+        "add.rn.f32x2 tz, bz, qz;\n\t"
+        "mul.rn.f32x2 dd, ty, ty;\n\t"
+        "fma.rn.f32x2 dd, tx, tx, dd;\n\t"
+        "fma.rn.f32x2 dd, tz, tz, dd;\n\t"
+        "mov.b64 {%0, %1}, dd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(rx.x), "f"(rx.y), "f"(ry.x), "f"(ry.y), "f"(rz.x), "f"(rz.y), "f"(nqx), "f"(nqy),
+          "f"(nqz));
+    return d;
+}
+
+// Three-input min/max (FMNMX3 on sm_100).
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+constexpr float PP_INF = __builtin_huge_valf();
+
+}  // namespace pp

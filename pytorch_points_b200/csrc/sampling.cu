@@ -1,0 +1,504 @@
+// sampling.cu -- farthest point sampling, gather, ball_query, group, three_nn for sm_100a.
+//
+// Replaces _ext/sampling_cuda.cu + _ext/interpolate_gpu.cu (three_nn) of the reference.
+#include <cooperative_groups.h>
+
+#include "pp_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pp {
+namespace {
+
+// ===========================================================================
+// Farthest point sampling (_ext/sampling_cuda.cu:162-233).
+//
+// The reference runs ONE 512-thread block per cloud, re-reads 97% of the points
+// and all running minima from global memory every round, and reduces with a
+// 9-level shared-memory tree.  FPS is a latency chain (m-1 dependent rounds), so
+// the B200 design minimises the per-round critical path instead:
+//   * a cloud is spread over a thread-block CLUSTER of C CTAs (C <= 8) x 512
+//     threads; every thread keeps P points and their running minima in REGISTERS
+//     for the whole kernel (no per-round memory traffic at all);
+//   * per round: register update -> 2 REDUX per warp (max value, then min
+//     tie-key among the maxima) -> one bar.sync -> 2 REDUX over the warp records
+//     -> the CTA winner (value, tie-key, xyz) is pushed into every CTA of the
+//     cluster through distributed shared memory -> one cluster barrier -> every
+//     thread picks the cluster winner from C records.
+//   * tie-break is the reference's: among equal maxima the smallest
+//     (k mod bs, k), bs = min(2^floor(log2 N), 512)  (SURVEY.md D3, A.2).
+// Thread t of the cluster owns points k = t + p*T_total (p = 0..P-1): T_total is a
+// multiple of bs, so (k mod bs) is constant per thread and the tie-key grows with
+// p; a strict > scan in p order therefore keeps the lowest tie-key per thread.
+// ===========================================================================
+constexpr int FPS_T = 512;
+constexpr int FPS_MAXC = 8;
+constexpr int FPS_W = FPS_T / 32;
+
+struct FpsRec {  // 32 bytes
+    int v;       // running-min value bits (>= 0 for real points, -1.0f for padding)
+    unsigned t;  // tie-key
+    float x, y, z;
+    int k;  // point index
+    int pad0, pad1;
+};
+
+__device__ __forceinline__ unsigned fps_tiekey(int k, int bs_log2) {
+    return ((unsigned)(k & ((1 << bs_log2) - 1)) << 22) | (unsigned)(k >> bs_log2);
+}
+
+template <int P, int C>
+__global__ void __launch_bounds__(FPS_T, 1)
+fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float *__restrict__ temp,
+                   int *__restrict__ idx, int bs_log2) {
+    extern __shared__ __align__(16) unsigned char fps_smem[];
+    float4 *sPts = reinterpret_cast<float4 *>(fps_smem);  // [P][FPS_T] this CTA's points
+    __shared__ __align__(8) int2 wrec[2][FPS_W];           // per-warp (value, tie-key)
+    __shared__ __align__(16) FpsRec crec[2][FPS_MAXC];     // per-CTA winners, written by peers
+
+    const int rank = (C > 1) ? (int)cg::this_cluster().block_rank() : 0;
+    const int b = blockIdx.x / C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tg = rank * FPS_T + tid;  // thread index within the cluster
+    constexpr int TT = FPS_T * C;
+
+    const float *pts = xyz + (size_t)b * N * 3;
+    float *tp = temp + (size_t)b * N;
+    int *out = idx + (size_t)b * m;
+
+    float px[P], py[P], pz[P], td[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const int k = tg + p * TT;
+        if (k < N) {
+            px[p] = __ldg(pts + (size_t)k * 3 + 0);
+            py[p] = __ldg(pts + (size_t)k * 3 + 1);
+            pz[p] = __ldg(pts + (size_t)k * 3 + 2);
+            td[p] = tp[k];
+        } else {
+            px[p] = py[p] = pz[p] = 0.f;
+            td[p] = -1.f;  // padding can never be the maximum (real minima are >= 0)
+        }
+        sPts[p * FPS_T + tid] = make_float4(px[p], py[p], pz[p], 0.f);
+    }
+    const unsigned tk0 = fps_tiekey(tg, bs_log2);  // tie-key of point p: tk0 + p * (TT >> bs_log2)
+    const unsigned tkstep = (unsigned)(TT >> bs_log2);
+
+    // coordinates of the seed point, first output
+    float ox = __ldg(pts + (size_t)seed * 3 + 0), oy = __ldg(pts + (size_t)seed * 3 + 1),
+          oz = __ldg(pts + (size_t)seed * 3 + 2);
+    if (tg == 0) out[0] = seed;
+    __syncthreads();
+    if (C > 1) cg::this_cluster().sync();  // peers' shared memory is live before any remote store
+
+    for (int j = 1; j < m; j++) {
+        const int par = j & 1;
+        float best = -1.f;
+        int bp = 0;
+#pragma unroll
+        for (int p = 0; p < P; p++) {
+            const float d = sqdist_yxz(__fsub_rn(px[p], ox), __fsub_rn(py[p], oy), __fsub_rn(pz[p], oz));
+            const float d2 = fminf(d, td[p]);
+            td[p] = d2;
+            if (d2 > best) {
+                best = d2;
+                bp = p;
+            }
+        }
+        // warp: max value, then min tie-key among the lanes holding it
+        const int myv = __float_as_int(best);
+        const unsigned mytk = tk0 + (unsigned)bp * tkstep;
+        const int wv = __reduce_max_sync(FULL_MASK, myv);
+        const unsigned wt = __reduce_min_sync(FULL_MASK, myv == wv ? mytk : 0xffffffffu);
+        if (lane == 0) wrec[par][warp] = make_int2(wv, (int)wt);
+        __syncthreads();
+        // every warp reduces the FPS_W warp records redundantly (no second barrier)
+        int2 r = lane < FPS_W ? wrec[par][lane] : make_int2(INT_MIN, -1);
+        const int cv = __reduce_max_sync(FULL_MASK, r.x);
+        const unsigned ct = __reduce_min_sync(FULL_MASK, r.x == cv ? (unsigned)r.y : 0xffffffffu);
+        // decode the CTA winner: k = (k div bs) * bs + (k mod bs)
+        const int ck = (int)((ct & 0x3fffffu) << bs_log2) | (int)(ct >> 22);
+        if (C == 1) {
+            const int slot = (ck / TT) * FPS_T + (ck % TT);
+            const float4 w = sPts[slot];
+            ox = w.x; oy = w.y; oz = w.z;
+            if (tid == 0) out[j] = ck;
+        } else {
+            if (warp == 0 && lane < C) {
+                const int slot = (ck / TT) * FPS_T + (ck % TT - rank * FPS_T);
+                const float4 w = sPts[slot];
+                FpsRec rec;
+                rec.v = cv; rec.t = ct; rec.x = w.x; rec.y = w.y; rec.z = w.z; rec.k = ck;
+                rec.pad0 = 0; rec.pad1 = 0;
+                FpsRec *dst = cg::this_cluster().map_shared_rank(&crec[par][rank], lane);
+                *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<float4 *>(&rec);
+                *(reinterpret_cast<float4 *>(dst) + 1) = *(reinterpret_cast<float4 *>(&rec) + 1);
+            }
+            cg::this_cluster().sync();
+            int bv = INT_MIN;
+            unsigned bt = 0xffffffffu;
+            int bk = 0;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const float4 lo = *reinterpret_cast<const float4 *>(&crec[par][c]);
+                const float4 hi = *(reinterpret_cast<const float4 *>(&crec[par][c]) + 1);
+                const int v = __float_as_int(lo.x);
+                const unsigned t = __float_as_uint(lo.y);
+                if (v > bv || (v == bv && t < bt)) {
+                    bv = v; bt = t; ox = lo.z; oy = lo.w; oz = hi.x; bk = __float_as_int(hi.y);
+                }
+            }
+            if (tg == 0) out[j] = bk;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+        const int k = tg + p * TT;
+        if (k < N) tp[k] = td[p];
+    }
+}
+
+// Fallback for clouds too large for the register-resident kernel: one 1024-thread CTA per
+// cloud streaming points and running minima from global/L2 each round.  Same arithmetic,
+// same tie-key; only meant to keep every size correct.
+__global__ void __launch_bounds__(1024, 1)
+fps_stream_kernel(const float *__restrict__ xyz, int N, int m, int seed, float *__restrict__ temp,
+                  int *__restrict__ idx, int bs_log2) {
+    __shared__ __align__(8) int2 wrec[2][32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *pts = xyz + (size_t)b * N * 3;
+    float *tp = temp + (size_t)b * N;
+    int *out = idx + (size_t)b * m;
+    int old = seed;
+    if (tid == 0) out[0] = seed;
+    for (int j = 1; j < m; j++) {
+        const int par = j & 1;
+        const float ox = __ldg(pts + (size_t)old * 3), oy = __ldg(pts + (size_t)old * 3 + 1),
+                    oz = __ldg(pts + (size_t)old * 3 + 2);
+        float best = -1.f;
+        unsigned btk = 0xffffffffu;
+        // 1024 is a multiple of bs, so (k mod bs) is constant per thread and k ascends
+        for (int k = tid; k < N; k += 1024) {
+            const float d = sqdist_yxz(__fsub_rn(__ldg(pts + (size_t)k * 3), ox),
+                                       __fsub_rn(__ldg(pts + (size_t)k * 3 + 1), oy),
+                                       __fsub_rn(__ldg(pts + (size_t)k * 3 + 2), oz));
+            const float t0 = tp[k];
+            const float d2 = fminf(d, t0);
+            if (d2 != t0) tp[k] = d2;
+            if (d2 > best) {
+                best = d2;
+                btk = fps_tiekey(k, bs_log2);
+            }
+        }
+        const int myv = __float_as_int(best);
+        const int wv = __reduce_max_sync(FULL_MASK, myv);
+        const unsigned wt = __reduce_min_sync(FULL_MASK, myv == wv ? btk : 0xffffffffu);
+        if (lane == 0) wrec[par][warp] = make_int2(wv, (int)wt);
+        __syncthreads();
+        const int2 r = wrec[par][lane];
+        const int cv = __reduce_max_sync(FULL_MASK, r.x);
+        const unsigned ct = __reduce_min_sync(FULL_MASK, r.x == cv ? (unsigned)r.y : 0xffffffffu);
+        old = (int)((ct & 0x3fffffu) << bs_log2) | (int)(ct >> 22);
+        if (tid == 0) out[j] = old;
+    }
+}
+
+// ===========================================================================
+// gather / group (_ext/sampling_cuda.cu:9-84, 447-514): flat one-element-per-thread copies.
+// ===========================================================================
+__global__ void __launch_bounds__(256)
+gather_fwd_kernel(const float *__restrict__ points, const int *__restrict__ idx, int C, int N,
+                  int npoint, long long total, float *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int j = (int)(t % npoint);
+    const long long bc = t / npoint;  // b*C + c
+    const int b = (int)(bc / C);
+    out[t] = __ldg(points + bc * N + __ldg(idx + (size_t)b * npoint + j));
+}
+
+__global__ void __launch_bounds__(256)
+gather_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx, int C, int N,
+                  int npoint, long long total, float *__restrict__ grad_points) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int j = (int)(t % npoint);
+    const long long bc = t / npoint;
+    const int b = (int)(bc / C);
+    atomicAdd(grad_points + bc * N + __ldg(idx + (size_t)b * npoint + j), __ldg(grad_out + t));
+}
+
+__global__ void __launch_bounds__(256)
+group_fwd_kernel(const float *__restrict__ points, const int *__restrict__ idx, int C, int N,
+                 int per_cloud /* npoint*nsample */, long long total, float *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int js = (int)(t % per_cloud);
+    const long long bc = t / per_cloud;
+    const int b = (int)(bc / C);
+    out[t] = __ldg(points + bc * N + __ldg(idx + (size_t)b * per_cloud + js));
+}
+
+__global__ void __launch_bounds__(256)
+group_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx, int C, int N,
+                 int per_cloud, long long total, float *__restrict__ grad_points) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int js = (int)(t % per_cloud);
+    const long long bc = t / per_cloud;
+    const int b = (int)(bc / C);
+    atomicAdd(grad_points + bc * N + __ldg(idx + (size_t)b * per_cloud + js), __ldg(grad_out + t));
+}
+
+// ===========================================================================
+// ball_query (_ext/sampling_cuda.cu:340-376): the reference lets ONE thread scan all N
+// points serially per centre.  Here a WARP owns a centre: 32 lanes test 32 consecutive
+// points per step, a ballot + prefix-popcount compacts the hits in ascending index
+// order, and the scan stops as soon as nsample hits exist.  First-hit padding and the
+// all-zero empty ball are written by the same warp, so no pre-zeroed output is needed.
+// ===========================================================================
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_UNROLL = 4;
+
+__global__ void __launch_bounds__(BQ_WARPS * 32)
+ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int N, int M,
+                  float r2, int nsample, int *__restrict__ idx) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * BQ_WARPS + (threadIdx.x >> 5);
+    if (j >= M) return;
+    const int lane = threadIdx.x & 31;
+    const float *q = new_xyz + ((size_t)b * M + j) * 3;
+    const float nx = __ldg(q), ny = __ldg(q + 1), nz = __ldg(q + 2);
+    const float *p = xyz + (size_t)b * N * 3;
+    int *out = idx + ((size_t)b * M + j) * nsample;
+    const unsigned lt = (1u << lane) - 1u;
+    int cnt = 0, first = 0;
+    for (int base = 0; base < N && cnt < nsample; base += 32 * BQ_UNROLL) {
+        float d2[BQ_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BQ_UNROLL; u++) {
+            const int k = base + u * 32 + lane;
+            d2[u] = PP_INF;
+            if (k < N) {
+                const float x = __ldg(p + (size_t)k * 3), y = __ldg(p + (size_t)k * 3 + 1),
+                            z = __ldg(p + (size_t)k * 3 + 2);
+                d2[u] = sqdist_yxz(__fsub_rn(nx, x), __fsub_rn(ny, y), __fsub_rn(nz, z));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BQ_UNROLL; u++) {
+            const bool hit = d2[u] < r2;  // strict, NaN never matches (:365)
+            const unsigned mask = __ballot_sync(FULL_MASK, hit);
+            if (mask != 0u && cnt < nsample) {
+                if (cnt == 0) first = base + u * 32 + __ffs(mask) - 1;
+                const int pos = cnt + __popc(mask & lt);
+                if (hit && pos < nsample) out[pos] = base + u * 32 + lane;
+                cnt += __popc(mask);
+            }
+        }
+    }
+    if (cnt > nsample) cnt = nsample;
+    // slots cnt.. hold the first hit (:366-370); an empty ball stays all zero (sampling.cpp:93-94)
+    for (int l = cnt + lane; l < nsample; l += 32) out[l] = first;
+}
+
+// ===========================================================================
+// three_nn (_ext/interpolate_gpu.cu:9-52): thread per unknown point, known points staged
+// through shared memory.  The reference keeps its three bests as double initialised to
+// 1e40; every stored value is an exact float and (double)d < 1e40 <=> d < +inf for all
+// non-NaN d, so float bests initialised to +inf give identical results and outputs.
+// ===========================================================================
+constexpr int NN3_TILE = 512;
+
+__global__ void __launch_bounds__(256)
+three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int N, int M,
+                float *__restrict__ dist2, int *__restrict__ idx) {
+    __shared__ float sk[NN3_TILE * 3];
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = j < N;
+    const float *u = unknown + ((size_t)b * N + (active ? j : 0)) * 3;
+    const float ux = u[0], uy = u[1], uz = u[2];
+    const float *kn = known + (size_t)b * M * 3;
+    float b1 = PP_INF, b2 = PP_INF, b3 = PP_INF;
+    int i1 = 0, i2 = 0, i3 = 0;
+    for (int k0 = 0; k0 < M; k0 += NN3_TILE) {
+        const int cnt = min(NN3_TILE, M - k0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt * 3; t += blockDim.x) sk[t] = __ldg(kn + (size_t)k0 * 3 + t);
+        __syncthreads();
+        for (int k = 0; k < cnt; k++) {
+            const float d = sqdist_yxz(__fsub_rn(ux, sk[k * 3]), __fsub_rn(uy, sk[k * 3 + 1]),
+                                       __fsub_rn(uz, sk[k * 3 + 2]));
+            if (d < b1) {
+                b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k0 + k;
+            } else if (d < b2) {
+                b3 = b2; i3 = i2; b2 = d; i2 = k0 + k;
+            } else if (d < b3) {
+                b3 = d; i3 = k0 + k;
+            }
+        }
+    }
+    if (active) {
+        float *od = dist2 + ((size_t)b * N + j) * 3;
+        int *oi = idx + ((size_t)b * N + j) * 3;
+        od[0] = b1; od[1] = b2; od[2] = b3;
+        oi[0] = i1; oi[1] = i2; oi[2] = i3;
+    }
+}
+
+template <int P, int C>
+int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
+                       int bs_log2, cudaStream_t st) {
+    const size_t smem = sizeof(float4) * P * FPS_T;
+    auto kern = fps_cluster_kernel<P, C>;
+    PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B * C);
+    cfg.blockDim = dim3(FPS_T);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PP_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, seed, temp, idx, bs_log2));
+    return PP_OK;
+}
+
+template <int C>
+int dispatch_fps_p(int P, const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
+                   int bs_log2, cudaStream_t st) {
+    if (P <= 1) return launch_fps_cluster<1, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
+    if (P <= 2) return launch_fps_cluster<2, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
+    if (P <= 4) return launch_fps_cluster<4, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
+    if (P <= 8) return launch_fps_cluster<8, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
+    return launch_fps_cluster<16, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
+}
+
+}  // namespace
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
+                      int device, void *stream) {
+    PP_REQUIRE(B >= 0 && N >= 1, "fps: bad sizes B=%d N=%d", B, N);
+    if (m <= 0 || B == 0) return PP_OK;  // _ext/sampling_cuda.cu:166
+    PP_REQUIRE(xyz && temp && idx, "fps: null pointer");
+    PP_REQUIRE(seed >= 0 && seed < N, "fps: seedIdx %d outside [0,%d)", seed, N);
+    PP_REQUIRE(N < (1 << 22), "fps: N=%d too large", N);
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    cudaStream_t st = (cudaStream_t)stream;
+    // bs = max(min(2^floor(log2 N), 512), 1)   (_ext/cuda_utils.h:11-16)
+    int bs_log2 = 0;
+    while ((2 << bs_log2) <= N && bs_log2 < 9) bs_log2++;
+    // cluster width: as wide as the cloud and the machine allow
+    int C = get_option("fps_cluster", 0);
+    if (C == 0) {
+        C = 8;
+        while (C > 1 && (N < C * FPS_T || (long long)B * C > 2 * NUM_SMS_B200)) C >>= 1;
+    }
+    const int P = ceil_div(N, C * FPS_T);
+    if (P > 16 || get_option("fps_stream", 0)) {
+        fps_stream_kernel<<<B, 1024, 0, st>>>(xyz, N, m, seed, temp, idx, bs_log2);
+        PP_LAUNCH_CHECK();
+        return PP_OK;
+    }
+    switch (C) {
+        case 1: return dispatch_fps_p<1>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st);
+        case 2: return dispatch_fps_p<2>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st);
+        case 4: return dispatch_fps_p<4>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st);
+        case 8: return dispatch_fps_p<8>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st);
+        default: break;
+    }
+    set_error("fps: unsupported cluster width %d", C);
+    return PP_EINVAL;
+}
+
+extern "C" int pp_gather_fwd(const float *points, const int32_t *idx, int B, int C, int N, int npoint,
+                             float *out, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && C >= 0 && N >= 0 && npoint >= 0, "gather_fwd: bad sizes");
+    const long long total = (long long)B * C * npoint;
+    if (total == 0) return PP_OK;
+    PP_REQUIRE(points && idx && out && N > 0, "gather_fwd: null pointer or empty source");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    gather_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(points, idx, C, N, npoint, total, out);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_gather_bwd(const float *grad_out, const int32_t *idx, int B, int C, int N, int npoint,
+                             float *grad_points, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && C >= 0 && N >= 0 && npoint >= 0, "gather_bwd: bad sizes");
+    const long long total = (long long)B * C * npoint;
+    if (total == 0) return PP_OK;
+    PP_REQUIRE(grad_out && idx && grad_points && N > 0, "gather_bwd: null pointer or empty target");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    gather_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, C, N, npoint, total, grad_points);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_group_fwd(const float *points, const int32_t *idx, int B, int C, int N, int npoint,
+                            int nsample, float *out, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && C >= 0 && N >= 0 && npoint >= 0 && nsample >= 0, "group_fwd: bad sizes");
+    PP_REQUIRE((long long)npoint * nsample < (1ll << 31), "group_fwd: npoint*nsample too large");
+    const long long total = (long long)B * C * npoint * nsample;
+    if (total == 0) return PP_OK;
+    PP_REQUIRE(points && idx && out && N > 0, "group_fwd: null pointer or empty source");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    group_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(points, idx, C, N, npoint * nsample, total, out);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_group_bwd(const float *grad_out, const int32_t *idx, int B, int C, int N, int npoint,
+                            int nsample, float *grad_points, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && C >= 0 && N >= 0 && npoint >= 0 && nsample >= 0, "group_bwd: bad sizes");
+    PP_REQUIRE((long long)npoint * nsample < (1ll << 31), "group_bwd: npoint*nsample too large");
+    const long long total = (long long)B * C * npoint * nsample;
+    if (total == 0) return PP_OK;
+    PP_REQUIRE(grad_out && idx && grad_points && N > 0, "group_bwd: null pointer or empty target");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    group_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, C, N, npoint * nsample, total, grad_points);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
+                             int nsample, int32_t *idx, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && nsample >= 0, "ball_query: bad sizes");
+    if (B == 0 || M == 0 || nsample == 0) return PP_OK;
+    PP_REQUIRE(new_xyz && idx && (xyz || N == 0), "ball_query: null pointer");
+    PP_REQUIRE(B <= 65535, "ball_query: B=%d too large", B);
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    const float r2 = radius * radius;  // rn(r*r) in fp32 (:354); host float multiply is the same single rounding
+    dim3 grid(ceil_div(M, BQ_WARPS), B);
+    ball_query_kernel<<<grid, BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(new_xyz, xyz, N, M, r2, nsample, idx);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_three_nn(const float *unknown, const float *known, int B, int N, int M, float *dist2,
+                           int32_t *idx, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && N >= 0 && M >= 0, "three_nn: bad sizes");
+    if (B == 0 || N == 0) return PP_OK;
+    PP_REQUIRE(unknown && dist2 && idx && (known || M == 0), "three_nn: null pointer");
+    PP_REQUIRE(B <= 65535, "three_nn: B=%d too large", B);
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    dim3 grid(ceil_div(N, 256), B);
+    three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(unknown, known, N, M, dist2, idx);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}

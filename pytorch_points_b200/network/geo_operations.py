@@ -1,0 +1,45 @@
+"""Farthest point sampling entry points.
+
+Drop-in for `pytorch_points.network.geo_operations.FurthestPointSampling` and
+`furthest_point_sample` (network/geo_operations.py:11-64)."""
+import torch
+
+from .._ext import sampling
+from .operations import gather_points
+
+
+class FurthestPointSampling(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, xyz, npoint, seedIdx):
+        """xyz (B, N, 3) -> idx (B, npoint) int32; idx[:, 0] == seedIdx.  Each next sample is the
+        point with the largest distance to the already selected set (reference tie-break)."""
+        B, N, _ = xyz.size()
+        idx = torch.empty([B, npoint], dtype=torch.int32, device=xyz.device)
+        temp = torch.full([B, N], 1e10, dtype=torch.float32, device=xyz.device)
+        sampling.furthest_sampling(npoint, seedIdx, xyz, temp, idx)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, grad_idx=None):
+        return None, None, None
+
+
+__furthest_point_sample = FurthestPointSampling.apply  # type: ignore
+
+
+def furthest_point_sample(xyz, npoint, NCHW=True, seedIdx=0):
+    """xyz (B, 3, N) if NCHW else (B, N, 3) -> (idx (B, npoint) int32,
+    sampled points (B, 3, npoint) if NCHW else (B, npoint, 3))."""
+    assert xyz.dim() == 3, "input for furthest sampling must be a 3D-tensor, but xyz.size() is {}".format(xyz.size())
+    if NCHW:
+        xyz = xyz.transpose(2, 1).contiguous()
+    else:
+        xyz = xyz.contiguous()
+    assert xyz.size(2) == 3, "furthest sampling is implemented for 3D points"
+    idx = __furthest_point_sample(xyz, npoint, seedIdx)
+    sampled_pc = gather_points(xyz.transpose(2, 1).contiguous(), idx)
+    if not NCHW:
+        sampled_pc = sampled_pc.transpose(2, 1).contiguous()
+    return idx, sampled_pc

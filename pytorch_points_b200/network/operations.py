@@ -1,0 +1,157 @@
+"""gather / ball_query / grouping / KNN entry points.
+
+Drop-in for `pytorch_points.network.operations.GatherFunction`, `gather_points`,
+`BallQuery`, `ball_query`, `GroupingOperation`, `grouping_operation`, `QueryAndGroup`
+(network/operations.py:38-213).  `group_knn` is named by the reference's README (README.md:12)
+but absent from the snapshot; its contract is defined here together with a
+`knn_points` adaptor shaped like the pytorch3d call the snapshot's callers use
+(network/layers.py:52, network/geo_operations.py:112,139)."""
+import torch
+
+from .._ext import sampling
+
+
+class GatherFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx):
+        """features (B, C, N), idx (B, npoint) -> (B, C, npoint)."""
+        features = features.contiguous()
+        idx = idx.contiguous().to(dtype=torch.int32)
+        B, npoint = idx.size()
+        _, C, N = features.size()
+        output = torch.empty(B, C, npoint, dtype=features.dtype, device=features.device)
+        sampling.gather_forward(B, C, N, npoint, features, idx, output)
+        ctx.save_for_backward(idx)
+        ctx.C = C
+        ctx.N = N
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, = ctx.saved_tensors
+        B, npoint = idx.size()
+        grad_features = torch.zeros(B, ctx.C, ctx.N, dtype=grad_out.dtype, device=grad_out.device)
+        sampling.gather_backward(B, ctx.C, ctx.N, npoint, grad_out.contiguous(), idx, grad_features)
+        return grad_features, None
+
+
+gather_points = GatherFunction.apply  # type: ignore
+
+
+class BallQuery(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, radius, nsample, xyz, new_xyz):
+        """radius, nsample, xyz (B, N, 3), new_xyz (B, npoint, 3) -> idx (B, npoint, nsample) int32."""
+        idx = sampling.ball_query(new_xyz, xyz, radius, nsample)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+ball_query = BallQuery.apply  # type: ignore
+
+
+class GroupingOperation(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, idx):
+        """features (B, C, N), idx (B, npoint, nsample) -> (B, C, npoint, nsample)."""
+        _, _, N = features.size()
+        ctx.for_backwards = (idx, N)
+        return sampling.group_points(features, idx)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, N = ctx.for_backwards
+        return sampling.group_points_grad(grad_out.contiguous(), idx, N), None
+
+
+grouping_operation = GroupingOperation.apply  # type: ignore
+
+
+class QueryAndGroup(torch.nn.Module):
+    """Ball query around `new_xyz`, then group (centre-relative) coordinates and features."""
+
+    def __init__(self, radius, nsample, use_xyz=True):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz, new_xyz, features=None):
+        """xyz (B, N, 3), new_xyz (B, npoint, 3), features (B, C, N) -> (B, 3 + C, npoint, nsample)."""
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
+        grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+        if features is None:
+            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+            return grouped_xyz
+        grouped_features = grouping_operation(features, idx)
+        if self.use_xyz:
+            return torch.cat([grouped_xyz, grouped_features], dim=1)
+        return grouped_features
+
+
+class _KNNFunction(torch.autograd.Function):
+    """dist/idx of the k nearest `points` for every `query` point; distances are differentiable
+    w.r.t. both clouds (d/dq = 2 (q - p), d/dp = -2 (q - p))."""
+
+    @staticmethod
+    def forward(ctx, k, query, points):
+        dist, idx = sampling.knn(k, query, points)
+        ctx.save_for_backward(query, points, idx)
+        ctx.mark_non_differentiable(idx)
+        return dist, idx
+
+    @staticmethod
+    def backward(ctx, grad_dist, grad_idx=None):
+        query, points, idx = ctx.saved_tensors
+        B, M, c = query.shape
+        k = idx.shape[2]
+        lidx = idx.long()
+        nn = torch.gather(points.unsqueeze(1).expand(B, M, points.shape[1], c), 2,
+                          lidx.unsqueeze(-1).expand(B, M, k, c))
+        g = 2.0 * grad_dist.unsqueeze(-1) * (query.unsqueeze(2) - nn)  # (B,M,k,c)
+        grad_query = g.sum(dim=2)
+        grad_points = torch.zeros_like(points)
+        grad_points.scatter_add_(1, lidx.reshape(B, M * k, 1).expand(B, M * k, c), -g.reshape(B, M * k, c))
+        return None, grad_query, grad_points
+
+
+def group_knn(k, query, points, unique=True, NCHW=True):
+    """k nearest neighbours of `query` among `points`.
+
+    query (B, C, M), points (B, C, N) if NCHW else (B, M, C) / (B, N, C).
+    Returns (knn_points, idx, dist): knn_points (B, C, M, k) if NCHW else (B, M, k, C),
+    idx (B, M, k) int32, dist (B, M, k) squared L2 ascending; ties broken by lower index.
+    `unique` is accepted for signature compatibility with the upstream project's historical
+    `group_knn`; duplicates are not removed (pytorch3d.knn_points, which the snapshot's callers
+    use, does not remove them either)."""
+    if NCHW:
+        q = query.transpose(1, 2).contiguous()
+        p = points.transpose(1, 2).contiguous()
+    else:
+        q = query.contiguous()
+        p = points.contiguous()
+    dist, idx = _KNNFunction.apply(k, q, p)
+    B, M, _ = q.shape
+    c = p.shape[2]
+    nn = torch.gather(p.unsqueeze(1).expand(B, M, p.shape[1], c), 2,
+                      idx.long().unsqueeze(-1).expand(B, M, k, c))  # (B,M,k,C)
+    if NCHW:
+        nn = nn.permute(0, 3, 1, 2).contiguous()
+    return nn, idx, dist
+
+
+def knn_points(p1, p2, K=1, return_nn=False):
+    """Adaptor with the calling convention of `pytorch3d.ops.knn_points` as used by the snapshot
+    (e.g. `ops.knn_points(x, x, K=k+1, return_nn=True)`, network/layers.py:52):
+    p1 (B, M, C), p2 (B, N, C) -> (dists (B, M, K), idx int64 (B, M, K), nn (B, M, K, C) or None)."""
+    dist, idx = _KNNFunction.apply(K, p1.contiguous(), p2.contiguous())
+    nn = None
+    if return_nn:
+        B, M, _ = p1.shape
+        c = p2.shape[2]
+        nn = torch.gather(p2.unsqueeze(1).expand(B, M, p2.shape[1], c), 2,
+                          idx.long().unsqueeze(-1).expand(B, M, K, c))
+    return dist, idx.long(), nn
