@@ -51,10 +51,14 @@ size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M);
  *   sums: optional (may be NULL) 2 floats receiving [sum(dist1), sum(dist2)]
  *   (fused reduction for the loss mean / NCCL all-reduce input).
  *   workspace: >= pp_chamfer_fwd_workspace_bytes(B,N,M) bytes, 8-byte aligned.
+ *   flags: 0, or PP_CHAMFER_WS_CLEAN when the first workspace_bytes(B,N,M) bytes are all
+ *   0xff -- true for a buffer filled once with 0xff and since then only ever used by
+ *   successful pp_chamfer_fwd calls on the same stream (each call restores that state).
  */
+#define PP_CHAMFER_WS_CLEAN 1
 int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
                    float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,
-                   void *workspace, size_t workspace_bytes, int device, void *stream);
+                   void *workspace, size_t workspace_bytes, int flags, int device, void *stream);
 
 /*
  * Labeled Chamfer forward.  Replaces losses.labeled_nmdistance_forward

@@ -20,7 +20,7 @@ SIGNATURES = {
     "pp_version": (_i, []),
     "pp_last_error_string": (ctypes.c_char_p, []),
     "pp_chamfer_fwd_workspace_bytes": (_sz, [_i, _i, _i]),
-    "pp_chamfer_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "pp_chamfer_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "pp_chamfer_labeled_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "pp_chamfer_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_fps": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
@@ -37,6 +37,7 @@ SIGNATURES = {
 }
 
 LIB_PATH = _build.LIB_PATH
+PP_CHAMFER_WS_CLEAN = 1
 
 
 def _load():

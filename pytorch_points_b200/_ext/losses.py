@@ -10,14 +10,17 @@ _workspaces = {}
 
 
 def _workspace(device, nbytes):
-    """Per-device scratch buffer, grown on demand (the packed (distance, granule) keys of the
-    one-pass Chamfer kernel).  Stream-ordered reuse: callers on one stream never overlap."""
+    """Persistent per-(device, stream) scratch for the packed (distance, granule) keys of the
+    one-pass Chamfer kernel.  It is filled with 0xff once; every successful forward call leaves
+    it in that state again (the finalize kernel resets the keys it consumed), so steady-state
+    calls pass PP_CHAMFER_WS_CLEAN and skip the fill.  Stream-ordered reuse: calls on one stream
+    never overlap."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        buf = torch.full((max(nbytes, 1 << 20),), 0xFF, dtype=torch.uint8, device=device)
         _workspaces[key] = buf
-    return buf
+    return key, buf
 
 
 def _check_f32(*ts):
@@ -40,11 +43,13 @@ def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None):
     if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
         raise RuntimeError("nmdistance_forward: idx tensors must be int32")
     nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
-    ws = _workspace(dev, nbytes)
+    key, ws = _workspace(dev, nbytes)
     with torch.cuda.device(dev):
         rc = _C.lib.pp_chamfer_fwd(_C.ptr(xyz1), _C.ptr(xyz2), B, N, M, c, _C.ptr(dist1), _C.ptr(dist2),
                                    _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums), _C.ptr(ws), ws.numel(),
-                                   dev.index, _C.stream_of(dev))
+                                   _C.PP_CHAMFER_WS_CLEAN, dev.index, _C.stream_of(dev))
+    if rc != 0:
+        _workspaces.pop(key, None)  # state unknown after a failure: start from a fresh fill
     _C.check(rc, "pp_chamfer_fwd")
     return 1
 

@@ -6,45 +6,70 @@
 //  * ONE pass over the B*N*M unique point pairs feeds both directions: d(i,j) is
 //    bit-identical either way round ((a-b) = -(b-a) exactly, squares drop the sign), so the
 //    reference's second launch is redundant arithmetic.
-//  * Each thread keeps Q query points of cloud 1 in registers and streams cloud 2 through a
-//    shared-memory SoA tile, four reference points per LDS.128 broadcast.  Distances are
-//    evaluated two at a time with the packed FADD2/FMUL2/FFMA2 pipe in the reference's exact
-//    rounding order; running minima use FMNMX3.
-//  * Hot loop tracks minima VALUES only.  Indices are recovered lazily:
-//      - row side (dist1/idx1): per query remember the 32-reference granule in which the
-//        running min last strictly improved (= lowest granule holding the final min);
-//      - column side (dist2/idx2): per reference, a warp-wide REDUX.MIN of the per-lane column
-//        minimum is compared with a shared-memory filter of the best value seen so far; only
-//        when it may improve does one lane push (value, query-group) with a 64-bit atomicMin.
-//    A tiny finalize kernel re-evaluates the <=32 (row) / <=Q (column) candidates of the
-//    recorded granule and picks the first exact match -> lowest index on ties, as the reference.
+//  * A CTA keeps a block of RB cloud-2 points ("references") resident in shared memory (SoA)
+//    together with their running column state, and sweeps tiles of cloud-1 points ("queries")
+//    past them: each thread holds Q queries in registers and reads four references per
+//    LDS.128 broadcast.  Distances are evaluated two at a time on the packed
+//    FADD2/FMUL2/FFMA2 pipe in the reference's exact rounding order; minima use FMNMX3.
+//  * The hot loop tracks minima VALUES only.  Indices are recovered lazily:
+//      - row side (dist1/idx1): per query, the 32-reference granule in which the running
+//        min last strictly improved (= lowest granule holding the final min) -> one
+//        64-bit RED.MIN of (value, granule) per query and reference block;
+//      - column side (dist2/idx2): per reference, a warp-wide REDUX.MIN of the per-lane
+//        column minimum is compared with a shared-memory filter (best value seen so far
+//        by this CTA, seeded from what earlier CTAs published); only when it may improve
+//        does one lane push (value, query-group) into the CTA's shared key array.
+//    A small finalize kernel re-evaluates the <=32 (row) / <=Q (column) candidates of the
+//    recorded granule and picks the first exact match -> lowest index on ties, like the
+//    reference's strict '<' scan.
 //  * Keys are (float bits << 32 | granule): distances are >= +0 so their bit patterns order
-//    like unsigned integers, and atomicMin over the packed key resolves ties to the lower
+//    like unsigned integers, and a min over the packed key resolves ties to the lower
 //    granule for free.
+//  * Query splits ride the slowest grid dimension, so CTAs of split s start after the CTAs
+//    of split s-1 have published their keys: the column filter starts tight.
 #include "pp_common.cuh"
 
 namespace pp {
 namespace {
 
-constexpr int CH_TILE = 128;  // reference points per shared-memory tile
-constexpr int CH_GR = 32;     // row-side index granule (references)
+constexpr int CH_GR = 32;  // row-side index granule (references)
 constexpr unsigned long long KEY_INIT = 0xffffffffffffffffull;
 
-template <int Q, int THREADS>
+// The leader lane publishes (value, group) to the CTA's shared key and tightens the shared
+// filter.  Predicated PTX: only one lane acts, nobody branches.
+__device__ __forceinline__ void publish_column_min(int lane, int leader, unsigned long long *skey,
+                                                   unsigned long long key, unsigned *filt,
+                                                   unsigned value) {
+    const unsigned kaddr = (unsigned)__cvta_generic_to_shared(skey);
+    const unsigned faddr = (unsigned)__cvta_generic_to_shared(filt);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.eq.s32 p, %0, %1;\n\t"
+        "@p red.shared.min.u64 [%2], %3;\n\t"
+        "@p red.shared.min.u32 [%4], %5;\n\t"
+        "}"
+        :
+        : "r"(lane), "r"(leader), "r"(kaddr), "l"(key), "r"(faddr), "r"(value)
+        : "memory");
+}
+
+template <int Q, int THREADS, int RB>
 __global__ void __launch_bounds__(THREADS)
 chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int N, int M,
                    unsigned long long *__restrict__ key1, unsigned long long *__restrict__ key2,
-                   int refs_per_block) {
-    __shared__ __align__(16) float sX[CH_TILE];
-    __shared__ __align__(16) float sY[CH_TILE];
-    __shared__ __align__(16) float sZ[CH_TILE];
-    __shared__ __align__(16) unsigned sW[CH_TILE];  // filter: best column value seen (bits)
+                   int queries_per_split) {
+    __shared__ __align__(16) float sX[RB];
+    __shared__ __align__(16) float sY[RB];
+    __shared__ __align__(16) float sZ[RB];
+    __shared__ __align__(16) unsigned sW[RB];            // filter: best column value seen (bits)
+    __shared__ __align__(16) unsigned long long sK[RB];  // (value, query group) per reference
 
-    const int b = blockIdx.z;
-    const int group = blockIdx.y * THREADS + threadIdx.x;  // query group of this thread
-    const int q0 = group * Q;                               // first query of this thread
-    const int ref_begin = blockIdx.x * refs_per_block;
-    const int ref_end = min(M, ref_begin + refs_per_block);
+    constexpr int TQ = Q * THREADS;
+    const int b = blockIdx.y;
+    const int ref_begin = blockIdx.x * RB;
+    const int q_begin = blockIdx.z * queries_per_split;
+    const int q_end = min(N, q_begin + queries_per_split);
     const int lane = threadIdx.x & 31;
 
     const float *p1 = xyz1 + (size_t)b * N * 3;
@@ -52,48 +77,52 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
     unsigned long long *k1 = key1 + (size_t)b * N;
     unsigned long long *k2 = key2 + (size_t)b * M;
 
-    // Negated query coordinates; queries past N become +inf (distance inf, never a minimum).
-    float nqx[Q], nqy[Q], nqz[Q], best[Q], prev[Q];
-    int granule[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        const int i = q0 + q;
-        float x = PP_INF, y = PP_INF, z = PP_INF;
-        if (i < N) {
-            x = __ldg(p1 + (size_t)i * 3 + 0);
-            y = __ldg(p1 + (size_t)i * 3 + 1);
-            z = __ldg(p1 + (size_t)i * 3 + 2);
+    for (int t = threadIdx.x; t < RB; t += THREADS) {
+        const int j = ref_begin + t;
+        float x = PP_INF, y = PP_INF, z = PP_INF;  // padding: distance inf, never a minimum
+        unsigned w = 0u;                           // padding: the filter can never pass
+        if (j < M) {
+            x = __ldg(p2 + (size_t)j * 3 + 0);
+            y = __ldg(p2 + (size_t)j * 3 + 1);
+            z = __ldg(p2 + (size_t)j * 3 + 2);
+            // upper half of the global key = best value any finished CTA has published
+            w = (unsigned)(__ldcg(k2 + j) >> 32);
         }
-        nqx[q] = -x;
-        nqy[q] = -y;
-        nqz[q] = -z;
-        best[q] = PP_INF;
-        prev[q] = PP_INF;
-        granule[q] = ref_begin / CH_GR;
+        sX[t] = x;
+        sY[t] = y;
+        sZ[t] = z;
+        sW[t] = w;
+        sK[t] = KEY_INIT;
     }
+    __syncthreads();
 
-    for (int tile0 = ref_begin; tile0 < ref_end; tile0 += CH_TILE) {
-        __syncthreads();  // previous tile fully consumed
-        for (int t = threadIdx.x; t < CH_TILE; t += THREADS) {
-            const int j = tile0 + t;
+    for (int qt = q_begin; qt < q_end; qt += TQ) {
+        // thread owns Q consecutive queries; a warp whose queries are all padding sits out
+        const int q0 = qt + threadIdx.x * Q;
+        if (qt + (int)(threadIdx.x & ~31u) * Q >= q_end) continue;
+        const int group = q0 / Q;
+
+        float nqx[Q], nqy[Q], nqz[Q], best[Q], prev[Q];
+        int granule[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int i = q0 + q;
             float x = PP_INF, y = PP_INF, z = PP_INF;
-            unsigned w = 0u;  // padded reference: filter can never pass
-            if (j < ref_end) {
-                x = __ldg(p2 + (size_t)j * 3 + 0);
-                y = __ldg(p2 + (size_t)j * 3 + 1);
-                z = __ldg(p2 + (size_t)j * 3 + 2);
-                // upper 32 bits of the global key = best value any block has published so far
-                w = (unsigned)(__ldcg(k2 + j) >> 32);
+            if (i < q_end) {
+                x = __ldg(p1 + (size_t)i * 3 + 0);
+                y = __ldg(p1 + (size_t)i * 3 + 1);
+                z = __ldg(p1 + (size_t)i * 3 + 2);
             }
-            sX[t] = x;
-            sY[t] = y;
-            sZ[t] = z;
-            sW[t] = w;
+            nqx[q] = -x;  // negated: rn(r + (-q)) == rn(r - q)
+            nqy[q] = -y;
+            nqz[q] = -z;
+            best[q] = PP_INF;
+            prev[q] = PP_INF;
+            granule[q] = ref_begin / CH_GR;
         }
-        __syncthreads();
 
 #pragma unroll 1
-        for (int jj = 0; jj < CH_TILE; jj += 4) {
+        for (int jj = 0; jj < RB; jj += 4) {
             const float4 X = *reinterpret_cast<const float4 *>(sX + jj);
             const float4 Y = *reinterpret_cast<const float4 *>(sY + jj);
             const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj);
@@ -120,26 +149,27 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
             const unsigned m1 = __reduce_min_sync(FULL_MASK, __float_as_uint(c1));
             const unsigned m2 = __reduce_min_sync(FULL_MASK, __float_as_uint(c2));
             const unsigned m3 = __reduce_min_sync(FULL_MASK, __float_as_uint(c3));
-            if ((m0 <= W.x) | (m1 <= W.y) | (m2 <= W.z) | (m3 <= W.w)) {
+            // NOTE: the filter words are updated concurrently by other warps and an LDS.128 is
+            // served in several passes, so lanes of ONE load may see different values: the
+            // decision must be made warp-uniform with a vote before any *_sync primitive.
+            if (__any_sync(FULL_MASK, (m0 <= W.x) | (m1 <= W.y) | (m2 <= W.z) | (m3 <= W.w))) {
                 const unsigned mm[4] = {m0, m1, m2, m3};
                 const unsigned ww[4] = {W.x, W.y, W.z, W.w};
                 const float cc[4] = {c0, c1, c2, c3};
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    if (mm[r] <= ww[r]) {
+                    if (__any_sync(FULL_MASK, mm[r] <= ww[r])) {
                         // lowest lane holding the minimum == lowest query group in this warp
                         const unsigned hit = __ballot_sync(FULL_MASK, __float_as_uint(cc[r]) == mm[r]);
-                        if (lane == __ffs(hit) - 1) {
-                            atomicMin(k2 + tile0 + jj + r,
-                                      ((unsigned long long)mm[r] << 32) | (unsigned)group);
-                            atomicMin(sW + jj + r, mm[r]);
-                        }
+                        publish_column_min(lane, __ffs(hit) - 1, sK + jj + r,
+                                           ((unsigned long long)mm[r] << 32) | (unsigned)group,
+                                           sW + jj + r, mm[r]);
                     }
                 }
             }
             // ---- row side: remember the granule of the last strict improvement ----
             if ((jj & (CH_GR - 1)) == CH_GR - 4) {
-                const int g = (tile0 + jj) / CH_GR;
+                const int g = (ref_begin + jj) / CH_GR;
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
                     if (best[q] < prev[q]) {
@@ -149,99 +179,133 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
                 }
             }
         }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int i = q0 + q;
+            if (i < q_end)
+                atomicMin(k1 + i, ((unsigned long long)__float_as_uint(best[q]) << 32) |
+                                      (unsigned)granule[q]);
+        }
     }
 
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        const int i = q0 + q;
-        if (i < N)
-            atomicMin(k1 + i, ((unsigned long long)__float_as_uint(best[q]) << 32) |
-                                  (unsigned)granule[q]);
+    __syncthreads();
+    for (int t = threadIdx.x; t < RB; t += THREADS) {
+        const unsigned long long k = sK[t];
+        if (k != KEY_INIT) atomicMin(k2 + ref_begin + t, k);
     }
 }
 
 // Resolve (value, granule) keys into (dist, idx): re-evaluate the candidates of the granule in
 // ascending index order and take the first whose distance equals the minimum bit for bit.
+// Also restores the key workspace to its all-ones "clean" state for the next call.
+//   rows   : a warp takes 32 queries; for each, its 32 lanes test the 32 references of the
+//            recorded granule at once (coalesced 384-byte read, ballot, find-first-set);
+//   columns: a thread re-evaluates the Q queries of the recorded group, fully unrolled.
 template <int Q>
 __global__ void __launch_bounds__(256)
 chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int B, int N,
-                        int M, const unsigned long long *__restrict__ key1,
-                        const unsigned long long *__restrict__ key2, float *__restrict__ dist1,
+                        int M, unsigned long long *__restrict__ key1,
+                        unsigned long long *__restrict__ key2, float *__restrict__ dist1,
                         float *__restrict__ dist2, int *__restrict__ idx1, int *__restrict__ idx2,
-                        float *__restrict__ sums) {
-    const long long total1 = (long long)B * N, total = total1 + (long long)B * M;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+                        float *__restrict__ sums, int row_blocks) {
+    const int lane = threadIdx.x & 31;
     float s1 = 0.f, s2 = 0.f;
-    if (t < total1) {
-        const int b = (int)(t / N), i = (int)(t % N);
-        const unsigned long long key = key1[t];
-        const unsigned want = (unsigned)(key >> 32);
-        const int g = (int)(unsigned)key;
-        const float *q = xyz1 + ((size_t)b * N + i) * 3;
-        const float qx = q[0], qy = q[1], qz = q[2];
-        const float *r = xyz2 + (size_t)b * M * 3;
-        const int j0 = g * CH_GR, j1 = min(M, j0 + CH_GR);
-        int found = j0;
-        for (int j = j0; j < j1; j++) {
-            const float d = sqdist_xyz(__ldg(r + (size_t)j * 3), __ldg(r + (size_t)j * 3 + 1),
-                                       __ldg(r + (size_t)j * 3 + 2), qx, qy, qz);
-            if (__float_as_uint(d) == want) {
-                found = j;
-                break;
-            }
+    if ((int)blockIdx.x < row_blocks) {
+        // ---- rows: 256 queries per block, 32 per warp, never straddling a cloud's end badly:
+        // t indexes the flattened (B*N) query array; lanes past the end idle.
+        const long long total1 = (long long)B * N;
+        const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+        unsigned want = 0u;
+        int g = 0, b = 0;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        const bool valid = t < total1;
+        if (valid) {
+            const unsigned long long key = key1[t];
+            key1[t] = KEY_INIT;
+            want = (unsigned)(key >> 32);
+            g = (int)(unsigned)key;
+            b = (int)(t / N);
+            const float *q = xyz1 + (size_t)t * 3;
+            qx = q[0]; qy = q[1]; qz = q[2];
         }
-        dist1[t] = __uint_as_float(want);
-        idx1[t] = found;
-        s1 = __uint_as_float(want);
-    } else if (t < total) {
-        const long long u = t - total1;
-        const int b = (int)(u / M), j = (int)(u % M);
-        const unsigned long long key = key2[u];
-        const unsigned want = (unsigned)(key >> 32);
-        const int g = (int)(unsigned)key;
-        const float *r = xyz2 + ((size_t)b * M + j) * 3;
-        const float rx = r[0], ry = r[1], rz = r[2];
-        const float *q = xyz1 + (size_t)b * N * 3;
-        const int i0 = g * Q, i1 = min(N, i0 + Q);
-        int found = i0;
-        for (int i = i0; i < i1; i++) {
-            // same operand roles as the hot loop: (cloud-2 point) - (cloud-1 point)
-            const float d = sqdist_xyz(rx, ry, rz, __ldg(q + (size_t)i * 3), __ldg(q + (size_t)i * 3 + 1),
-                                       __ldg(q + (size_t)i * 3 + 2));
-            if (__float_as_uint(d) == want) {
-                found = i;
-                break;
+        int found = g * CH_GR;
+#pragma unroll 4
+        for (int s = 0; s < 32; s++) {
+            const unsigned w_s = __shfl_sync(FULL_MASK, want, s);
+            const int g_s = __shfl_sync(FULL_MASK, g, s);
+            const int b_s = __shfl_sync(FULL_MASK, b, s);
+            const float x_s = __shfl_sync(FULL_MASK, qx, s);
+            const float y_s = __shfl_sync(FULL_MASK, qy, s);
+            const float z_s = __shfl_sync(FULL_MASK, qz, s);
+            const int j = g_s * CH_GR + lane;
+            bool match = false;
+            if (j < M) {
+                const float *r = xyz2 + ((size_t)b_s * M + j) * 3;
+                const float d = sqdist_xyz(__ldg(r), __ldg(r + 1), __ldg(r + 2), x_s, y_s, z_s);
+                match = __float_as_uint(d) == w_s;
             }
+            const unsigned hit = __ballot_sync(FULL_MASK, match);
+            if (lane == s && hit != 0u) found = g_s * CH_GR + __ffs(hit) - 1;
         }
-        dist2[u] = __uint_as_float(want);
-        idx2[u] = found;
-        s2 = __uint_as_float(want);
+        if (valid) {
+            dist1[t] = __uint_as_float(want);
+            idx1[t] = found;
+            s1 = __uint_as_float(want);
+        }
+    } else {
+        const long long total2 = (long long)B * M;
+        const long long u = (long long)((int)blockIdx.x - row_blocks) * 256 + threadIdx.x;
+        if (u < total2) {
+            const int b = (int)(u / M);
+            const unsigned long long key = key2[u];
+            key2[u] = KEY_INIT;
+            const unsigned want = (unsigned)(key >> 32);
+            const int g = (int)(unsigned)key;
+            const float *r = xyz2 + (size_t)u * 3;
+            const float rx = r[0], ry = r[1], rz = r[2];
+            const float *q = xyz1 + (size_t)b * N * 3;
+            const int i0 = g * Q;
+            int found = i0;
+#pragma unroll
+            for (int e = Q - 1; e >= 0; e--) {  // descending so the lowest match wins
+                const int i = i0 + e;
+                if (i < N) {
+                    // same operand roles as the hot loop: (cloud-2 point) - (cloud-1 point)
+                    const float d = sqdist_xyz(rx, ry, rz, __ldg(q + (size_t)i * 3), __ldg(q + (size_t)i * 3 + 1),
+                                               __ldg(q + (size_t)i * 3 + 2));
+                    if (__float_as_uint(d) == want) found = i;
+                }
+            }
+            dist2[u] = __uint_as_float(want);
+            idx2[u] = found;
+            s2 = __uint_as_float(want);
+        }
     }
     if (sums != nullptr) {
-        // fused loss partial sums: warp shuffle -> shared -> one atomicAdd pair per block
+        // fused loss partial sums: warp shuffle -> shared -> one atomicAdd per block
         __shared__ float sh1[8], sh2[8];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(FULL_MASK, s1, o);
             s2 += __shfl_xor_sync(FULL_MASK, s2, o);
         }
-        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-        if (l == 0) {
+        const int w = threadIdx.x >> 5;
+        if (lane == 0) {
             sh1[w] = s1;
             sh2[w] = s2;
         }
         __syncthreads();
         if (w == 0) {
-            s1 = l < 8 ? sh1[l] : 0.f;
-            s2 = l < 8 ? sh2[l] : 0.f;
+            s1 = lane < 8 ? sh1[lane] : 0.f;
+            s2 = lane < 8 ? sh2[lane] : 0.f;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) {
                 s1 += __shfl_xor_sync(FULL_MASK, s1, o);
                 s2 += __shfl_xor_sync(FULL_MASK, s2, o);
             }
-            if (l == 0) {
-                if (s1 != 0.f) atomicAdd(sums + 0, s1);
-                if (s2 != 0.f) atomicAdd(sums + 1, s2);
+            if (lane == 0) {
+                if ((int)blockIdx.x < row_blocks) atomicAdd(sums + 0, s1);
+                else atomicAdd(sums + 1, s2);
             }
         }
     }
@@ -369,27 +433,30 @@ extern "C" size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M) {
     return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M);
 }
 
-template <int Q, int THREADS>
+template <int Q, int THREADS, int RB>
 static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                               unsigned long long *key1, unsigned long long *key2, float *dist1,
                               float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st) {
-    const int qtiles = ceil_div(N, Q * THREADS);
-    // enough blocks for ~8 per SM, each covering a whole number of tiles
-    const long long want_blocks = (long long)NUM_SMS_B200 * get_option("chamfer_blocks_per_sm", 8);
-    int splits = (int)ceil_div_ll(want_blocks, (long long)B * qtiles);
-    const int max_splits = ceil_div(M, CH_TILE);
+    constexpr int TQ = Q * THREADS;
+    const int ref_blocks = ceil_div(M, RB);
+    // Query splits: enough CTAs for several waves (tail effect), but as few as possible so
+    // that every CTA sweeps many query tiles past its resident references (filter depth).
+    const long long want_blocks = (long long)NUM_SMS_B200 * get_option("chamfer_blocks_per_sm", 24);
+    int splits = (int)ceil_div_ll(want_blocks, (long long)B * ref_blocks);
+    const int max_splits = ceil_div(N, TQ);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
-    const int refs_per_block = ceil_div(ceil_div(M, splits), CH_TILE) * CH_TILE;
-    splits = ceil_div(M, refs_per_block);
-    PP_REQUIRE(qtiles <= 65535 && B <= 65535, "chamfer: grid too large (N=%d B=%d)", N, B);
-    dim3 grid(splits, qtiles, B);
-    chamfer_fwd_kernel<Q, THREADS><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
-                                                           refs_per_block);
+    const int queries_per_split = ceil_div(ceil_div(N, splits), TQ) * TQ;
+    splits = ceil_div(N, queries_per_split);
+    PP_REQUIRE(B <= 65535 && splits <= 65535, "chamfer: grid too large (B=%d)", B);
+    dim3 grid(ref_blocks, B, splits);
+    chamfer_fwd_kernel<Q, THREADS, RB><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
+                                                               queries_per_split);
     PP_LAUNCH_CHECK();
-    const long long total = (long long)B * N + (long long)B * M;
-    chamfer_finalize_kernel<Q><<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(
-        xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums);
+    const int row_blocks = (int)ceil_div_ll((long long)B * N, 256);
+    const int col_blocks = (int)ceil_div_ll((long long)B * M, 256);
+    chamfer_finalize_kernel<Q><<<row_blocks + col_blocks, 256, 0, st>>>(
+        xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks);
     PP_LAUNCH_CHECK();
     return PP_OK;
 }
@@ -421,12 +488,14 @@ static int launch_generic(bool labeled, const float *xyz1, const float *xyz2, co
 
 extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
                               float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,
-                              void *workspace, size_t workspace_bytes, int device, void *stream) {
+                              void *workspace, size_t workspace_bytes, int flags, int device,
+                              void *stream) {
     PP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && c >= 1, "chamfer_fwd: bad sizes B=%d N=%d M=%d c=%d", B, N, M, c);
     PP_REQUIRE((long long)B * N * c < (1ll << 31) && (long long)B * M * c < (1ll << 31),
                "chamfer_fwd: B*N*c must fit int32 indexing like the reference");
     if (B == 0 || (N == 0 && M == 0)) return PP_OK;
-    PP_REQUIRE(xyz1 && xyz2 && dist1 && dist2 && idx1 && idx2, "chamfer_fwd: null pointer");
+    // empty tensors legitimately carry null data pointers
+    PP_REQUIRE((N == 0 || (xyz1 && dist1 && idx1)) && (M == 0 || (xyz2 && dist2 && idx2)), "chamfer_fwd: null pointer");
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
     cudaStream_t st = (cudaStream_t)stream;
@@ -449,20 +518,21 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     }
     unsigned long long *key1 = (unsigned long long *)workspace;
     unsigned long long *key2 = key1 + (size_t)B * N;
-    PP_CUDA(cudaMemsetAsync(workspace, 0xff, need, st));
-    // query-tile shape: keep padding waste low for small clouds, more reuse for large ones
-    const int variant = get_option("chamfer_variant", 0);
-    int pick = variant;
-    if (pick == 0) pick = (N <= 4096) ? 1 : 2;
+    // The finalize kernel leaves the keys all-ones again; callers that own a persistent
+    // workspace say so with PP_CHAMFER_WS_CLEAN and save the fill.
+    if (!(flags & PP_CHAMFER_WS_CLEAN)) PP_CUDA(cudaMemsetAsync(workspace, 0xff, need, st));
+    int pick = get_option("chamfer_variant", 0);
+    if (pick == 0) pick = 1;
     switch (pick) {
-        case 1: return launch_chamfer_fwd<8, 64>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 2: return launch_chamfer_fwd<8, 128>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 3: return launch_chamfer_fwd<4, 128>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 4: return launch_chamfer_fwd<16, 64>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 5: return launch_chamfer_fwd<16, 128>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 1: return launch_chamfer_fwd<8, 128, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 2: return launch_chamfer_fwd<8, 128, 128>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 3: return launch_chamfer_fwd<8, 64, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 4: return launch_chamfer_fwd<16, 128, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 5: return launch_chamfer_fwd<4, 128, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 6: return launch_chamfer_fwd<8, 256, 512>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         default: break;
     }
-    set_error("chamfer_fwd: unknown variant %d", variant);
+    set_error("chamfer_fwd: unknown variant %d", pick);
     return PP_EINVAL;
 }
 
@@ -472,7 +542,7 @@ extern "C" int pp_chamfer_labeled_fwd(const float *xyz1, const float *xyz2, cons
                                       void *stream) {
     PP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && c >= 1, "chamfer_labeled_fwd: bad sizes");
     if (B == 0 || (N == 0 && M == 0)) return PP_OK;
-    PP_REQUIRE(xyz1 && xyz2 && label1 && label2 && dist1 && dist2 && idx1 && idx2, "chamfer_labeled_fwd: null pointer");
+    PP_REQUIRE((N == 0 || (xyz1 && label1 && dist1 && idx1)) && (M == 0 || (xyz2 && label2 && dist2 && idx2)), "chamfer_labeled_fwd: null pointer");
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
     cudaStream_t st = (cudaStream_t)stream;
@@ -490,7 +560,7 @@ extern "C" int pp_chamfer_bwd(const float *xyz1, const float *xyz2, const float 
                               void *stream) {
     PP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && c >= 1, "chamfer_bwd: bad sizes");
     if (B == 0 || (N == 0 && M == 0)) return PP_OK;
-    PP_REQUIRE(xyz1 && xyz2 && graddist1 && graddist2 && idx1 && idx2 && gradxyz1 && gradxyz2, "chamfer_bwd: null pointer");
+    PP_REQUIRE((N == 0 || (xyz1 && graddist1 && idx1 && gradxyz1)) && (M == 0 || (xyz2 && graddist2 && idx2 && gradxyz2)), "chamfer_bwd: null pointer");
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
     cudaStream_t st = (cudaStream_t)stream;

@@ -47,7 +47,7 @@ CHAMFER_CASES = [
     (4, 2500, 2500, uniform_cloud, 7),       # config 2 shape, smaller batch
     (2, 1000, 3000, sphere_cloud, 8),
     (2, 2048, 2048, lattice_cloud, 9),       # massive exact ties
-    (1, 4097, 4099, uniform_cloud, 10),      # crosses the N<=4096 variant switch
+    (1, 4097, 4099, uniform_cloud, 10),
 ]
 
 
@@ -63,7 +63,7 @@ def test_chamfer_forward_bit_exact(pp, oracle_mod, B, N, M, maker, seed):
     assert np.array_equal(np32(d2).view(np.uint32), e2.view(np.uint32)), "dist2 bits"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_chamfer_forward_all_variants(pp, oracle_mod, variant):
     from pytorch_points_b200 import _C
     a = with_duplicates(uniform_cloud(2, 1500, 11))

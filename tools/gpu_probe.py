@@ -60,14 +60,14 @@ ch = {}
 for (B, N) in [(32, 2500), (32, 8192)]:
     a, b = uniform_cloud(B, N, 1).cuda(), uniform_cloud(B, N, 2).cuda()
     bufs = chamfer_bufs(B, N, N)
-    for variant in [1, 2, 3, 4, 5]:
-        for bps in [4, 8, 16]:
+    for variant in [1, 2, 3, 4, 5, 6]:
+        for bps in [8, 24, 48]:
             _C.set_option("chamfer_variant", variant)
             _C.set_option("chamfer_blocks_per_sm", bps)
             med, mn = timeit(lambda: losses.nmdistance_forward(a, b, *bufs))
             ch["B%d_N%d_v%d_bps%d" % (B, N, variant, bps)] = {"ms": med, "min_ms": mn, "pairs_per_s": B * N * N / (med * 1e-3)}
     _C.set_option("chamfer_variant", 0)
-    _C.set_option("chamfer_blocks_per_sm", 8)
+    _C.set_option("chamfer_blocks_per_sm", 24)
     gd1, gd2 = torch.rand(B, N, device="cuda"), torch.rand(B, N, device="cuda")
     g1, g2 = torch.empty_like(a), torch.empty_like(b)
     med, mn = timeit(lambda: losses.nmdistance_backward(a, b, g1, g2, gd1, gd2, bufs[2], bufs[3]))
