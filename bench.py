@@ -1,0 +1,460 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pytorch_points hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Default workload = BASELINE.json configs[1]: Chamfer distance fwd+bwd, B=32 clouds per GPU,
+N=M=2500 points (AtlasNet training shape), metric = unique point-pairs/s (B*N*M per step,
+whole job).  One "step" = nndistance forward (both directions + fused loss partial sums),
+the NCCL all-reduce of the two partial sums when N>1, and the backward scatter.
+
+Legs printed in ONE JSON line by rank 0:
+  value     device-resident: inputs already in HBM, C-ABI calls on the current stream;
+  e2e       through the public API (autograd Function `nndistance` + sharded mean loss) with
+            pinned HOST buffers copied in every step and the loss read back every step;
+  roofline  dominant kernel (chamfer_fwd_kernel), duration from CUDA events on the launching
+            stream (library timing hooks), against the FP32 pipe peak measured live;
+  cpu_baseline  the CPU oracle port (oracle/pp_oracle.c, OpenMP) on the box's host cores;
+  extras    (N=1 only) the other BASELINE.json configs: Chamfer B=32 N=M=8192, FPS
+            16384->1024 + ball_query (B=16), group_knn k=16 (B=32 N=8192; B=4 N=131072).
+`--impl reference` times the reference's CPU-side equivalent: the reference has NO CPU
+implementation of this path, so the oracle port stands in (kind "port").
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (kind, per-GPU batch, N, M)
+    "chamfer_b32_n2500": ("chamfer", 32, 2500, 2500),     # BASELINE.json configs[1]
+    "chamfer_b32_n8192": ("chamfer", 32, 8192, 8192),     # north-star target shape
+    "chamfer_b256_n8192": ("chamfer", 256, 8192, 8192),   # configs[4] at 1 GPU (batch is sharded /W)
+}
+L2_FLUSH_BYTES = 256 << 20
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:  # noqa: BLE001
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_chamfer_step(a, b, total_batch):
+    """One fwd+bwd pass of the oracle port over numpy clouds; returns the loss."""
+    import numpy as np
+    import oracle
+    d1, d2, i1, i2 = oracle.chamfer_fwd(a, b)
+    B, N = d1.shape
+    M = d2.shape[1]
+    gd1 = np.full((B, N), 1.0 / (total_batch * N), np.float32)
+    gd2 = np.full((B, M), 1.0 / (total_batch * M), np.float32)
+    oracle.chamfer_bwd(a, b, gd1, gd2, i1, i2)
+    return float(d1.sum() / (total_batch * N) + d2.sum() / (total_batch * M))
+
+
+def run_cpu_baseline(N, M, budget_s=12.0):
+    """Oracle port on the host cores over a bounded sample of the workload."""
+    import numpy as np
+    from helpers import np32, uniform_cloud
+    import oracle
+    oracle.lib()
+    a1, b1 = np32(uniform_cloud(1, N, 1001)), np32(uniform_cloud(1, M, 2001))
+    cpu_chamfer_step(a1, b1, 1)  # warm up threads
+    t0 = time.perf_counter()
+    cpu_chamfer_step(a1, b1, 1)
+    t1 = max(time.perf_counter() - t0, 1e-4)
+    bs = int(max(1, min(32, budget_s / 3 / t1)))
+    a, b = np32(uniform_cloud(bs, N, 1001)), np32(uniform_cloud(bs, M, 2001))
+    best = None
+    t_start = time.perf_counter()
+    reps = 0
+    while reps < 3 or (time.perf_counter() - t_start < budget_s and reps < 50):
+        t0 = time.perf_counter()
+        cpu_chamfer_step(a, b, bs)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        reps += 1
+    return {"value": bs * N * M / best, "unit": "point-pairs/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle port (C + OpenMP, all host threads), Chamfer fwd+bwd on %d of the clouds, "
+                      "N=M=%d, best of %d runs (%.2f s each)" % (bs, N, reps, best)}
+
+
+def reference_arm(args, world, rank):
+    """--impl reference: the reference's CPU-side equivalent of the path on the host cores."""
+    kind, B, N, M = WORKLOADS[args.workload]
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+    from helpers import np32, uniform_cloud
+    import oracle
+    oracle.lib()
+    a1, b1 = np32(uniform_cloud(1, N, 1001)), np32(uniform_cloud(1, M, 2001))
+    cpu_chamfer_step(a1, b1, 1)
+    t0 = time.perf_counter()
+    cpu_chamfer_step(a1, b1, 1)
+    t1 = max(time.perf_counter() - t0, 1e-4)
+    budget = 150.0
+    bs = int(max(1, min(B, budget / max(args.steps + args.warmup, 1) / t1)))
+    a, b = np32(uniform_cloud(bs, N, 1001)), np32(uniform_cloud(bs, M, 2001))
+    for _ in range(args.warmup):
+        cpu_chamfer_step(a, b, bs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_chamfer_step(a, b, bs)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = bs * N * M / dt
+    sample = ("each step = oracle port (C + OpenMP) Chamfer fwd+bwd over %d of the %d clouds per GPU, "
+              "N=M=%d; the reference has no CPU implementation of this path (SURVEY.md D2)" % (bs, B, N))
+    line = {
+        "impl": "reference", "metric": "chamfer_fwd_bwd_point_pairs_per_s", "value": value,
+        "unit": "point-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: Chamfer fwd+bwd B=%d N=M=%d (CPU sample of %d clouds)" % (args.workload, B, N, bs)},
+        "cpu_baseline": {"value": value, "unit": "point-pairs/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "point-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="chamfer_b32_n2500", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        reference_arm(args, world, rank)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this benchmark has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    from helpers import uniform_cloud
+    from pytorch_points_b200 import _C
+    from pytorch_points_b200._ext import losses
+    from pytorch_points_b200.dist import sharded_chamfer_loss
+
+    kind, B, N, M = WORKLOADS[args.workload]
+    if args.workload == "chamfer_b256_n8192":
+        B = B // world           # configs[4]: the batch of 256 is sharded
+        scaling = "strong"
+    else:
+        scaling = "weak"         # fixed per-GPU batch
+    total_B = B * world
+    pairs_per_step = float(total_B) * N * M
+
+    # ---- inputs: seeded on CPU (identical bits on every path), one shard per rank
+    a_host = uniform_cloud(B, N, 1001 + rank).pin_memory()
+    b_host = uniform_cloud(B, M, 2001 + rank).pin_memory()
+    a, b = a_host.to(dev), b_host.to(dev)
+    d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, M, device=dev)
+    i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
+    sums = torch.zeros(2, device=dev)
+    gd1 = torch.full((B, N), 1.0 / (total_B * N), device=dev)
+    gd2 = torch.full((B, M), 1.0 / (total_B * M), device=dev)
+    g1, g2 = torch.empty_like(a), torch.empty_like(b)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
+        if world > 1:
+            dist.all_reduce(sums)
+        losses.nmdistance_backward(a, b, g1, g2, gd1, gd2, i1, i2)
+
+    def step_e2e():
+        x = a_host.to(dev, non_blocking=True).requires_grad_(True)
+        y = b_host.to(dev, non_blocking=True).requires_grad_(True)
+        loss = sharded_chamfer_loss(x, y, total_batch=total_B)
+        loss.backward()
+        return loss.item()  # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, steps, warmup):
+        for _ in range(warmup):
+            step()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()  # evict L2 between timed iterations (inputs are smaller than L2)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        total_ms = sum(x.elapsed_time(y) for x, y in evs)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms / steps
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _C.set_option("timing", 1)
+    for nm in ("chamfer_fwd", "chamfer_finalize", "chamfer_bwd"):
+        _C.timing_collect(nm)
+    ms_step = timed(step_device, args.steps, args.warmup)
+    kt = {nm: _C.timing_collect(nm) for nm in ("chamfer_fwd", "chamfer_finalize", "chamfer_bwd")}
+    _C.set_option("timing", 0)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop()
+    loss_dev = float((sums[0] / (total_B * N) + sums[1] / (total_B * M)).item())
+    loss_e2e = step_e2e()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel: chamfer_fwd_kernel, FP32 pipe bound
+    n_all = args.steps + args.warmup
+    fwd_ms = kt["chamfer_fwd"][0] / max(kt["chamfer_fwd"][1], 1)
+    flops_per_launch = 8.0 * B * N * M            # 8 FLOP per unique pair
+    ffma_ms, ffma_flop = _C.microbench(0, 4096, local_rank)
+    mix_ms, mix_pairs = _C.microbench(3, 2048, local_rank)
+    peak_tflops = ffma_flop / (ffma_ms * 1e-3) / 1e12
+    pipe_pairs = mix_pairs / (mix_ms * 1e-3)
+    achieved = flops_per_launch / (fwd_ms * 1e-3) / 1e12
+    traffic = None
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+        traffic = summ.get(args.workload, {}).get("chamfer_fwd_dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {
+        "kernel": "chamfer_fwd_kernel", "bound": "fp32", "achieved": achieved, "peak": peak_tflops,
+        "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
+        "peak_source": "FFMA peak measured live by pp_microbench (MEASURED_PEAKS.json holds no FP32 entry)",
+        "kernel_ms": fwd_ms, "kernel_launches_timed": kt["chamfer_fwd"][1],
+        "algorithmic_flop_per_launch": flops_per_launch,
+        "pair_rate": B * N * M / (fwd_ms * 1e-3),
+        "op_mix_ceiling_pairs_per_s": pipe_pairs,
+        "frac_of_op_mix_ceiling": B * N * M / (fwd_ms * 1e-3) / pipe_pairs,
+        "note": "the reference rounding order needs 6 FP32 lane-ops per pair (3 sub, 1 mul, 2 fma = 8 FLOP in "
+                "12 FLOP slots), so 0.667 of the FFMA peak is the hard ceiling; op_mix_ceiling is that bound "
+                "measured live with the packed FADD2/FMUL2/FFMA2+FMNMX3 mix",
+        "other_kernels_ms": {"chamfer_finalize": kt["chamfer_finalize"][0] / max(kt["chamfer_finalize"][1], 1),
+                             "chamfer_bwd(2 launches)": kt["chamfer_bwd"][0] / max(kt["chamfer_bwd"][1], 1)},
+    }
+
+    line = {
+        "metric": "chamfer_fwd_bwd_point_pairs_per_s", "value": pairs_per_step / (ms_step * 1e-3),
+        "unit": "point-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: Chamfer (nndistance) fwd+bwd, B=%d clouds per GPU, N=M=%d, uniform [0,1)^3, "
+                               "loss = mean(dist1)+mean(dist2)%s" % (
+                                   args.workload, B, N, ", NCCL all-reduce of the 2 partial sums" if world > 1 else ""),
+                   "global_batch": total_B, "l2": "flushed between timed steps (256 MiB write); inputs 1.9 MB < L2",
+                   "timing": "per-step CUDA events on the current stream, max over ranks"},
+        "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3), "unit": "point-pairs/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": world * (a_host.numel() + b_host.numel()) * 4, "d2h_bytes_per_step": world * 4,
+                "api": "pytorch_points_b200.network.nndistance (autograd) + dist.sharded_chamfer_loss, pinned host inputs"},
+        "gpu_launches": 4 * args.steps,
+        "gpu_launches_note": "per step: chamfer_fwd_kernel, chamfer_finalize_kernel, chamfer_bwd_kernel<0>, <1>",
+        "clocks": clocks, "roofline": roofline,
+        "loss": {"device_leg": loss_dev, "e2e_leg": loss_e2e},
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = run_cpu_baseline(N, M)
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"error": repr(e)}
+    if world == 1 and not args.no_extras:
+        try:
+            line["extras"] = run_extras(dev, _C, peak_tflops, pipe_pairs)
+        except Exception as e:  # noqa: BLE001
+            line["extras"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_extras(dev, _C, peak_tflops, pipe_pairs):
+    """The remaining BASELINE.json configs and north-star shapes on one GPU (kernel-level)."""
+    import torch
+    from helpers import uniform_cloud
+    from pytorch_points_b200._ext import losses, sampling
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, iters=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    out = {}
+    # Chamfer fwd+bwd at the north-star target shape
+    B, N = 32, 8192
+    a, b = uniform_cloud(B, N, 1).to(dev), uniform_cloud(B, N, 2).to(dev)
+    d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, N, device=dev)
+    i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, N, dtype=torch.int32, device=dev)
+    gd = torch.full((B, N), 1.0 / (B * N), device=dev)
+    g1, g2 = torch.empty_like(a), torch.empty_like(b)
+    sums = torch.zeros(2, device=dev)
+
+    def chamfer_step():
+        losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
+        losses.nmdistance_backward(a, b, g1, g2, gd, gd, i1, i2)
+    _C.set_option("timing", 1)
+    _C.timing_collect("chamfer_fwd")
+    ms = timeit(chamfer_step)
+    tot, cnt = _C.timing_collect("chamfer_fwd")
+    _C.set_option("timing", 0)
+    kms = tot / max(cnt, 1)
+    out["chamfer_fwd_bwd_B32_N8192"] = {
+        "ms_per_step": ms, "point_pairs_per_s": B * N * N / (ms * 1e-3), "fwd_kernel_ms": kms,
+        "fwd_kernel_tflops": 8.0 * B * N * N / (kms * 1e-3) / 1e12,
+        "fwd_kernel_frac_of_fp32_peak": 8.0 * B * N * N / (kms * 1e-3) / 1e12 / peak_tflops,
+        "fwd_kernel_frac_of_op_mix_ceiling": B * N * N / (kms * 1e-3) / pipe_pairs}
+    del a, b, d1, d2, i1, i2, gd, g1, g2
+
+    # config 3: FPS 16384 -> 1024 (+gather) and ball_query r=0.2 nsample=32, B=16
+    B, N, m = 16, 16384, 1024
+    x = uniform_cloud(B, N, 3).to(dev)
+    idx = torch.empty(B, m, dtype=torch.int32, device=dev)
+    temp = torch.empty(B, N, device=dev)
+
+    def fps_step():
+        temp.fill_(1e10)
+        sampling.furthest_sampling(m, 0, x, temp, idx)
+    _C.set_option("timing", 1)
+    _C.timing_collect("fps")
+    ms = timeit(fps_step, iters=5, warm=2)
+    tot, cnt = _C.timing_collect("fps")
+    _C.set_option("timing", 0)
+    kms = tot / max(cnt, 1)
+    alg_bytes = 20.0 * N * (m - 1) * B
+    out["fps_B16_N16384_m1024"] = {
+        "ms_per_step": ms, "samples_per_s": B * m / (ms * 1e-3), "kernel_ms": kms,
+        "us_per_round": kms * 1e3 / (m - 1),
+        "algorithmic_GBps": alg_bytes / (kms * 1e-3) / 1e9,
+        "note": "cloud and running minima are register-resident across a thread-block cluster: no per-round "
+                "memory traffic; algorithmic bytes = 20*N per selected sample (SURVEY.md 8d)"}
+    ctr = torch.gather(x, 1, idx.long().unsqueeze(-1).expand(B, m, 3)).contiguous()
+    ms = timeit(lambda: sampling.ball_query(ctr, x, 0.2, 32))
+    out["ball_query_B16_N16384_M1024_r0.2_ns32"] = {"ms_per_step": ms, "centres_per_s": B * m / (ms * 1e-3),
+                                                     "pair_tests_upper_bound_per_s": B * m * N / (ms * 1e-3)}
+    feats = x.transpose(1, 2).contiguous()
+    gout = torch.empty(B, 3, m, device=dev)
+    ms = timeit(lambda: sampling.gather_forward(B, 3, N, m, feats, idx, gout))
+    out["gather_B16_C3_m1024"] = {"ms_per_step": ms}
+    del x, ctr, feats
+
+    # group_knn k=16: target shape and config 4
+    for (B, N, iters) in [(32, 8192, 5), (4, 131072, 2)]:
+        p = uniform_cloud(B, N, 4).to(dev)
+        _C.set_option("timing", 1)
+        _C.timing_collect("knn")
+        ms = timeit(lambda: sampling.knn(16, p, p), iters=iters, warm=1)
+        tot, cnt = _C.timing_collect("knn")
+        _C.set_option("timing", 0)
+        kms = tot / max(cnt, 1)
+        out["knn_k16_B%d_N%d" % (B, N)] = {
+            "ms_per_step": ms, "point_pairs_per_s": float(B) * N * N / (ms * 1e-3), "kernel_ms": kms,
+            "kernel_tflops": 8.0 * B * N * N / (kms * 1e-3) / 1e12,
+            "kernel_frac_of_fp32_peak": 8.0 * B * N * N / (kms * 1e-3) / 1e12 / peak_tflops,
+            "kernel_frac_of_op_mix_ceiling": float(B) * N * N / (kms * 1e-3) / pipe_pairs}
+        del p
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -162,6 +162,14 @@ int pp_three_nn(const float *unknown, const float *known, int B, int N, int M, f
  */
 int pp_microbench(int which, int iters, float *ms, double *work, int device);
 
+/*
+ * With pp_set_option("timing", 1) every launch of a dominant kernel is bracketed by CUDA
+ * events on the launching stream.  pp_timing_collect(name) waits for the recorded events and
+ * returns their summed duration and count, then forgets them.  Names: "chamfer_fwd",
+ * "chamfer_finalize", "chamfer_bwd", "fps", "ball_query", "knn", "gather_fwd".
+ */
+int pp_timing_collect(const char *name, double *total_ms, int *count);
+
 /* Tuning knob for experiments: selects a kernel variant (0 = default). */
 int pp_set_option(const char *name, int value);
 

@@ -34,6 +34,7 @@ SIGNATURES = {
     "pp_three_nn": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_microbench": (_i, [_i, _i, ctypes.POINTER(_f), ctypes.POINTER(ctypes.c_double), _i]),
     "pp_set_option": (_i, [ctypes.c_char_p, _i]),
+    "pp_timing_collect": (_i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i)]),
 }
 
 LIB_PATH = _build.LIB_PATH
@@ -103,3 +104,12 @@ def microbench(which, iters, device=0):
     work = ctypes.c_double(0)
     check(lib.pp_microbench(int(which), int(iters), ctypes.byref(ms), ctypes.byref(work), int(device)), "pp_microbench")
     return ms.value, work.value
+
+
+def timing_collect(name):
+    """(total_ms, count) of the CUDA-event timings recorded for kernel `name` since the last call
+    (requires set_option("timing", 1))."""
+    total = ctypes.c_double(0)
+    count = _i(0)
+    check(lib.pp_timing_collect(name.encode(), ctypes.byref(total), ctypes.byref(count)), "pp_timing_collect")
+    return total.value, count.value

@@ -450,13 +450,19 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     splits = ceil_div(N, queries_per_split);
     PP_REQUIRE(B <= 65535 && splits <= 65535, "chamfer: grid too large (B=%d)", B);
     dim3 grid(ref_blocks, B, splits);
-    chamfer_fwd_kernel<Q, THREADS, RB><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
-                                                               queries_per_split);
+    {
+        KernelTimer timer("chamfer_fwd", st);
+        chamfer_fwd_kernel<Q, THREADS, RB><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
+                                                                   queries_per_split);
+    }
     PP_LAUNCH_CHECK();
     const int row_blocks = (int)ceil_div_ll((long long)B * N, 256);
     const int col_blocks = (int)ceil_div_ll((long long)B * M, 256);
-    chamfer_finalize_kernel<Q><<<row_blocks + col_blocks, 256, 0, st>>>(
-        xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks);
+    {
+        KernelTimer timer("chamfer_finalize", st);
+        chamfer_finalize_kernel<Q><<<row_blocks + col_blocks, 256, 0, st>>>(
+            xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks);
+    }
     PP_LAUNCH_CHECK();
     return PP_OK;
 }
@@ -571,6 +577,7 @@ extern "C" int pp_chamfer_bwd(const float *xyz1, const float *xyz2, const float 
     }
     const long long total = (long long)B * N + (long long)B * M;
     const unsigned blocks = (unsigned)ceil_div_ll(total, 256);
+    KernelTimer timer("chamfer_bwd", st);
     chamfer_bwd_kernel<0><<<blocks, 256, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, N, M, c, gradxyz1, gradxyz2);
     PP_LAUNCH_CHECK();
     chamfer_bwd_kernel<1><<<blocks, 256, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, N, M, c, gradxyz1, gradxyz2);

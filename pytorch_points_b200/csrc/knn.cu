@@ -229,6 +229,7 @@ extern "C" int pp_knn(const float *query, const float *points, int B, int M, int
     const size_t smem = knn_smem_bytes(k);
     PP_CUDA(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(M, KNN_LISTS), B);
+    KernelTimer timer("knn", st);
     knn_kernel<<<grid, KNN_THREADS, smem, st>>>(query, points, M, N, k, dist, idx);
     PP_LAUNCH_CHECK();
     return PP_OK;

@@ -15,6 +15,18 @@ constexpr int NUM_SMS_B200 = 148;
 void set_error(const char *fmt, ...);
 int get_option(const char *name, int dflt);
 
+// Optional per-kernel timing (option "timing" = 1): CUDA events recorded on the launching
+// stream right around one kernel; read back with pp_timing_collect().  Used by bench.py to
+// measure the dominant kernel's duration without a profiler.
+struct KernelTimer {
+    const char *name;
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr;
+    bool on;
+    KernelTimer(const char *name, cudaStream_t st);
+    ~KernelTimer();
+};
+
 // RAII device switch: every entry point runs on the device the caller names and
 // restores the previous one, so a mismatched "current device" can never send a
 // launch to the wrong GPU (the reference has no device guard).

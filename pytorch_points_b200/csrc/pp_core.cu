@@ -5,6 +5,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "pp_common.cuh"
 
@@ -25,6 +26,29 @@ int get_option(const char *name, int dflt) {
     std::lock_guard<std::mutex> lk(g_opt_mu);
     auto it = g_opts.find(name);
     return it == g_opts.end() ? dflt : it->second;
+}
+
+struct TimingRec {
+    cudaEvent_t e0, e1;
+};
+static std::mutex g_time_mu;
+static std::map<std::string, std::vector<TimingRec>> g_timings;
+
+KernelTimer::KernelTimer(const char *name_, cudaStream_t st_) : name(name_), st(st_) {
+    on = get_option("timing", 0) != 0;
+    if (on) {
+        if (cudaEventCreate(&e0) != cudaSuccess) { on = false; return; }
+        cudaEventRecord(e0, st);
+    }
+}
+
+KernelTimer::~KernelTimer() {
+    if (!on) return;
+    cudaEvent_t e1;
+    if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return; }
+    cudaEventRecord(e1, st);
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    g_timings[name].push_back({e0, e1});
 }
 
 namespace {
@@ -179,6 +203,31 @@ extern "C" int pp_set_option(const char *name, int value) {
     if (!name) return PP_EINVAL;
     std::lock_guard<std::mutex> lk(g_opt_mu);
     g_opts[name] = value;
+    return PP_OK;
+}
+
+extern "C" int pp_timing_collect(const char *name, double *total_ms, int *count) {
+    PP_REQUIRE(name && total_ms && count, "timing_collect: null argument");
+    std::vector<TimingRec> recs;
+    {
+        std::lock_guard<std::mutex> lk(g_time_mu);
+        auto it = g_timings.find(name);
+        if (it != g_timings.end()) {
+            recs.swap(it->second);
+            g_timings.erase(it);
+        }
+    }
+    *total_ms = 0.0;
+    *count = 0;
+    for (auto &r : recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            *total_ms += ms;
+            *count += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
     return PP_OK;
 }
 

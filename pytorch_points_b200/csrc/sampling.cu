@@ -365,6 +365,7 @@ int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    KernelTimer timer("fps", st);
     PP_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, seed, temp, idx, bs_log2));
     return PP_OK;
 }
@@ -405,6 +406,7 @@ extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *te
     }
     const int P = ceil_div(N, C * FPS_T);
     if (P > 16 || get_option("fps_stream", 0)) {
+        KernelTimer timer("fps", st);
         fps_stream_kernel<<<B, 1024, 0, st>>>(xyz, N, m, seed, temp, idx, bs_log2);
         PP_LAUNCH_CHECK();
         return PP_OK;
@@ -428,6 +430,7 @@ extern "C" int pp_gather_fwd(const float *points, const int32_t *idx, int B, int
     PP_REQUIRE(points && idx && out && N > 0, "gather_fwd: null pointer or empty source");
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
+    KernelTimer timer("gather_fwd", (cudaStream_t)stream);
     gather_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(points, idx, C, N, npoint, total, out);
     PP_LAUNCH_CHECK();
     return PP_OK;
@@ -484,6 +487,7 @@ extern "C" int pp_ball_query(const float *new_xyz, const float *xyz, int B, int 
     PP_CUDA(guard.err);
     const float r2 = radius * radius;  // rn(r*r) in fp32 (:354); host float multiply is the same single rounding
     dim3 grid(ceil_div(M, BQ_WARPS), B);
+    KernelTimer timer("ball_query", (cudaStream_t)stream);
     ball_query_kernel<<<grid, BQ_WARPS * 32, 0, (cudaStream_t)stream>>>(new_xyz, xyz, N, M, r2, nsample, idx);
     PP_LAUNCH_CHECK();
     return PP_OK;

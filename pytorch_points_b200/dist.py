@@ -1,0 +1,73 @@
+"""Batch-sharded execution over the GPUs of one box (one process per GPU, torch.distributed).
+
+The reference has no distributed code at all.  Every op on the hot path is
+independent per batch element, so rank r of W simply owns a contiguous slice of the batch and
+runs the kernels on it; outputs stay sharded.  The ONLY collective is the all-reduce (SUM) of
+the two Chamfer partial sums [sum(dist1), sum(dist2)] -- 8 bytes over NVLink -- needed for the
+global loss mean.  Backward needs no collective: d(loss)/d(dist) = 1/(B_total*N) is a constant.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total_batch, rank, world_size):
+    """Contiguous split of the batch dimension; the first (total % world) ranks get one extra."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad rank/world_size %r/%r" % (rank, world_size))
+    base, rem = divmod(total_batch, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_batch(tensor, rank=None, world_size=None):
+    """The slice of `tensor` (batch-first) this rank owns."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    lo, hi = shard_range(tensor.shape[0], rank, world_size)
+    return tensor[lo:hi]
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
+def sharded_chamfer_loss(xyz1, xyz2, total_batch=None, group=None, local_op=None):
+    """Mean Chamfer loss  mean(dist1) + mean(dist2)  over a batch sharded across ranks.
+
+    xyz1 (b_local, N, 3), xyz2 (b_local, M, 3): this rank's clouds.  `total_batch` is the global
+    batch size (defaults to the all-reduced sum of local batch sizes).  Returns a scalar that is
+    identical on every rank; its gradient w.r.t. the local clouds is the local share of the global
+    mean, so `loss.backward()` needs no communication.  `local_op` defaults to the CUDA
+    `nndistance`; tests inject a CPU stand-in to exercise the host logic under gloo."""
+    if local_op is None:
+        from .network.model_loss import nndistance as local_op
+    d1, d2, _, _ = local_op(xyz1, xyz2)
+    world = _world(group)
+    if total_batch is None:
+        tb = torch.tensor([float(xyz1.shape[0])], device=d1.device)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM, group=group)
+        total_batch = int(tb.item())
+    n, m = d1.shape[1], d2.shape[1]
+    sums = torch.stack([d1.sum(), d2.sum()])
+    scale = torch.tensor([1.0 / (total_batch * max(n, 1)), 1.0 / (total_batch * max(m, 1))],
+                         dtype=sums.dtype, device=sums.device)
+    local = (sums * scale).sum()
+    total = sums.detach().clone()
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    global_loss = (total * scale).sum()
+    # value = global mean, gradient = this rank's share of it
+    return local + (global_loss - local).detach()
+
+
+def allreduce_chamfer_sums(sums, group=None):
+    """In-place all-reduce (SUM) of the fused [sum(dist1), sum(dist2)] buffer written by
+    `pp_chamfer_fwd`; the device-resident path bench.py measures."""
+    if _world(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
