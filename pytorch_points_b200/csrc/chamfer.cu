@@ -35,22 +35,24 @@ namespace {
 constexpr int CH_GR = 32;  // row-side index granule (references)
 constexpr unsigned long long KEY_INIT = 0xffffffffffffffffull;
 
-// The leader lane publishes (value, group) to the CTA's shared key and tightens the shared
-// filter.  Predicated PTX: only one lane acts, nobody branches.
-__device__ __forceinline__ void publish_column_min(int lane, int leader, unsigned long long *skey,
+// The leader lane publishes (value, group) to the global key with one fire-and-forget
+// RED.MIN.64 and tightens the CTA's shared filter.  Predicated PTX: only one lane acts, nobody
+// branches.  The filter update is a plain store on purpose: every value ever stored is an
+// observed warp minimum, hence >= the final minimum, so a lost or reordered update can only let
+// a few extra candidates through -- it can never hide one.
+__device__ __forceinline__ void publish_column_min(int lane, int leader, unsigned long long *gkey,
                                                    unsigned long long key, unsigned *filt,
                                                    unsigned value) {
-    const unsigned kaddr = (unsigned)__cvta_generic_to_shared(skey);
     const unsigned faddr = (unsigned)__cvta_generic_to_shared(filt);
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.eq.s32 p, %0, %1;\n\t"
-        "@p red.shared.min.u64 [%2], %3;\n\t"
-        "@p red.shared.min.u32 [%4], %5;\n\t"
+        "@p red.global.min.u64 [%2], %3;\n\t"
+        "@p st.shared.u32 [%4], %5;\n\t"
         "}"
         :
-        : "r"(lane), "r"(leader), "r"(kaddr), "l"(key), "r"(faddr), "r"(value)
+        : "r"(lane), "r"(leader), "l"(gkey), "l"(key), "r"(faddr), "r"(value)
         : "memory");
 }
 
@@ -62,8 +64,7 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
     __shared__ __align__(16) float sX[RB];
     __shared__ __align__(16) float sY[RB];
     __shared__ __align__(16) float sZ[RB];
-    __shared__ __align__(16) unsigned sW[RB];            // filter: best column value seen (bits)
-    __shared__ __align__(16) unsigned long long sK[RB];  // (value, query group) per reference
+    __shared__ __align__(16) unsigned sW[RB];  // filter: best column value seen (bits)
 
     constexpr int TQ = Q * THREADS;
     const int b = blockIdx.y;
@@ -92,14 +93,15 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
         sY[t] = y;
         sZ[t] = z;
         sW[t] = w;
-        sK[t] = KEY_INIT;
     }
     __syncthreads();
 
     for (int qt = q_begin; qt < q_end; qt += TQ) {
         // thread owns Q consecutive queries; a warp whose queries are all padding sits out
         const int q0 = qt + threadIdx.x * Q;
-        if (qt + (int)(threadIdx.x & ~31u) * Q >= q_end) continue;
+        // (the shuffle tells the compiler the test is warp-uniform, so the sweep below keeps
+        //  its loop state in uniform registers)
+        if (__shfl_sync(FULL_MASK, qt + (int)(threadIdx.x & ~31u) * Q, 0) >= q_end) continue;
         const int group = q0 / Q;
 
         float nqx[Q], nqy[Q], nqz[Q], best[Q], prev[Q];
@@ -143,27 +145,28 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
                 c2 = fmin3(c2, a23.x, b23.x);
                 c3 = fmin3(c3, a23.y, b23.y);
             }
-            // ---- column side: warp minimum per reference, filtered publish ----
+            // ---- column side: filtered publish of the warp minimum per reference ----
+            // Fast path: each lane tests its own column minimum against the filter; some lane
+            // passes iff the warp minimum passes.  NOTE: the filter words are updated
+            // concurrently by other warps and an LDS.128 is served in several passes, so lanes
+            // of ONE load may see different values: every decision is made warp-uniform with
+            // a vote before any *_sync primitive.
             const uint4 W = *reinterpret_cast<const uint4 *>(sW + jj);
-            const unsigned m0 = __reduce_min_sync(FULL_MASK, __float_as_uint(c0));
-            const unsigned m1 = __reduce_min_sync(FULL_MASK, __float_as_uint(c1));
-            const unsigned m2 = __reduce_min_sync(FULL_MASK, __float_as_uint(c2));
-            const unsigned m3 = __reduce_min_sync(FULL_MASK, __float_as_uint(c3));
-            // NOTE: the filter words are updated concurrently by other warps and an LDS.128 is
-            // served in several passes, so lanes of ONE load may see different values: the
-            // decision must be made warp-uniform with a vote before any *_sync primitive.
-            if (__any_sync(FULL_MASK, (m0 <= W.x) | (m1 <= W.y) | (m2 <= W.z) | (m3 <= W.w))) {
-                const unsigned mm[4] = {m0, m1, m2, m3};
-                const unsigned ww[4] = {W.x, W.y, W.z, W.w};
+            const bool p0 = __float_as_uint(c0) <= W.x, p1 = __float_as_uint(c1) <= W.y;
+            const bool p2 = __float_as_uint(c2) <= W.z, p3 = __float_as_uint(c3) <= W.w;
+            if (__any_sync(FULL_MASK, p0 | p1 | p2 | p3)) {
+                const bool pp_[4] = {p0, p1, p2, p3};
                 const float cc[4] = {c0, c1, c2, c3};
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
-                    if (__any_sync(FULL_MASK, mm[r] <= ww[r])) {
+                    if (__any_sync(FULL_MASK, pp_[r])) {
+                        const unsigned mine = __float_as_uint(cc[r]);
+                        const unsigned mn = __reduce_min_sync(FULL_MASK, mine);
                         // lowest lane holding the minimum == lowest query group in this warp
-                        const unsigned hit = __ballot_sync(FULL_MASK, __float_as_uint(cc[r]) == mm[r]);
-                        publish_column_min(lane, __ffs(hit) - 1, sK + jj + r,
-                                           ((unsigned long long)mm[r] << 32) | (unsigned)group,
-                                           sW + jj + r, mm[r]);
+                        const unsigned hit = __ballot_sync(FULL_MASK, mine == mn);
+                        publish_column_min(lane, __ffs(hit) - 1, k2 + ref_begin + jj + r,
+                                           ((unsigned long long)mn << 32) | (unsigned)group,
+                                           sW + jj + r, mn);
                     }
                 }
             }
@@ -188,11 +191,6 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
         }
     }
 
-    __syncthreads();
-    for (int t = threadIdx.x; t < RB; t += THREADS) {
-        const unsigned long long k = sK[t];
-        if (k != KEY_INIT) atomicMin(k2 + ref_begin + t, k);
-    }
 }
 
 // Resolve (value, granule) keys into (dist, idx): re-evaluate the candidates of the granule in
@@ -528,7 +526,7 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     // workspace say so with PP_CHAMFER_WS_CLEAN and save the fill.
     if (!(flags & PP_CHAMFER_WS_CLEAN)) PP_CUDA(cudaMemsetAsync(workspace, 0xff, need, st));
     int pick = get_option("chamfer_variant", 0);
-    if (pick == 0) pick = 1;
+    if (pick == 0) pick = (M <= 4096) ? 2 : 1;  // smaller reference blocks keep small clouds spread over all SMs
     switch (pick) {
         case 1: return launch_chamfer_fwd<8, 128, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 2: return launch_chamfer_fwd<8, 128, 128>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);

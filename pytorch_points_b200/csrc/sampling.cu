@@ -349,7 +349,7 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
 
 template <int P, int C>
 int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
-                       int bs_log2, cudaStream_t st) {
+                       int bs_log2, cudaStream_t st, int *max_clusters) {
     const size_t smem = sizeof(float4) * P * FPS_T;
     auto kern = fps_cluster_kernel<P, C>;
     PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -365,6 +365,16 @@ int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (max_clusters) {  // query only: how many such clusters can be co-resident on this GPU
+        if (C == 1) {
+            int per_sm = 0;
+            PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FPS_T, smem));
+            *max_clusters = per_sm * NUM_SMS_B200;
+        } else {
+            PP_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg));
+        }
+        return PP_OK;
+    }
     KernelTimer timer("fps", st);
     PP_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, seed, temp, idx, bs_log2));
     return PP_OK;
@@ -372,12 +382,25 @@ int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *t
 
 template <int C>
 int dispatch_fps_p(int P, const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
-                   int bs_log2, cudaStream_t st) {
-    if (P <= 1) return launch_fps_cluster<1, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
-    if (P <= 2) return launch_fps_cluster<2, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
-    if (P <= 4) return launch_fps_cluster<4, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
-    if (P <= 8) return launch_fps_cluster<8, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
-    return launch_fps_cluster<16, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st);
+                   int bs_log2, cudaStream_t st, int *max_clusters) {
+    if (P <= 1) return launch_fps_cluster<1, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+    if (P <= 2) return launch_fps_cluster<2, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+    if (P <= 4) return launch_fps_cluster<4, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+    if (P <= 8) return launch_fps_cluster<8, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+    return launch_fps_cluster<16, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+}
+
+int dispatch_fps(int C, int P, const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
+                 int bs_log2, cudaStream_t st, int *max_clusters) {
+    switch (C) {
+        case 1: return dispatch_fps_p<1>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+        case 2: return dispatch_fps_p<2>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+        case 4: return dispatch_fps_p<4>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+        case 8: return dispatch_fps_p<8>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+        default: break;
+    }
+    set_error("fps: unsupported cluster width %d", C);
+    return PP_EINVAL;
 }
 
 }  // namespace
@@ -398,11 +421,39 @@ extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *te
     // bs = max(min(2^floor(log2 N), 512), 1)   (_ext/cuda_utils.h:11-16)
     int bs_log2 = 0;
     while ((2 << bs_log2) <= N && bs_log2 < 9) bs_log2++;
-    // cluster width: as wide as the cloud and the machine allow
+    // Cluster width: FPS is a latency chain, so spread each cloud over as many SMs as possible
+    // -- but only as long as ALL clouds' clusters are co-resident (a second wave doubles the
+    // time).  The driver knows how many clusters of each width fit (GPC topology).
     int C = get_option("fps_cluster", 0);
     if (C == 0) {
-        C = 8;
-        while (C > 1 && (N < C * FPS_T || (long long)B * C > 2 * NUM_SMS_B200)) C >>= 1;
+        C = 1;
+        for (int c = 8; c > 1; c >>= 1) {
+            if (N < c * FPS_T) continue;  // not enough points to give every thread one
+            const int p = ceil_div(N, c * FPS_T);
+            if (p > 16) continue;
+            // occupancy answers are cached per (device, width, points-per-thread bucket)
+            static int fit_cache[16][4][17];
+            int pb = p <= 1 ? 1 : p <= 2 ? 2 : p <= 4 ? 4 : p <= 8 ? 8 : 16;
+            int ci = c == 8 ? 3 : c == 4 ? 2 : 1;
+            int &slot = fit_cache[device & 15][ci][pb];
+            if (slot == 0) {
+                int fit = 0;
+                const int rc = dispatch_fps(c, p, xyz, B, N, m, seed, temp, idx, bs_log2, st, &fit);
+                if (rc != PP_OK) return rc;
+                slot = fit + 1;
+            }
+            const int fit = slot - 1;
+            if (get_option("fps_verbose", 0)) fprintf(stderr, "[pp_fps] cluster %d x P %d: %d co-resident\n", c, p, fit);
+            if (fit >= B) {
+                C = c;
+                break;
+            }
+        }
+        if (C == 1 && ceil_div(N, FPS_T) > 16) {
+            // too large for one CTA's registers: take the widest cluster that holds the cloud
+            for (int c = 2; c <= 8; c <<= 1)
+                if (ceil_div(N, c * FPS_T) <= 16) { C = c; break; }
+        }
     }
     const int P = ceil_div(N, C * FPS_T);
     if (P > 16 || get_option("fps_stream", 0)) {
@@ -411,15 +462,7 @@ extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *te
         PP_LAUNCH_CHECK();
         return PP_OK;
     }
-    switch (C) {
-        case 1: return dispatch_fps_p<1>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st);
-        case 2: return dispatch_fps_p<2>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st);
-        case 4: return dispatch_fps_p<4>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st);
-        case 8: return dispatch_fps_p<8>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st);
-        default: break;
-    }
-    set_error("fps: unsupported cluster width %d", C);
-    return PP_EINVAL;
+    return dispatch_fps(C, P, xyz, B, N, m, seed, temp, idx, bs_log2, st, nullptr);
 }
 
 extern "C" int pp_gather_fwd(const float *points, const int32_t *idx, int B, int C, int N, int npoint,
