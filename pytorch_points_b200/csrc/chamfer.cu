@@ -56,8 +56,8 @@ __device__ __forceinline__ void publish_column_min(int lane, int leader, unsigne
         : "memory");
 }
 
-template <int Q, int THREADS, int RB>
-__global__ void __launch_bounds__(THREADS)
+template <int Q, int THREADS, int RB, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int N, int M,
                    unsigned long long *__restrict__ key1, unsigned long long *__restrict__ key2,
                    int queries_per_split) {
@@ -431,7 +431,7 @@ extern "C" size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M) {
     return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M);
 }
 
-template <int Q, int THREADS, int RB>
+template <int Q, int THREADS, int RB, int MINB>
 static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                               unsigned long long *key1, unsigned long long *key2, float *dist1,
                               float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st) {
@@ -450,7 +450,7 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     dim3 grid(ref_blocks, B, splits);
     {
         KernelTimer timer("chamfer_fwd", st);
-        chamfer_fwd_kernel<Q, THREADS, RB><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
+        chamfer_fwd_kernel<Q, THREADS, RB, MINB><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
                                                                    queries_per_split);
     }
     PP_LAUNCH_CHECK();
@@ -528,12 +528,18 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     int pick = get_option("chamfer_variant", 0);
     if (pick == 0) pick = (M <= 4096) ? 2 : 1;  // smaller reference blocks keep small clouds spread over all SMs
     switch (pick) {
-        case 1: return launch_chamfer_fwd<8, 128, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 2: return launch_chamfer_fwd<8, 128, 128>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 3: return launch_chamfer_fwd<8, 64, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 4: return launch_chamfer_fwd<16, 128, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 5: return launch_chamfer_fwd<4, 128, 256>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 6: return launch_chamfer_fwd<8, 256, 512>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 1: return launch_chamfer_fwd<8, 128, 256, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 2: return launch_chamfer_fwd<8, 128, 128, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 3: return launch_chamfer_fwd<8, 64, 256, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 4: return launch_chamfer_fwd<16, 128, 256, 3>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 5: return launch_chamfer_fwd<4, 128, 256, 8>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 6: return launch_chamfer_fwd<8, 256, 512, 2>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 7: return launch_chamfer_fwd<8, 128, 256, 6>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 8: return launch_chamfer_fwd<8, 128, 256, 7>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 9: return launch_chamfer_fwd<8, 128, 256, 8>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 10: return launch_chamfer_fwd<8, 128, 128, 6>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 11: return launch_chamfer_fwd<8, 256, 256, 3>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 12: return launch_chamfer_fwd<4, 128, 256, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         default: break;
     }
     set_error("chamfer_fwd: unknown variant %d", pick);
