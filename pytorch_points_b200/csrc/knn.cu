@@ -160,6 +160,161 @@ knn_kernel(const float *__restrict__ query, const float *__restrict__ points, in
     }
 }
 
+// ---------------------------------------------------------------------------
+// Register-list kernel (k <= 32): the k best (distance, index) pairs of each query live in
+// REGISTERS, sorted ascending.  Candidates found by the hot loop are parked in a small
+// per-thread shared-memory buffer; when any lane of the warp is about to run out of buffer the
+// whole warp drains its buffers in lock-step: every drain pass pushes one buffered candidate
+// per lane (or +inf for lanes that have none) through a branch-free compare-exchange chain
+// over the K slots, so the selection work is shared by all 32 lanes instead of diverging.
+// ---------------------------------------------------------------------------
+constexpr int KR_THREADS = 128;
+constexpr int KR_TILE = 256;
+constexpr int KR_CB = 8;  // buffered candidates per query
+
+template <int K>
+__device__ __forceinline__ void knn_insert(float (&ld)[K], int (&li)[K], float d, int j) {
+    // (d, j) enters at the first slot whose distance is strictly larger; everything after it
+    // shifts down one slot; the former last entry falls out.  Strict '<' keeps the earlier
+    // (lower) index in front on equal distances, because candidates arrive in ascending index.
+    // The list is sorted, so (d0 < ld[s]) is false..false,true..true: from the first true on,
+    // every slot takes its predecessor (a pure shift, which keeps equal distances in order).
+    const float d0 = d;
+#pragma unroll
+    for (int s = 0; s < K; s++) {
+        const float td = ld[s];
+        const int ti = li[s];
+        const bool sw = d0 < td;
+        ld[s] = sw ? d : td;
+        li[s] = sw ? j : ti;
+        d = sw ? td : d;
+        j = sw ? ti : j;
+    }
+}
+
+template <int K, int Q>
+__global__ void __launch_bounds__(KR_THREADS)
+knn_reg_kernel(const float *__restrict__ query, const float *__restrict__ points, int M, int N, int k,
+               float *__restrict__ dist, int *__restrict__ idx) {
+    __shared__ __align__(16) float sX[KR_TILE];
+    __shared__ __align__(16) float sY[KR_TILE];
+    __shared__ __align__(16) float sZ[KR_TILE];
+    __shared__ float sBD[Q][KR_CB][KR_THREADS];
+    __shared__ int sBI[Q][KR_CB][KR_THREADS];
+
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const float *qp = query + (size_t)b * M * 3;
+    const float *pp_ = points + (size_t)b * N * 3;
+    const int qbase = blockIdx.x * (KR_THREADS * Q);
+
+    float nqx[Q], nqy[Q], nqz[Q], tau[Q];
+    int cnt[Q];
+    float ld[Q][K];
+    int li[Q][K];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int i = qbase + q * KR_THREADS + tid;
+        float x = PP_INF, y = PP_INF, z = PP_INF;
+        if (i < M) {
+            x = __ldg(qp + (size_t)i * 3);
+            y = __ldg(qp + (size_t)i * 3 + 1);
+            z = __ldg(qp + (size_t)i * 3 + 2);
+        }
+        nqx[q] = -x; nqy[q] = -y; nqz[q] = -z;
+        tau[q] = PP_INF;
+        cnt[q] = 0;
+#pragma unroll
+        for (int s = 0; s < K; s++) {
+            // slots >= k are never reported: keep them at -inf so they never accept anything
+            ld[q][s] = s < k ? PP_INF : -PP_INF;
+            li[q][s] = -1;
+        }
+    }
+
+    auto drain = [&]() {
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int most = __reduce_max_sync(FULL_MASK, cnt[q]);
+            for (int e = 0; e < most; e++) {
+                float d = PP_INF;
+                int j = -1;
+                if (e < cnt[q]) {
+                    d = sBD[q][e][tid];
+                    j = sBI[q][e][tid];
+                }
+                knn_insert<K>(ld[q], li[q], d, j);
+            }
+            cnt[q] = 0;
+            // current k-th best; slots >= k hold -inf so index k-1 is found with a static select
+            float t = ld[q][0];
+#pragma unroll
+            for (int s = 1; s < K; s++) t = (s < k) ? ld[q][s] : t;
+            tau[q] = t;
+        }
+    };
+
+    for (int tile0 = 0; tile0 < N; tile0 += KR_TILE) {
+        __syncthreads();
+        for (int t = tid; t < KR_TILE; t += KR_THREADS) {
+            const int j = tile0 + t;
+            float x = PP_INF, y = PP_INF, z = PP_INF;  // padding: d = inf, never < tau
+            if (j < N) {
+                x = __ldg(pp_ + (size_t)j * 3);
+                y = __ldg(pp_ + (size_t)j * 3 + 1);
+                z = __ldg(pp_ + (size_t)j * 3 + 2);
+            }
+            sX[t] = x; sY[t] = y; sZ[t] = z;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int jj = 0; jj < KR_TILE; jj += 4) {
+            const float4 X = *reinterpret_cast<const float4 *>(sX + jj);
+            const float4 Y = *reinterpret_cast<const float4 *>(sY + jj);
+            const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj);
+            bool full = false;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const float2 d01 = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y),
+                                               make_float2(Z.x, Z.y), nqx[q], nqy[q], nqz[q]);
+                const float2 d23 = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w),
+                                               make_float2(Z.z, Z.w), nqx[q], nqy[q], nqz[q]);
+                const float mn = fminf(fmin3(d01.x, d01.y, d23.x), d23.y);
+                if (mn < tau[q]) {
+                    const float dd[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        if (dd[r] < tau[q]) {
+                            sBD[q][cnt[q]][tid] = dd[r];
+                            sBI[q][cnt[q]][tid] = tile0 + jj + r;
+                            cnt[q]++;
+                        }
+                    }
+                    full |= cnt[q] > KR_CB - 4;
+                }
+            }
+            if (__any_sync(FULL_MASK, full)) drain();
+        }
+    }
+    drain();
+
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int i = qbase + q * KR_THREADS + tid;
+        if (i < M) {
+            float *od = dist + ((size_t)b * M + i) * k;
+            int *oi = idx + ((size_t)b * M + i) * k;
+#pragma unroll
+            for (int s = 0; s < K; s++) {
+                if (s < k) {
+                    od[s] = ld[q][s];
+                    oi[s] = li[q][s];
+                }
+            }
+        }
+    }
+}
+
 // Generic point dimension (c != 3): simple thread-per-query kernel, candidates inserted
 // directly.  Correctness path only.
 __global__ void __launch_bounds__(128)
@@ -223,6 +378,21 @@ extern "C" int pp_knn(const float *query, const float *points, int B, int M, int
     if (c != 3 || get_option("knn_generic", 0)) {
         dim3 grid(ceil_div(M, 128), B);
         knn_generic_kernel<<<grid, 128, 0, st>>>(query, points, M, N, c, k, dist, idx);
+        PP_LAUNCH_CHECK();
+        return PP_OK;
+    }
+    if (k <= 32 && !get_option("knn_smem_lists", 0)) {
+        KernelTimer timer("knn", st);
+        if (k <= 8) {
+            dim3 grid(ceil_div(M, KR_THREADS * 2), B);
+            knn_reg_kernel<8, 2><<<grid, KR_THREADS, 0, st>>>(query, points, M, N, k, dist, idx);
+        } else if (k <= 16) {
+            dim3 grid(ceil_div(M, KR_THREADS * 2), B);
+            knn_reg_kernel<16, 2><<<grid, KR_THREADS, 0, st>>>(query, points, M, N, k, dist, idx);
+        } else {
+            dim3 grid(ceil_div(M, KR_THREADS), B);
+            knn_reg_kernel<32, 1><<<grid, KR_THREADS, 0, st>>>(query, points, M, N, k, dist, idx);
+        }
         PP_LAUNCH_CHECK();
         return PP_OK;
     }

@@ -326,6 +326,9 @@ KNN_CASES = [
     (2, 700, 1500, 16, lattice_cloud),    # ties -> (distance, index) order
     (1, 300, 5000, 32, sphere_cloud),
     (2, 513, 999, 7, uniform_cloud),
+    (2, 300, 700, 20, lattice_cloud),     # 16 < k <= 32: one query per thread
+    (1, 200, 600, 40, lattice_cloud),     # k > 32: shared-memory list kernel
+    (1, 100, 64, 64, uniform_cloud),      # k == N == PP_KNN_MAX_K
 ]
 
 
@@ -339,6 +342,20 @@ def test_knn_bit_exact(pp, oracle_mod, B, M, N, k, maker):
     assert np.array_equal(np32(idx), ei)
     assert np.array_equal(np32(dist), ed)
     assert np.array_equal(np32(nn), np.take_along_axis(np32(p)[:, None], ei[..., None].astype(np.int64), 2))
+
+
+def test_knn_shared_list_kernel_matches(pp, oracle_mod):
+    from pytorch_points_b200 import _C
+    p = with_duplicates(uniform_cloud(2, 3000, 60), 0.2)
+    ed, ei = oracle_mod.knn(16, np32(p[:, :500]), np32(p))
+    _C.set_option("knn_smem_lists", 1)
+    try:
+        _, idx, dist = pp.group_knn(16, dev(p[:, :500].contiguous()), dev(p), NCHW=False)
+    finally:
+        _C.set_option("knn_smem_lists", 0)
+    assert np.array_equal(np32(idx), ei) and np.array_equal(np32(dist), ed)
+    _, idx, dist = pp.group_knn(16, dev(p[:, :500].contiguous()), dev(p), NCHW=False)
+    assert np.array_equal(np32(idx), ei) and np.array_equal(np32(dist), ed)
 
 
 def test_knn_nchw_and_knn_points_adaptor(pp, oracle_mod):
