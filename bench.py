@@ -132,7 +132,7 @@ def run_cpu_baseline(N, M, budget_s=12.0):
     best = None
     t_start = time.perf_counter()
     reps = 0
-    while reps < 3 or (time.perf_counter() - t_start < budget_s and reps < 50):
+    while reps < 3 or time.perf_counter() - t_start < budget_s:
         t0 = time.perf_counter()
         cpu_chamfer_step(a, b, bs)
         dt = time.perf_counter() - t0
@@ -140,7 +140,8 @@ def run_cpu_baseline(N, M, budget_s=12.0):
         reps += 1
     return {"value": bs * N * M / best, "unit": "point-pairs/s", "cores": os.cpu_count(), "kind": "port",
             "sample": "oracle port (C + OpenMP, all host threads), Chamfer fwd+bwd on %d of the clouds, "
-                      "N=M=%d, best of %d runs (%.2f s each)" % (bs, N, reps, best)}
+                      "N=M=%d, best of %d back-to-back runs over %.0f s (%.3f s each)" % (
+                          bs, N, reps, time.perf_counter() - t_start, best)}
 
 
 def reference_arm(args, world, rank):
@@ -232,16 +233,18 @@ def main():
     d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, M, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, M, dtype=torch.int32, device=dev)
     sums = torch.zeros(2, device=dev)
-    gd1 = torch.full((B, N), 1.0 / (total_B * N), device=dev)
-    gd2 = torch.full((B, M), 1.0 / (total_B * M), device=dev)
     g1, g2 = torch.empty_like(a), torch.empty_like(b)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
+    gw = torch.tensor([1.0 / (total_B * N), 1.0 / (total_B * M)], device=dev)
+
     def step_device():
+        # forward (+ fused partial sums) -> all-reduce of the 2 sums -> backward with the two
+        # constant upstream weights d(loss)/d(dist) = 1/(B_total*N), 1/(B_total*M)
         losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
         if world > 1:
             dist.all_reduce(sums)
-        losses.nmdistance_backward(a, b, g1, g2, gd1, gd2, i1, i2)
+        losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
 
     def step_e2e():
         x = a_host.to(dev, non_blocking=True).requires_grad_(True)
@@ -277,13 +280,16 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
+    ms_step = timed(step_device, args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    # separate short pass with the library's per-kernel CUDA events switched on, so the event
+    # records do not perturb the two timed legs above
     _C.set_option("timing", 1)
     for nm in ("chamfer_fwd", "chamfer_finalize", "chamfer_bwd"):
         _C.timing_collect(nm)
-    ms_step = timed(step_device, args.steps, args.warmup)
+    timed(step_device, min(args.steps, 50), 3)
     kt = {nm: _C.timing_collect(nm) for nm in ("chamfer_fwd", "chamfer_finalize", "chamfer_bwd")}
     _C.set_option("timing", 0)
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop()
     loss_dev = float((sums[0] / (total_B * N) + sums[1] / (total_B * M)).item())
     loss_e2e = step_e2e()
@@ -336,7 +342,7 @@ def main():
                    "timing": "per-step CUDA events on the current stream, max over ranks"},
         "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3), "unit": "point-pairs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": world * (a_host.numel() + b_host.numel()) * 4, "d2h_bytes_per_step": world * 4,
-                "api": "pytorch_points_b200.network.nndistance (autograd) + dist.sharded_chamfer_loss, pinned host inputs"},
+                "api": "pytorch_points_b200.dist.sharded_chamfer_loss (autograd, fused chamfer_sums) + loss.backward() + loss.item(), pinned host inputs"},
         "gpu_launches": 4 * args.steps,
         "gpu_launches_note": "per step: chamfer_fwd_kernel, chamfer_finalize_kernel, chamfer_bwd_kernel<0>, <1>",
         "clocks": clocks, "roofline": roofline,
@@ -386,13 +392,13 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
     a, b = uniform_cloud(B, N, 1).to(dev), uniform_cloud(B, N, 2).to(dev)
     d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, N, device=dev)
     i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, N, dtype=torch.int32, device=dev)
-    gd = torch.full((B, N), 1.0 / (B * N), device=dev)
+    gw = torch.full((2,), 1.0 / (B * N), device=dev)
     g1, g2 = torch.empty_like(a), torch.empty_like(b)
     sums = torch.zeros(2, device=dev)
 
     def chamfer_step():
         losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
-        losses.nmdistance_backward(a, b, g1, g2, gd, gd, i1, i2)
+        losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
     _C.set_option("timing", 1)
     _C.timing_collect("chamfer_fwd")
     ms = timeit(chamfer_step)
@@ -404,7 +410,7 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
         "fwd_kernel_tflops": 8.0 * B * N * N / (kms * 1e-3) / 1e12,
         "fwd_kernel_frac_of_fp32_peak": 8.0 * B * N * N / (kms * 1e-3) / 1e12 / peak_tflops,
         "fwd_kernel_frac_of_op_mix_ceiling": B * N * N / (kms * 1e-3) / pipe_pairs}
-    del a, b, d1, d2, i1, i2, gd, g1, g2
+    del a, b, d1, d2, i1, i2, g1, g2
 
     # config 3: FPS 16384 -> 1024 (+gather) and ball_query r=0.2 nsample=32, B=16
     B, N, m = 16, 16384, 1024

@@ -80,6 +80,16 @@ int pp_chamfer_bwd(const float *xyz1, const float *xyz2, const float *graddist1,
                    const float *graddist2, const int32_t *idx1, const int32_t *idx2, int B, int N,
                    int M, int c, float *gradxyz1, float *gradxyz2, int device, void *stream);
 
+/*
+ * Chamfer backward for sum/mean-type losses (extension, no reference counterpart): identical
+ * to pp_chamfer_bwd with graddist1[b,i] = gw[0] and graddist2[b,j] = gw[1] for all points,
+ * gw being a 2-float DEVICE vector (the upstream gradient of [sum(dist1), sum(dist2)]).
+ * Saves materialising the two constant graddist arrays.
+ */
+int pp_chamfer_bwd_uniform(const float *xyz1, const float *xyz2, const float *gw,
+                           const int32_t *idx1, const int32_t *idx2, int B, int N, int M, int c,
+                           float *gradxyz1, float *gradxyz2, int device, void *stream);
+
 /* ---------------------------------------------------------------- sampling */
 
 /*

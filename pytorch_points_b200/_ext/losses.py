@@ -86,3 +86,22 @@ def nmdistance_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, id
                                    dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_bwd")
     return 1
+
+
+def nmdistance_backward_uniform(xyz1, xyz2, gradxyz1, gradxyz2, gw, idx1, idx2):
+    """Extension: backward for a loss that depends on dist1/dist2 only through
+    [sum(dist1), sum(dist2)]; `gw` is the 2-element CUDA tensor of upstream gradients of those
+    sums.  No (B,N)/(B,M) graddist tensors are materialised."""
+    dev = _C.require_cuda(xyz1, xyz2, gradxyz1, gradxyz2, gw, idx1, idx2)
+    _C.require_contiguous(xyz1, xyz2, gradxyz1, gradxyz2, gw, idx1, idx2)
+    _check_f32(xyz1, xyz2, gradxyz1, gradxyz2, gw)
+    if gw.numel() != 2:
+        raise RuntimeError("nmdistance_backward_uniform: gw must hold 2 floats")
+    B, N, c = xyz1.shape
+    M = xyz2.shape[1]
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_chamfer_bwd_uniform(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(gw), _C.ptr(idx1), _C.ptr(idx2),
+                                           B, N, M, c, _C.ptr(gradxyz1), _C.ptr(gradxyz2), dev.index,
+                                           _C.stream_of(dev))
+    _C.check(rc, "pp_chamfer_bwd_uniform")
+    return 1

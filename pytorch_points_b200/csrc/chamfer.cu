@@ -381,12 +381,15 @@ nmdist_generic_kernel(int n, int c, const float *__restrict__ q, const float *__
 //   phase 0: every point STORES its own term (the reference's first add onto 0);
 //   phase 1: every point scatters -v onto its nearest neighbour with RED.ADD.
 // ---------------------------------------------------------------------------
+// gd1/gd2 == nullptr selects the uniform form used by the fused sum/mean loss: every point of
+// side s has the upstream gradient gw[s] (a 2-float DEVICE vector).
 template <int PHASE>
 __global__ void __launch_bounds__(256)
 chamfer_bwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2,
                    const float *__restrict__ gd1, const float *__restrict__ gd2,
                    const int *__restrict__ idx1, const int *__restrict__ idx2, int B, int N, int M,
-                   int c, float *__restrict__ g1, float *__restrict__ g2) {
+                   int c, float *__restrict__ g1, float *__restrict__ g2,
+                   const float *__restrict__ gw) {
     const long long total1 = (long long)B * N, total = total1 + (long long)B * M;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
@@ -395,14 +398,16 @@ chamfer_bwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
     float *ga, *gb;
     long long u;
     int na, nb;
+    int side;
     if (t < total1) {
-        u = t; a = xyz1; bb = xyz2; gd = gd1; idx = idx1; ga = g1; gb = g2; na = N; nb = M;
+        u = t; a = xyz1; bb = xyz2; gd = gd1; idx = idx1; ga = g1; gb = g2; na = N; nb = M; side = 0;
     } else {
-        u = t - total1; a = xyz2; bb = xyz1; gd = gd2; idx = idx2; ga = g2; gb = g1; na = M; nb = N;
+        u = t - total1; a = xyz2; bb = xyz1; gd = gd2; idx = idx2; ga = g2; gb = g1; na = M; nb = N; side = 1;
     }
     const int b = (int)(u / na);
     const int j2 = idx[u];
-    const float g = __fmul_rn(gd[u], 2.f);
+    const float up = gd != nullptr ? gd[u] : __ldg(gw + side);
+    const float g = __fmul_rn(up, 2.f);
     const float *pa = a + (size_t)u * c;
     float *pga = ga + (size_t)u * c;
     if (j2 < 0) {  // labeled variant: no neighbour, no gradient (:175)
@@ -564,13 +569,12 @@ extern "C" int pp_chamfer_labeled_fwd(const float *xyz1, const float *xyz2, cons
     return launch_generic(true, xyz1, xyz2, label1, label2, B, N, M, c, dist1, dist2, idx1, idx2, st);
 }
 
-extern "C" int pp_chamfer_bwd(const float *xyz1, const float *xyz2, const float *graddist1,
-                              const float *graddist2, const int32_t *idx1, const int32_t *idx2, int B,
-                              int N, int M, int c, float *gradxyz1, float *gradxyz2, int device,
-                              void *stream) {
+static int chamfer_bwd_impl(const float *xyz1, const float *xyz2, const float *graddist1,
+                            const float *graddist2, const float *gw, const int32_t *idx1, const int32_t *idx2, int B, int N, int M, int c,
+                            float *gradxyz1, float *gradxyz2, int device, void *stream) {
     PP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && c >= 1, "chamfer_bwd: bad sizes");
     if (B == 0 || (N == 0 && M == 0)) return PP_OK;
-    PP_REQUIRE((N == 0 || (xyz1 && graddist1 && idx1 && gradxyz1)) && (M == 0 || (xyz2 && graddist2 && idx2 && gradxyz2)), "chamfer_bwd: null pointer");
+    PP_REQUIRE((N == 0 || (xyz1 && idx1 && gradxyz1)) && (M == 0 || (xyz2 && idx2 && gradxyz2)), "chamfer_bwd: null pointer");
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
     cudaStream_t st = (cudaStream_t)stream;
@@ -582,9 +586,27 @@ extern "C" int pp_chamfer_bwd(const float *xyz1, const float *xyz2, const float 
     const long long total = (long long)B * N + (long long)B * M;
     const unsigned blocks = (unsigned)ceil_div_ll(total, 256);
     KernelTimer timer("chamfer_bwd", st);
-    chamfer_bwd_kernel<0><<<blocks, 256, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, N, M, c, gradxyz1, gradxyz2);
+    chamfer_bwd_kernel<0><<<blocks, 256, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, N, M, c, gradxyz1, gradxyz2, gw);
     PP_LAUNCH_CHECK();
-    chamfer_bwd_kernel<1><<<blocks, 256, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, N, M, c, gradxyz1, gradxyz2);
+    chamfer_bwd_kernel<1><<<blocks, 256, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, N, M, c, gradxyz1, gradxyz2, gw);
     PP_LAUNCH_CHECK();
     return PP_OK;
+}
+
+extern "C" int pp_chamfer_bwd(const float *xyz1, const float *xyz2, const float *graddist1,
+                              const float *graddist2, const int32_t *idx1, const int32_t *idx2, int B,
+                              int N, int M, int c, float *gradxyz1, float *gradxyz2, int device,
+                              void *stream) {
+    PP_REQUIRE((N == 0 || B == 0 || graddist1) && (M == 0 || B == 0 || graddist2), "chamfer_bwd: null graddist");
+    return chamfer_bwd_impl(xyz1, xyz2, graddist1, graddist2, nullptr, idx1, idx2, B, N, M, c,
+                            gradxyz1, gradxyz2, device, stream);
+}
+
+extern "C" int pp_chamfer_bwd_uniform(const float *xyz1, const float *xyz2, const float *gw,
+                                      const int32_t *idx1, const int32_t *idx2, int B, int N, int M,
+                                      int c, float *gradxyz1, float *gradxyz2, int device,
+                                      void *stream) {
+    PP_REQUIRE(gw != nullptr || B == 0, "chamfer_bwd_uniform: null weight vector");
+    return chamfer_bwd_impl(xyz1, xyz2, nullptr, nullptr, gw, idx1, idx2, B, N, M, c,
+                            gradxyz1, gradxyz2, device, stream);
 }

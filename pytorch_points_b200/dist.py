@@ -43,26 +43,45 @@ def sharded_chamfer_loss(xyz1, xyz2, total_batch=None, group=None, local_op=None
     identical on every rank; its gradient w.r.t. the local clouds is the local share of the global
     mean, so `loss.backward()` needs no communication.  `local_op` defaults to the CUDA
     `nndistance`; tests inject a CPU stand-in to exercise the host logic under gloo."""
-    if local_op is None:
-        from .network.model_loss import nndistance as local_op
-    d1, d2, _, _ = local_op(xyz1, xyz2)
     world = _world(group)
+    if local_op is None:
+        # fused path: the forward kernel's epilogue already produced the two partial sums and the
+        # backward kernel takes the two scalar weights directly
+        from .network.model_loss import chamfer_sums
+        sums = chamfer_sums(xyz1, xyz2)
+        n, m = xyz1.shape[1], xyz2.shape[1]
+    else:
+        d1, d2, _, _ = local_op(xyz1, xyz2)
+        n, m = d1.shape[1], d2.shape[1]
+        sums = torch.stack([d1.sum(), d2.sum()])
     if total_batch is None:
-        tb = torch.tensor([float(xyz1.shape[0])], device=d1.device)
+        tb = torch.tensor([float(xyz1.shape[0])], device=sums.device)
         if world > 1:
             dist.all_reduce(tb, op=dist.ReduceOp.SUM, group=group)
         total_batch = int(tb.item())
-    n, m = d1.shape[1], d2.shape[1]
-    sums = torch.stack([d1.sum(), d2.sum()])
-    scale = torch.tensor([1.0 / (total_batch * max(n, 1)), 1.0 / (total_batch * max(m, 1))],
-                         dtype=sums.dtype, device=sums.device)
+    scale = _scale_vector(total_batch, n, m, sums.dtype, sums.device)
     local = (sums * scale).sum()
+    if world == 1:
+        return local
     total = sums.detach().clone()
-    if world > 1:
-        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     global_loss = (total * scale).sum()
     # value = global mean, gradient = this rank's share of it
     return local + (global_loss - local).detach()
+
+
+_scale_cache = {}
+
+
+def _scale_vector(total_batch, n, m, dtype, device):
+    key = (total_batch, n, m, dtype, str(device))
+    v = _scale_cache.get(key)
+    if v is None:
+        v = torch.tensor([1.0 / (total_batch * max(n, 1)), 1.0 / (total_batch * max(m, 1))], dtype=dtype, device=device)
+        if len(_scale_cache) > 64:
+            _scale_cache.clear()
+        _scale_cache[key] = v
+    return v
 
 
 def allreduce_chamfer_sums(sums, group=None):

@@ -1,6 +1,7 @@
 """Host-side mirror of the reference's `pytorch_points.network` entry points that sit on the
 hot path (same names, argument order and defaults)."""
-from .model_loss import NmDistanceFunction, LabeledNmdistanceFunction, nndistance, labeled_nndistance  # noqa: F401
+from .model_loss import (NmDistanceFunction, LabeledNmdistanceFunction, nndistance, labeled_nndistance,  # noqa: F401
+                         ChamferSumsFunction, chamfer_sums, chamfer_mean_loss)
 from .geo_operations import FurthestPointSampling, furthest_point_sample  # noqa: F401
 from .operations import (GatherFunction, gather_points, BallQuery, ball_query, GroupingOperation,  # noqa: F401
                          grouping_operation, QueryAndGroup, group_knn, knn_points)

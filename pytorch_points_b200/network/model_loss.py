@@ -80,3 +80,45 @@ class LabeledNmdistanceFunction(torch.autograd.Function):
 
 
 labeled_nndistance = LabeledNmdistanceFunction.apply  # type: ignore
+
+
+class ChamferSumsFunction(torch.autograd.Function):
+    """Fused building block for mean-type Chamfer losses (extension; the reference leaves the
+    reduction to user code): returns the 2-vector [sum(dist1), sum(dist2)] produced inside the
+    forward kernel's epilogue.  Its backward scatters with two scalar weights instead of two
+    (B,N)/(B,M) graddist tensors."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        xyz1 = xyz1.contiguous()
+        xyz2 = xyz2.contiguous()
+        B, n, _ = xyz1.size()
+        _, m, _ = xyz2.size()
+        dev = xyz1.device
+        dist1 = torch.empty(B, n, dtype=xyz1.dtype, device=dev)
+        dist2 = torch.empty(B, m, dtype=xyz1.dtype, device=dev)
+        idx1 = torch.empty(B, n, dtype=torch.int32, device=dev)
+        idx2 = torch.empty(B, m, dtype=torch.int32, device=dev)
+        sums = torch.empty(2, dtype=xyz1.dtype, device=dev)
+        losses.nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=sums)
+        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        return sums
+
+    @staticmethod
+    def backward(ctx, gsums):
+        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+        gradxyz1 = torch.empty_like(xyz1)
+        gradxyz2 = torch.empty_like(xyz2)
+        losses.nmdistance_backward_uniform(xyz1, xyz2, gradxyz1, gradxyz2, gsums.contiguous(), idx1, idx2)
+        return gradxyz1, gradxyz2
+
+
+chamfer_sums = ChamferSumsFunction.apply  # type: ignore
+
+
+def chamfer_mean_loss(xyz1, xyz2):
+    """mean(dist1) + mean(dist2) with the reduction fused into the kernels (extension)."""
+    s = chamfer_sums(xyz1, xyz2)
+    B, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    return s[0] / (B * n) + s[1] / (B * m)

@@ -153,6 +153,37 @@ def test_chamfer_loss_mean_backward_matches_torch_autograd(pp):
     assert_grad_close(np32(b.grad), np32(b2.grad), "grad b")
 
 
+def test_fused_mean_loss_matches_nndistance_path(pp):
+    """chamfer_mean_loss / chamfer_sums (fused reduction + uniform backward) vs the reference-shaped
+    nndistance path followed by .mean()."""
+    a0, b0 = uniform_cloud(3, 700, 61), uniform_cloud(3, 500, 62)
+    a, b = dev(a0).requires_grad_(True), dev(b0).requires_grad_(True)
+    d1, d2, _, _ = pp.nndistance(a, b)
+    l1 = d1.mean() + d2.mean()
+    l1.backward()
+    a2, b2 = dev(a0).requires_grad_(True), dev(b0).requires_grad_(True)
+    l2 = pp.chamfer_mean_loss(a2, b2)
+    (3.0 * l2).backward()
+    assert abs(l1.item() - l2.item()) <= 1e-6 * abs(l1.item())
+    assert_grad_close(np32(a2.grad), 3.0 * np32(a.grad), "fused grad a")
+    assert_grad_close(np32(b2.grad), 3.0 * np32(b.grad), "fused grad b")
+
+
+def test_sharded_loss_single_rank_on_gpu(pp):
+    from pytorch_points_b200.dist import sharded_chamfer_loss
+    a0, b0 = uniform_cloud(2, 300, 63), uniform_cloud(2, 400, 64)
+    a, b = dev(a0).requires_grad_(True), dev(b0).requires_grad_(True)
+    loss = sharded_chamfer_loss(a, b)
+    loss.backward()
+    a2, b2 = dev(a0).requires_grad_(True), dev(b0).requires_grad_(True)
+    d1, d2, _, _ = pp.nndistance(a2, b2)
+    ref = d1.mean() + d2.mean()
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item())
+    assert_grad_close(np32(a.grad), np32(a2.grad), "sharded grad a")
+    assert_grad_close(np32(b.grad), np32(b2.grad), "sharded grad b")
+
+
 def test_labeled_chamfer(pp, oracle_mod):
     a, b = uniform_cloud(2, 700, 27), uniform_cloud(2, 900, 28)
     g = torch.Generator().manual_seed(29)
