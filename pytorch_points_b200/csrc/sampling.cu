@@ -35,13 +35,49 @@ constexpr int FPS_T = 512;
 constexpr int FPS_MAXC = 8;
 constexpr int FPS_W = FPS_T / 32;
 
-struct FpsRec {  // 32 bytes
+struct FpsRec {  // 32 bytes: (value, tie-key) in the first half, the point itself in the second
     int v;       // running-min value bits (>= 0 for real points, -1.0f for padding)
     unsigned t;  // tie-key
+    int pad0, pad1;
     float x, y, z;
     int k;  // point index
-    int pad0, pad1;
 };
+
+// ---- cluster point-to-point signalling (mbarrier in the destination CTA's shared memory) ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned map_to_cta(unsigned local_addr, int cta) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// Asynchronous remote store: the 16 bytes land in the destination CTA's shared memory and, as
+// part of the same operation, complete 16 transaction bytes on that CTA's mbarrier.  Fire and
+// forget for the sender -- no release fence (a .release.cluster arrive costs a full
+// MEMBAR.GPU per round, measured ~600 cycles).
+__device__ __forceinline__ void st_async_v4(unsigned dst, float4 v, unsigned mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(dst),
+                 "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)),
+                 "r"(__float_as_uint(v.w)), "r"(mbar)
+                 : "memory");
+}
+// One local thread arms the next phase: one arrival (this one) + `bytes` of remote stores.
+__device__ __forceinline__ void mbar_arm(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "}" ::"r"(a), "r"(parity)
+        : "memory");
+}
 
 __device__ __forceinline__ unsigned fps_tiekey(int k, int bs_log2) {
     return ((unsigned)(k & ((1 << bs_log2) - 1)) << 22) | (unsigned)(k >> bs_log2);
@@ -50,11 +86,21 @@ __device__ __forceinline__ unsigned fps_tiekey(int k, int bs_log2) {
 template <int P, int C>
 __global__ void __launch_bounds__(FPS_T, 1)
 fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float *__restrict__ temp,
-                   int *__restrict__ idx, int bs_log2) {
+                   int *__restrict__ idx, int bs_log2, long long *__restrict__ prof) {
+    // prof != nullptr: thread 0 of cluster 0 accumulates clock64() deltas per phase (debug only)
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long pc = 0;
+#define FPS_STAMP(i)                                   \
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { \
+        const long long now = clock64();               \
+        pt[i] += now - pc;                             \
+        pc = now;                                      \
+    }
     extern __shared__ __align__(16) unsigned char fps_smem[];
     float4 *sPts = reinterpret_cast<float4 *>(fps_smem);  // [P][FPS_T] this CTA's points
     __shared__ __align__(8) int2 wrec[2][FPS_W];           // per-warp (value, tie-key)
     __shared__ __align__(16) FpsRec crec[2][FPS_MAXC];     // per-CTA winners, written by peers
+    __shared__ __align__(8) unsigned long long cbar[2];     // "all C records of this parity arrived"
 
     const int rank = (C > 1) ? (int)cg::this_cluster().block_rank() : 0;
     const int b = blockIdx.x / C;
@@ -88,13 +134,22 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
     float ox = __ldg(pts + (size_t)seed * 3 + 0), oy = __ldg(pts + (size_t)seed * 3 + 1),
           oz = __ldg(pts + (size_t)seed * 3 + 2);
     if (tg == 0) out[0] = seed;
+    if (C > 1 && tid == 0) {
+        mbar_init(&cbar[0], 1);
+        mbar_init(&cbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arm(&cbar[0], C * (unsigned)sizeof(FpsRec));  // first use of each barrier
+        mbar_arm(&cbar[1], C * (unsigned)sizeof(FpsRec));
+    }
     __syncthreads();
-    if (C > 1) cg::this_cluster().sync();  // peers' shared memory is live before any remote store
+    if (C > 1) cg::this_cluster().sync();  // peers' shared memory and barriers are live before any remote store
 
+    if (prof != nullptr) pc = clock64();
     for (int j = 1; j < m; j++) {
         const int par = j & 1;
         float best = -1.f;
         int bp = 0;
+        FPS_STAMP(7)
 #pragma unroll
         for (int p = 0; p < P; p++) {
             const float d = sqdist_yxz(__fsub_rn(px[p], ox), __fsub_rn(py[p], oy), __fsub_rn(pz[p], oz));
@@ -105,57 +160,79 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
                 bp = p;
             }
         }
-        // warp: max value, then min tie-key among the lanes holding it
+        FPS_STAMP(0)
+        // warp: max value, then min tie-key among the lanes holding it (two REDUX; measured
+        // faster than one REDUX + vote + rare tie path)
         const int myv = __float_as_int(best);
         const unsigned mytk = tk0 + (unsigned)bp * tkstep;
         const int wv = __reduce_max_sync(FULL_MASK, myv);
         const unsigned wt = __reduce_min_sync(FULL_MASK, myv == wv ? mytk : 0xffffffffu);
         if (lane == 0) wrec[par][warp] = make_int2(wv, (int)wt);
+        FPS_STAMP(1)
         __syncthreads();
-        // every warp reduces the FPS_W warp records redundantly (no second barrier)
-        int2 r = lane < FPS_W ? wrec[par][lane] : make_int2(INT_MIN, -1);
-        const int cv = __reduce_max_sync(FULL_MASK, r.x);
-        const unsigned ct = __reduce_min_sync(FULL_MASK, r.x == cv ? (unsigned)r.y : 0xffffffffu);
-        // decode the CTA winner: k = (k div bs) * bs + (k mod bs)
-        const int ck = (int)((ct & 0x3fffffu) << bs_log2) | (int)(ct >> 22);
+        FPS_STAMP(2)
         if (C == 1) {
+            // every warp reduces the FPS_W warp records redundantly (no second barrier)
+            int2 r = lane < FPS_W ? wrec[par][lane] : make_int2(INT_MIN, -1);
+            const int cv = __reduce_max_sync(FULL_MASK, r.x);
+            const unsigned ct = __reduce_min_sync(FULL_MASK, r.x == cv ? (unsigned)r.y : 0xffffffffu);
+            // decode the winner: k = (k div bs) * bs + (k mod bs)
+            const int ck = (int)((ct & 0x3fffffu) << bs_log2) | (int)(ct >> 22);
+            FPS_STAMP(3)
             const int slot = (ck / TT) * FPS_T + (ck % TT);
             const float4 w = sPts[slot];
             ox = w.x; oy = w.y; oz = w.z;
             if (tid == 0) out[j] = ck;
         } else {
-            if (warp == 0 && lane < C) {
-                const int slot = (ck / TT) * FPS_T + (ck % TT - rank * FPS_T);
-                const float4 w = sPts[slot];
-                FpsRec rec;
-                rec.v = cv; rec.t = ct; rec.x = w.x; rec.y = w.y; rec.z = w.z; rec.k = ck;
-                rec.pad0 = 0; rec.pad1 = 0;
-                FpsRec *dst = cg::this_cluster().map_shared_rank(&crec[par][rank], lane);
-                *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<float4 *>(&rec);
-                *(reinterpret_cast<float4 *>(dst) + 1) = *(reinterpret_cast<float4 *>(&rec) + 1);
-            }
-            cg::this_cluster().sync();
-            int bv = INT_MIN;
-            unsigned bt = 0xffffffffu;
-            int bk = 0;
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                const float4 lo = *reinterpret_cast<const float4 *>(&crec[par][c]);
-                const float4 hi = *(reinterpret_cast<const float4 *>(&crec[par][c]) + 1);
-                const int v = __float_as_int(lo.x);
-                const unsigned t = __float_as_uint(lo.y);
-                if (v > bv || (v == bv && t < bt)) {
-                    bv = v; bt = t; ox = lo.z; oy = lo.w; oz = hi.x; bk = __float_as_int(hi.y);
+            if (warp == 0) {
+                // only warp 0 needs this CTA's winner: it ships it to every CTA of the cluster
+                int2 r = lane < FPS_W ? wrec[par][lane] : make_int2(INT_MIN, -1);
+                const int cv = __reduce_max_sync(FULL_MASK, r.x);
+                const unsigned ct = __reduce_min_sync(FULL_MASK, r.x == cv ? (unsigned)r.y : 0xffffffffu);
+                const int ck = (int)((ct & 0x3fffffu) << bs_log2) | (int)(ct >> 22);
+                FPS_STAMP(3)
+                if (lane < C) {
+                    const int slot = (ck / TT) * FPS_T + (ck % TT - rank * FPS_T);
+                    const float4 w = sPts[slot];
+                    // lane c delivers the record to CTA c; each 16-byte st.async also completes
+                    // 16 transaction bytes on CTA c's barrier (point-to-point: no cluster-wide
+                    // barrier and no fence on the critical path)
+                    const unsigned dst = map_to_cta(smem_u32(&crec[par][rank]), lane);
+                    const unsigned bar = map_to_cta(smem_u32(&cbar[par]), lane);
+                    st_async_v4(dst, make_float4(__int_as_float(cv), __uint_as_float(ct), 0.f, 0.f), bar);
+                    st_async_v4(dst + 16, make_float4(w.x, w.y, w.z, __int_as_float(ck)), bar);
                 }
             }
-            if (tg == 0) out[j] = bk;
+            FPS_STAMP(4)
+            mbar_wait(&cbar[par], (unsigned)((j - 1) >> 1) & 1u);  // u-th use of this barrier
+            if (tid == 0) mbar_arm(&cbar[par], C * (unsigned)sizeof(FpsRec));  // arm its next use
+            FPS_STAMP(5)
+            // cluster winner, lane-parallel: lane c looks at CTA c's (value, tie-key)
+            int v = INT_MIN;
+            unsigned t = 0xffffffffu;
+            if (lane < C) {
+                const int2 vt = *reinterpret_cast<const int2 *>(&crec[par][lane]);
+                v = vt.x;
+                t = (unsigned)vt.y;
+            }
+            const int bv = __reduce_max_sync(FULL_MASK, v);
+            const unsigned bt = __reduce_min_sync(FULL_MASK, v == bv ? t : 0xffffffffu);
+            const unsigned who = __ballot_sync(FULL_MASK, v == bv && t == bt);  // tie-keys are unique
+            const float4 w = *(reinterpret_cast<const float4 *>(&crec[par][__ffs(who) - 1]) + 1);
+            ox = w.x; oy = w.y; oz = w.z;
+            if (tg == 0) out[j] = __float_as_int(w.w);
+            FPS_STAMP(6)
         }
     }
+    if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int i = 0; i < 8; i++) prof[i] = pt[i];
+#undef FPS_STAMP
 #pragma unroll
     for (int p = 0; p < P; p++) {
         const int k = tg + p * TT;
         if (k < N) tp[k] = td[p];
     }
+    if (C > 1) cg::this_cluster().sync();  // nobody exits while a peer may still write into it
 }
 
 // Fallback for clouds too large for the register-resident kernel: one 1024-thread CTA per
@@ -376,7 +453,11 @@ int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *t
         return PP_OK;
     }
     KernelTimer timer("fps", st);
-    PP_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, seed, temp, idx, bs_log2));
+    long long *prof = (long long *)(uintptr_t)(unsigned long long)get_option("fps_prof_ptr_lo", 0);
+    if (prof != nullptr)
+        prof = (long long *)(((unsigned long long)(unsigned)get_option("fps_prof_ptr_hi", 0) << 32) |
+                             (unsigned long long)(unsigned)get_option("fps_prof_ptr_lo", 0));
+    PP_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, seed, temp, idx, bs_log2, prof));
     return PP_OK;
 }
 
