@@ -272,16 +272,22 @@ knn_reg_kernel(const float *__restrict__ query, const float *__restrict__ points
             const float4 X = *reinterpret_cast<const float4 *>(sX + jj);
             const float4 Y = *reinterpret_cast<const float4 *>(sY + jj);
             const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj);
-            bool full = false;
+            float2 d01[Q], d23[Q];
+            bool cand = false;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-                const float2 d01 = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y),
-                                               make_float2(Z.x, Z.y), nqx[q], nqy[q], nqz[q]);
-                const float2 d23 = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w),
-                                               make_float2(Z.z, Z.w), nqx[q], nqy[q], nqz[q]);
-                const float mn = fminf(fmin3(d01.x, d01.y, d23.x), d23.y);
-                if (mn < tau[q]) {
-                    const float dd[4] = {d01.x, d01.y, d23.x, d23.y};
+                d01[q] = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y),
+                                     nqx[q], nqy[q], nqz[q]);
+                d23[q] = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
+                                     nqx[q], nqy[q], nqz[q]);
+                cand |= fminf(fmin3(d01[q].x, d01[q].y, d23[q].x), d23[q].y) < tau[q];
+            }
+            // hot path ends here: one vote, one (warp-uniform) branch per 4 points x Q queries
+            if (__any_sync(FULL_MASK, cand)) {
+                bool full = false;
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const float dd[4] = {d01[q].x, d01[q].y, d23[q].x, d23[q].y};
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
                         if (dd[r] < tau[q]) {
@@ -292,8 +298,8 @@ knn_reg_kernel(const float *__restrict__ query, const float *__restrict__ points
                     }
                     full |= cnt[q] > KR_CB - 4;
                 }
+                if (__any_sync(FULL_MASK, full)) drain();
             }
-            if (__any_sync(FULL_MASK, full)) drain();
         }
     }
     drain();
