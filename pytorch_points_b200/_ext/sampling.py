@@ -135,8 +135,10 @@ def knn(k, query, points):
     _check(points.shape[0] == B and points.shape[2] == c, "knn: query/points shapes disagree")
     dist = torch.empty(B, M, int(k), dtype=torch.float32, device=dev)
     idx = torch.empty(B, M, int(k), dtype=torch.int32, device=dev)
+    nbytes = _C.lib.pp_knn_workspace_bytes(B, M, N, c, int(k))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
     with torch.cuda.device(dev):
         rc = _C.lib.pp_knn(_C.ptr(query), _C.ptr(points), B, M, N, c, int(k), _C.ptr(dist), _C.ptr(idx),
-                           _C.ptr(None), 0, dev.index, _C.stream_of(dev))
+                           _C.ptr(ws), nbytes, dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_knn")
     return dist, idx

@@ -365,13 +365,24 @@ size_t knn_smem_bytes(int k) {
 
 using namespace pp;
 
-extern "C" size_t pp_knn_workspace_bytes(int, int, int, int, int) { return 0; }
+// Spatially ordered sweep (knn_morton.cu) pays off once the clouds are large enough for the
+// sort (a handful of small launches) to vanish next to the distance work.
+static bool knn_use_morton(int B, int M, int N, int c, int k) {
+    if (c != 3 || k > 32) return false;
+    const int opt = get_option("knn_morton", -1);
+    if (opt >= 0) return opt != 0;
+    return N >= 4096 && (long long)B * M >= 4096;
+}
+
+extern "C" size_t pp_knn_workspace_bytes(int B, int M, int N, int c, int k) {
+    if (B <= 0 || M <= 0 || N <= 0) return 0;
+    if (c != 3 || k > 32) return 0;
+    return knn_morton_workspace_bytes(B, M, N);  // upper bound: needed whenever the ordered sweep is chosen
+}
 
 extern "C" int pp_knn(const float *query, const float *points, int B, int M, int N, int c, int k,
                       float *dist, int32_t *idx, void *workspace, size_t workspace_bytes, int device,
                       void *stream) {
-    (void)workspace;
-    (void)workspace_bytes;
     PP_REQUIRE(B >= 0 && M >= 0 && N >= 0 && c >= 1, "knn: bad sizes");
     PP_REQUIRE(k >= 1 && k <= PP_KNN_MAX_K, "knn: k=%d outside [1,%d]", k, PP_KNN_MAX_K);
     if (B == 0 || M == 0) return PP_OK;
@@ -387,6 +398,8 @@ extern "C" int pp_knn(const float *query, const float *points, int B, int M, int
         PP_LAUNCH_CHECK();
         return PP_OK;
     }
+    if (knn_use_morton(B, M, N, c, k) && !get_option("knn_smem_lists", 0))
+        return knn_morton_launch(query, points, B, M, N, k, dist, idx, workspace, workspace_bytes, st);
     if (k <= 32 && !get_option("knn_smem_lists", 0)) {
         KernelTimer timer("knn", st);
         if (k <= 8) {

@@ -1,0 +1,425 @@
+// knn_morton.cu -- spatially ordered sweep for group_knn on large clouds.
+//
+// Why: the streaming top-k of knn.cu is dominated, on unordered clouds, by its "rare" path --
+// with 32 lanes x Q queries looking at unrelated neighbourhoods, some lane finds a candidate
+// in most 4-point steps, so the warp keeps leaving the FP32-bound hot loop.  Here both clouds
+// are first sorted along a Morton (Z-order) curve, a CTA's queries are therefore spatial
+// neighbours, and the sweep over the (sorted) points STARTS at the CTA's own position on the
+// curve and works outwards.  After the first tiles every query's k-th distance is nearly final,
+// candidates become rare AND coincide across lanes, and the rest of the sweep stays in the
+// hot loop.  The result is exactly the same as the unordered sweep: selection and final order
+// use the lexicographic key (distance, ORIGINAL index), distances are evaluated in the same
+// rounding order, and the permutation is undone when rows are written.
+//
+// Pipeline (all on the caller's stream, scratch in the caller's workspace):
+//   bbox (atomic min/max) -> 30-bit Morton keys tagged with the batch index -> cub radix sort
+//   -> gather sorted coordinates + original indices -> knn_morton_kernel.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "pp_common.cuh"
+
+namespace pp {
+namespace {
+
+constexpr int KM_THREADS = 128;
+constexpr int KM_TILE = 256;
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) {
+    return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff);
+}
+
+// bbox[0..2] = min (ordered ints), bbox[3..5] = max
+__global__ void __launch_bounds__(256)
+km_bbox_kernel(const float *__restrict__ xyz, long long n, int *__restrict__ bbox) {
+    float lo[3] = {PP_INF, PP_INF, PP_INF}, hi[3] = {-PP_INF, -PP_INF, -PP_INF};
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float v = __ldg(xyz + e * 3 + c);
+            if (v == v && fabsf(v) != PP_INF) {  // ignore NaN / inf
+                lo[c] = fminf(lo[c], v);
+                hi[c] = fmaxf(hi[c], v);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(FULL_MASK, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(FULL_MASK, hi[c], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            atomicMin(bbox + c, float_to_ordered(lo[c]));
+            atomicMax(bbox + 3 + c, float_to_ordered(hi[c]));
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned spread10(unsigned v) {  // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+km_keys_kernel(const float *__restrict__ xyz, int per_cloud, long long n, const int *__restrict__ bbox,
+               unsigned long long *__restrict__ keys, unsigned *__restrict__ vals) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    unsigned code = 0;
+    unsigned q[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float lo = ordered_to_float(bbox[c]), hi = ordered_to_float(bbox[3 + c]);
+        const float ext = hi - lo;
+        const float v = __ldg(xyz + e * 3 + c);
+        float t = ext > 0.f ? (v - lo) / ext * 1023.f : 0.f;
+        t = (t == t) ? fminf(fmaxf(t, 0.f), 1023.f) : 0.f;
+        q[c] = (unsigned)t;
+    }
+    code = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+    keys[e] = ((unsigned long long)(e / per_cloud) << 32) | code;
+    vals[e] = (unsigned)e;
+}
+
+__global__ void __launch_bounds__(256)
+km_gather_kernel(const float *__restrict__ xyz, const unsigned *__restrict__ order, int per_cloud,
+                 long long n, float *__restrict__ sorted_xyz, int *__restrict__ sorted_idx) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const unsigned src = order[e];
+    sorted_xyz[e * 3 + 0] = __ldg(xyz + (size_t)src * 3 + 0);
+    sorted_xyz[e * 3 + 1] = __ldg(xyz + (size_t)src * 3 + 1);
+    sorted_xyz[e * 3 + 2] = __ldg(xyz + (size_t)src * 3 + 2);
+    sorted_idx[e] = (int)(src % (unsigned)per_cloud);
+}
+
+// Insertion of (d0,j0) into the ascending list: it enters in front of the first slot that is
+// larger; from there on every slot takes its predecessor (pure shift).  LEX = false compares
+// distances only (5 instructions per slot) and reports whether an exactly equal distance was
+// met; LEX = true uses the full (distance, original index) key (8 per slot).
+template <int K, bool LEX>
+__device__ __forceinline__ bool km_insert(float (&ld)[K], int (&li)[K], float d, int j) {
+    const float d0 = d;
+    const int j0 = j;
+    bool tie = false;
+#pragma unroll
+    for (int s = 0; s < K; s++) {
+        const float td = ld[s];
+        const int ti = li[s];
+        bool sw;
+        if (LEX) {
+            sw = d0 < td || (d0 == td && j0 < ti);
+        } else {
+            sw = d0 < td;
+            tie |= d0 == td;
+        }
+        ld[s] = sw ? d : td;
+        li[s] = sw ? j : ti;
+        d = sw ? td : d;
+        j = sw ? ti : j;
+    }
+    return tie;
+}
+
+template <int K, int Q, int KM_CB, bool PRECHECK>
+__global__ void __launch_bounds__(KM_THREADS)
+knn_morton_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, const unsigned long long *__restrict__ qkeys,
+                  const float *__restrict__ sp, const int *__restrict__ spi, const unsigned long long *__restrict__ pkeys,
+                  int M, int N, int k, float *__restrict__ dist, int *__restrict__ idx) {
+    __shared__ __align__(16) float sX[KM_TILE];
+    __shared__ __align__(16) float sY[KM_TILE];
+    __shared__ __align__(16) float sZ[KM_TILE];
+    __shared__ int sI[KM_TILE];
+    __shared__ float sBD[Q][KM_CB][KM_THREADS];
+    __shared__ int sBI[Q][KM_CB][KM_THREADS];
+    __shared__ int s_start;
+
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const float *qp = sq + (size_t)b * M * 3;
+    const float *pp_ = sp + (size_t)b * N * 3;
+    const int *pi = spi + (size_t)b * N;
+    const int qbase = blockIdx.x * (KM_THREADS * Q);
+    const int ntiles = ceil_div(N, KM_TILE);
+
+    // where on the points' curve do this CTA's queries sit?  lower_bound of the CTA's middle
+    // query key among the sorted point keys of this cloud (warp 0, 32-ary search)
+    if (tid < 32) {
+        const int mid = min(M - 1, qbase + (KM_THREADS * Q) / 2);
+        const unsigned long long want = qkeys[(size_t)b * M + mid];
+        const unsigned long long *pk = pkeys + (size_t)b * N;
+        int lo = 0, hi = N;  // answer in [lo, hi]
+        while (hi - lo > 0) {
+            const int span = hi - lo;
+            const int step = (span + 31) / 32;
+            const int probe = lo + tid * step;
+            const bool below = probe < hi && pk[probe] < want;
+            const unsigned m = __ballot_sync(FULL_MASK, below);
+            const int nb = __popc(m);  // probes 0..nb-1 are below (keys sorted)
+            if (nb == 0) {
+                hi = lo;
+            } else {
+                const int nlo = lo + (nb - 1) * step + 1;
+                const int nhi = min(hi, lo + nb * step);
+                lo = nlo;
+                hi = nhi;
+            }
+        }
+        if (tid == 0) s_start = min(ntiles - 1, lo / KM_TILE);
+    }
+
+    float nqx[Q], nqy[Q], nqz[Q], tau[Q];
+    int cnt[Q];
+    float ld[Q][K];
+    int li[Q][K];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int i = qbase + q * KM_THREADS + tid;
+        float x = PP_INF, y = PP_INF, z = PP_INF;
+        if (i < M) {
+            x = __ldg(qp + (size_t)i * 3);
+            y = __ldg(qp + (size_t)i * 3 + 1);
+            z = __ldg(qp + (size_t)i * 3 + 2);
+        }
+        nqx[q] = -x; nqy[q] = -y; nqz[q] = -z;
+        tau[q] = PP_INF;
+        cnt[q] = 0;
+#pragma unroll
+        for (int s = 0; s < K; s++) {
+            ld[q][s] = s < k ? PP_INF : -PP_INF;  // slots >= k never accept anything
+            li[q][s] = s < k ? 0x7fffffff : -1;
+        }
+    }
+
+    auto drain = [&]() {
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int most = __reduce_max_sync(FULL_MASK, cnt[q]);
+            for (int e = 0; e < most; e++) {
+                float d = PP_INF;
+                int j = 0x7fffffff;
+                if (e < cnt[q]) {
+                    d = sBD[q][e][tid];
+                    j = sBI[q][e][tid];
+                }
+                // An exactly equal distance already in some lane's list?  Only then does the
+                // original index decide and the (more expensive) full-key insertion run.
+                if (PRECHECK) {
+                    bool tie = false;
+#pragma unroll
+                    for (int s = 0; s < K; s++) tie |= d == ld[q][s];
+                    if (__any_sync(FULL_MASK, tie && d < PP_INF))
+                        km_insert<K, true>(ld[q], li[q], d, j);
+                    else
+                        km_insert<K, false>(ld[q], li[q], d, j);
+                } else {
+                    km_insert<K, true>(ld[q], li[q], d, j);
+                }
+            }
+            cnt[q] = 0;
+            float t = ld[q][0];
+#pragma unroll
+            for (int s = 1; s < K; s++) t = (s < k) ? ld[q][s] : t;
+            tau[q] = t;
+        }
+    };
+
+    __syncthreads();
+    const int t0 = s_start;
+    for (int s = 0; s < ntiles; s++) {
+        // outward sweep: t0, t0+1, t0-1, t0+2, ... (wrapping), nearest tiles first
+        int t = (s & 1) ? t0 + (s + 1) / 2 : t0 - s / 2;
+        t %= ntiles;
+        if (t < 0) t += ntiles;
+        const int tile0 = t * KM_TILE;
+        __syncthreads();
+        for (int u = tid; u < KM_TILE; u += KM_THREADS) {
+            const int j = tile0 + u;
+            float x = PP_INF, y = PP_INF, z = PP_INF;  // padding: d = inf
+            int oi = 0x7fffffff;
+            if (j < N) {
+                x = __ldg(pp_ + (size_t)j * 3);
+                y = __ldg(pp_ + (size_t)j * 3 + 1);
+                z = __ldg(pp_ + (size_t)j * 3 + 2);
+                oi = __ldg(pi + j);
+            }
+            sX[u] = x; sY[u] = y; sZ[u] = z; sI[u] = oi;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int jj = 0; jj < KM_TILE; jj += 4) {
+            const float4 X = *reinterpret_cast<const float4 *>(sX + jj);
+            const float4 Y = *reinterpret_cast<const float4 *>(sY + jj);
+            const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj);
+            float2 d01[Q], d23[Q];
+            bool cand = false;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                d01[q] = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y),
+                                     nqx[q], nqy[q], nqz[q]);
+                d23[q] = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
+                                     nqx[q], nqy[q], nqz[q]);
+                // '<=': an equal distance with a lower original index still has to get in
+                cand |= fminf(fmin3(d01[q].x, d01[q].y, d23[q].x), d23[q].y) <= tau[q];
+            }
+            if (__any_sync(FULL_MASK, cand)) {
+                bool full = false;
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const float dd[4] = {d01[q].x, d01[q].y, d23[q].x, d23[q].y};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        if (dd[r] <= tau[q] && dd[r] < PP_INF) {
+                            sBD[q][cnt[q]][tid] = dd[r];
+                            sBI[q][cnt[q]][tid] = sI[jj + r];
+                            cnt[q]++;
+                        }
+                    }
+                    full |= cnt[q] > KM_CB - 4;
+                }
+                if (__any_sync(FULL_MASK, full)) drain();
+            }
+        }
+    }
+    drain();
+
+    const int *qi = sqi + (size_t)b * M;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int i = qbase + q * KM_THREADS + tid;
+        if (i < M) {
+            const int orig = __ldg(qi + i);
+            float *od = dist + ((size_t)b * M + orig) * k;
+            int *oi = idx + ((size_t)b * M + orig) * k;
+#pragma unroll
+            for (int s = 0; s < K; s++) {
+                if (s < k) {
+                    od[s] = ld[q][s];
+                    oi[s] = li[q][s] == 0x7fffffff ? -1 : li[q][s];
+                }
+            }
+        }
+    }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct KmLayout {
+    size_t bbox, keys_in, keys_out, vals_in, vals_out, sorted_xyz, sorted_idx, cub_temp, cub_bytes, total;
+};
+
+// One set of buffers sized for max(nq, np) elements is laid out twice (points, then queries).
+KmLayout km_layout(size_t n) {
+    KmLayout L;
+    size_t off = 0;
+    L.bbox = off; off = align_up(off + 6 * sizeof(int), 256);
+    L.keys_in = off; off = align_up(off + n * 8, 256);
+    L.keys_out = off; off = align_up(off + n * 8, 256);
+    L.vals_in = off; off = align_up(off + n * 4, 256);
+    L.vals_out = off; off = align_up(off + n * 4, 256);
+    L.sorted_xyz = off; off = align_up(off + n * 12, 256);
+    L.sorted_idx = off; off = align_up(off + n * 4, 256);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (const unsigned *)nullptr, (unsigned *)nullptr, (long long)n, 0, 64);
+    L.cub_bytes = tb;
+    L.cub_temp = off; off = align_up(off + tb, 256);
+    L.total = off;
+    return L;
+}
+
+int km_sort_cloud(const float *xyz, int B, int per_cloud, unsigned char *ws, const KmLayout &L, const int *bbox,
+                  cudaStream_t st) {
+    const long long n = (long long)B * per_cloud;
+    unsigned long long *keys_in = (unsigned long long *)(ws + L.keys_in), *keys_out = (unsigned long long *)(ws + L.keys_out);
+    unsigned *vals_in = (unsigned *)(ws + L.vals_in), *vals_out = (unsigned *)(ws + L.vals_out);
+    const unsigned blocks = (unsigned)ceil_div_ll(n, 256);
+    km_keys_kernel<<<blocks, 256, 0, st>>>(xyz, per_cloud, n, bbox, keys_in, vals_in);
+    PP_LAUNCH_CHECK();
+    int batch_bits = 1;
+    while ((1 << batch_bits) < B) batch_bits++;
+    size_t tb = L.cub_bytes;
+    PP_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub_temp, tb, keys_in, keys_out, vals_in, vals_out, n, 0,
+                                            32 + batch_bits, st));
+    km_gather_kernel<<<blocks, 256, 0, st>>>(xyz, vals_out, per_cloud, n, (float *)(ws + L.sorted_xyz),
+                                             (int *)(ws + L.sorted_idx));
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+}  // namespace
+
+size_t knn_morton_workspace_bytes(int B, int M, int N) {
+    const size_t n = (size_t)B * (size_t)(M > N ? M : N);
+    return 2 * km_layout(n).total + 256;
+}
+
+// Returns PP_OK after launching everything, or a negative/positive error.
+int knn_morton_launch(const float *query, const float *points, int B, int M, int N, int k, float *dist, int *idx,
+                      void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    const size_t n = (size_t)B * (size_t)(M > N ? M : N);
+    const KmLayout L = km_layout(n);
+    unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    if (workspace == nullptr || (size_t)(ws - (unsigned char *)workspace) + 2 * L.total > workspace_bytes) {
+        set_error("knn: workspace %zu < %zu bytes", workspace_bytes, 2 * L.total + 256);
+        return PP_ENOSPC;
+    }
+    unsigned char *wsP = ws, *wsQ = ws + L.total;
+    int *bbox = (int *)(wsP + L.bbox);
+    // bbox over both clouds: min <- big positive ints (0x7f7f7f7f), max <- big negative (0x80808080)
+    PP_CUDA(cudaMemsetAsync(bbox, 0x7f, 3 * sizeof(int), st));
+    PP_CUDA(cudaMemsetAsync(bbox + 3, 0x80, 3 * sizeof(int), st));
+    const bool self = (query == points && M == N);
+    km_bbox_kernel<<<NUM_SMS_B200 * 2, 256, 0, st>>>(points, (long long)B * N, bbox);
+    PP_LAUNCH_CHECK();
+    if (!self) {
+        km_bbox_kernel<<<NUM_SMS_B200 * 2, 256, 0, st>>>(query, (long long)B * M, bbox);
+        PP_LAUNCH_CHECK();
+    }
+    int rc = km_sort_cloud(points, B, N, wsP, L, bbox, st);
+    if (rc != PP_OK) return rc;
+    if (!self) {
+        rc = km_sort_cloud(query, B, M, wsQ, L, bbox, st);
+        if (rc != PP_OK) return rc;
+    } else {
+        wsQ = wsP;
+    }
+    const float *sp = (const float *)(wsP + L.sorted_xyz), *sq = (const float *)(wsQ + L.sorted_xyz);
+    const int *spi = (const int *)(wsP + L.sorted_idx), *sqi = (const int *)(wsQ + L.sorted_idx);
+    const unsigned long long *pk = (const unsigned long long *)(wsP + L.keys_out), *qk = (const unsigned long long *)(wsQ + L.keys_out);
+    KernelTimer timer("knn", st);
+    // Two tunings of the same kernel (measured on B200, k=16): small clouds sweep few points per
+    // candidate, so selection dominates -> deeper candidate buffers and the cheaper
+    // distances-only insertion with a tie pre-check (1.39 vs 1.51 ms at B=32 N=8192); large
+    // clouds live in the hot loop, where the leaner full-key-only variant wins (18.6 vs 20.6 ms
+    // at B=4 N=131072).
+    const bool small = get_option("knn_small_tuning", N <= 32768 ? 1 : 0) != 0;
+#define KM_LAUNCH(KK, QQ)                                                                                   \
+    do {                                                                                                    \
+        dim3 grid(ceil_div(M, KM_THREADS * QQ), B);                                                         \
+        if (small)                                                                                          \
+            knn_morton_kernel<KK, QQ, 16, true><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, M, N, k, dist, idx); \
+        else                                                                                                \
+            knn_morton_kernel<KK, QQ, 8, false><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, M, N, k, dist, idx); \
+    } while (0)
+    if (k <= 8) KM_LAUNCH(8, 2);
+    else if (k <= 16) KM_LAUNCH(16, 2);
+    else KM_LAUNCH(32, 1);
+#undef KM_LAUNCH
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+}  // namespace pp

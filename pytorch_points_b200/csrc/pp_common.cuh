@@ -15,6 +15,11 @@ constexpr int NUM_SMS_B200 = 148;
 void set_error(const char *fmt, ...);
 int get_option(const char *name, int dflt);
 
+// knn_morton.cu
+size_t knn_morton_workspace_bytes(int B, int M, int N);
+int knn_morton_launch(const float *query, const float *points, int B, int M, int N, int k, float *dist,
+                      int *idx, void *workspace, size_t workspace_bytes, cudaStream_t st);
+
 // Optional per-kernel timing (option "timing" = 1): CUDA events recorded on the launching
 // stream right around one kernel; read back with pp_timing_collect().  Used by bench.py to
 // measure the dominant kernel's duration without a profiler.
@@ -74,7 +79,7 @@ struct DeviceGuard {
         }                                                                                     \
     } while (0)
 
-static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------

@@ -375,6 +375,26 @@ def test_knn_bit_exact(pp, oracle_mod, B, M, N, k, maker):
     assert np.array_equal(np32(nn), np.take_along_axis(np32(p)[:, None], ei[..., None].astype(np.int64), 2))
 
 
+@pytest.mark.parametrize("maker,M,N,k", [(uniform_cloud, 700, 5000, 16), (lattice_cloud, 600, 4500, 16),
+                                          (sphere_cloud, 300, 6000, 32), (uniform_cloud, 513, 4097, 5)])
+def test_knn_morton_sweep_matches_oracle(pp, oracle_mod, maker, M, N, k):
+    """Spatially ordered sweep (forced on): same (distance, original index) order, bit for bit,
+    including exact ties (lattice) and query != points."""
+    from pytorch_points_b200 import _C
+    p = maker(2, N, 70)
+    q = maker(2, M, 71)
+    ed, ei = oracle_mod.knn(k, np32(q), np32(p))
+    _C.set_option("knn_morton", 1)
+    try:
+        _, idx, dist = pp.group_knn(k, dev(q), dev(p), NCHW=False)
+        _, idx_s, dist_s = pp.group_knn(k, dev(p), dev(p), NCHW=False)   # self-KNN shares the sort
+    finally:
+        _C.set_option("knn_morton", -1)
+    assert np.array_equal(np32(idx), ei) and np.array_equal(np32(dist), ed)
+    ed2, ei2 = oracle_mod.knn(k, np32(p[:1, :800]), np32(p[:1]))
+    assert np.array_equal(np32(idx_s[:1, :800]), ei2) and np.array_equal(np32(dist_s[:1, :800]), ed2)
+
+
 def test_knn_shared_list_kernel_matches(pp, oracle_mod):
     from pytorch_points_b200 import _C
     p = with_duplicates(uniform_cloud(2, 3000, 60), 0.2)

@@ -10,7 +10,11 @@ def t(fn, iters=5):
         e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return sorted(ts)[len(ts)//2]
-for (B,N,it) in [(2,2048,5),(32,8192,5),(4,131072,2)]:
+for (B,N,it) in [(2,2048,5),(32,8192,5),(4,131072,3)]:
     p = uniform_cloud(B,N,4).cuda()
-    ms = t(lambda: sampling.knn(16,p,p), it)
-    print("knn k16 B%d N%d: %.3f ms  %.3g pairs/s" % (B,N,ms,B*N*N/ms*1e3), flush=True)
+    for morton in (0, 1):
+        for deep in ((0, 1) if morton else (0,)):
+          for lex in ((0, 1) if morton else (0,)):
+            _C.set_option("knn_morton", morton); _C.set_option("knn_deep_buffers", deep); _C.set_option("knn_lex_only", lex)
+            ms = t(lambda: sampling.knn(16,p,p), it)
+            print("knn k16 B%d N%d morton=%d deep=%d lexonly=%d: %.3f ms  %.3g pairs/s" % (B,N,morton,deep,lex,ms,B*N*N/ms*1e3), flush=True)
