@@ -56,7 +56,7 @@ __device__ __forceinline__ void publish_column_min(int lane, int leader, unsigne
         : "memory");
 }
 
-template <int Q, int THREADS, int RB, int MINB>
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE>
 __global__ void __launch_bounds__(THREADS, MINB)
 chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int N, int M,
                    unsigned long long *__restrict__ key1, unsigned long long *__restrict__ key2,
@@ -123,8 +123,32 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
             granule[q] = ref_begin / CH_GR;
         }
 
+        // Warp w starts its sweep over the resident points at offset w*RB/WARPS and wraps: at any
+        // moment the warps of a CTA work on DIFFERENT resident points, so each point meets the
+        // CTA's warps one after the other and the filter a warp sees already contains what the
+        // previous warps found (fewer publishes).  The row side stays exact: when the sweep wraps
+        // to index 0 the row minima found so far are published and tracking restarts -- the
+        // packed (value, granule) RED.MIN resolves ties towards the lower granule.
+        constexpr int WARPS = THREADS / 32;
+        const int rot = ROTATE ? __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5) * (RB / WARPS), 0) : 0;
 #pragma unroll 1
-        for (int jj = 0; jj < RB; jj += 4) {
+        for (int step = 0; step < RB; step += 4) {
+            int jj = step + rot;
+            if (ROTATE && jj >= RB) {
+                jj -= RB;
+                if (jj == 0) {  // wrap point (warp-uniform): publish and restart the row tracking
+#pragma unroll
+                    for (int q = 0; q < Q; q++) {
+                        const int i = q0 + q;
+                        if (i < q_end)
+                            atomicMin(k1 + i, ((unsigned long long)__float_as_uint(best[q]) << 32) |
+                                                  (unsigned)granule[q]);
+                        best[q] = PP_INF;
+                        prev[q] = PP_INF;
+                        granule[q] = ref_begin / CH_GR;
+                    }
+                }
+            }
             const float4 X = *reinterpret_cast<const float4 *>(sX + jj);
             const float4 Y = *reinterpret_cast<const float4 *>(sY + jj);
             const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj);
@@ -436,7 +460,7 @@ extern "C" size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M) {
     return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M);
 }
 
-template <int Q, int THREADS, int RB, int MINB>
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true>
 static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                               unsigned long long *key1, unsigned long long *key2, float *dist1,
                               float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st) {
@@ -455,7 +479,7 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     dim3 grid(ref_blocks, B, splits);
     {
         KernelTimer timer("chamfer_fwd", st);
-        chamfer_fwd_kernel<Q, THREADS, RB, MINB><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
+        chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
                                                                    queries_per_split);
     }
     PP_LAUNCH_CHECK();
@@ -545,6 +569,8 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
         case 10: return launch_chamfer_fwd<8, 128, 128, 6>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 11: return launch_chamfer_fwd<8, 256, 256, 3>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 12: return launch_chamfer_fwd<4, 128, 256, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 13: return launch_chamfer_fwd<8, 128, 256, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 14: return launch_chamfer_fwd<8, 128, 128, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         default: break;
     }
     set_error("chamfer_fwd: unknown variant %d", pick);
