@@ -246,12 +246,45 @@ def main():
             dist.all_reduce(sums)
         losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
 
+    from pytorch_points_b200.pipeline import HostPrefetcher
+    prefetcher = HostPrefetcher(dev, depth=2)
+    prefetcher.prefetch((a_host, b_host))
+    sums_host = torch.zeros(2).pin_memory()
+    e_g1, e_g2 = torch.empty_like(a), torch.empty_like(b)
+
     def step_e2e():
+        """Plugin-level step with HOST buffers: the reference-shaped `_ext.losses` calls (the drop-in
+        boundary) fed from pinned host memory.  Inputs of THIS step were enqueued on the copy stream
+        during the previous step; the next step's copies are enqueued now so that they overlap
+        this step's kernels.  Ends with a device->host read of the step's result (the loss)."""
+        xd, yd = prefetcher.get()
+        prefetcher.prefetch((a_host, b_host))
+        losses.nmdistance_forward(xd, yd, d1, d2, i1, i2, sums=sums)
+        if world > 1:
+            dist.all_reduce(sums)
+        losses.nmdistance_backward_uniform(xd, yd, e_g1, e_g2, gw, i1, i2)
+        prefetcher.release()
+        sums_host.copy_(sums, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(sums_host[0]) / (total_B * N) + float(sums_host[1]) / (total_B * M)
+
+    graphed = None
+    if world == 1:
+        from pytorch_points_b200.pipeline import GraphedChamferStep
+        graphed = GraphedChamferStep([(a_host, b_host)], total_batch=total_B, device=dev)
+
+    def step_e2e_graph():
+        """The whole step (H2D x2 from pinned host, forward, backward, D2H of the loss sums) as one
+        CUDA-graph replay followed by the host read of the loss."""
+        return graphed.run()
+
+    def step_e2e_autograd():
+        """Same step through the autograd API a PyTorch user calls."""
         x = a_host.to(dev, non_blocking=True).requires_grad_(True)
         y = b_host.to(dev, non_blocking=True).requires_grad_(True)
         loss = sharded_chamfer_loss(x, y, total_batch=total_B)
         loss.backward()
-        return loss.item()  # device -> host read of the step's result
+        return loss.item()
 
     def barrier():
         if world > 1:
@@ -278,10 +311,38 @@ def main():
             total_ms = float(t.item())
         return total_ms / steps
 
+    def timed_e2e(step, steps, warmup, stream_sync=None):
+        """One timed region over all K steps (every step's inputs arrive fresh over PCIe, so there is
+        nothing to flush): CUDA events on the current stream, every step ends with a host read."""
+        for _ in range(warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms / steps
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_step = timed(step_device, args.steps, args.warmup)
-    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e_plugin = timed_e2e(step_e2e, args.steps, args.warmup)
+    ms_e2e_autograd = timed_e2e(step_e2e_autograd, min(args.steps, 50), 3)
+    if graphed is not None:
+        ms_e2e = timed_e2e(step_e2e_graph, args.steps, args.warmup)
+        e2e_api = ("pipeline.GraphedChamferStep.run(): compute graph (pp_chamfer_fwd + finalize with fused loss sums, "
+                   "pp_chamfer_bwd_uniform, D2H of the sums) on one stream, copy graph (H2D of the NEXT step's two clouds "
+                   "from pinned host) on a second stream, then sync + host read of the loss")
+        loss_graph = step_e2e_graph()
+    else:
+        ms_e2e, e2e_api, loss_graph = ms_e2e_plugin, "see plugin_api (CUDA-graph step is single-GPU only)", None
     # separate short pass with the library's per-kernel CUDA events switched on, so the event
     # records do not perturb the two timed legs above
     _C.set_option("timing", 1)
@@ -341,12 +402,17 @@ def main():
                    "global_batch": total_B, "l2": "flushed between timed steps (256 MiB write); inputs 1.9 MB < L2",
                    "timing": "per-step CUDA events on the current stream, max over ranks"},
         "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3), "unit": "point-pairs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": world * (a_host.numel() + b_host.numel()) * 4, "d2h_bytes_per_step": world * 4,
-                "api": "pytorch_points_b200.dist.sharded_chamfer_loss (autograd, fused chamfer_sums) + loss.backward() + loss.item(), pinned host inputs"},
+                "h2d_bytes_per_step": world * (a_host.numel() + b_host.numel()) * 4, "d2h_bytes_per_step": world * 8,
+                "api": e2e_api,
+                "plugin_api": {"value": pairs_per_step / (ms_e2e_plugin * 1e-3), "ms_per_step": ms_e2e_plugin,
+                               "api": "pipeline.HostPrefetcher (pinned host -> device, double buffered) + _ext.losses.nmdistance_forward / "
+                                      "nmdistance_backward_uniform (the reference-shaped plugin boundary) + D2H of the loss sums"},
+                "autograd_api": {"value": pairs_per_step / (ms_e2e_autograd * 1e-3), "ms_per_step": ms_e2e_autograd,
+                                 "api": "host .to(device) + dist.sharded_chamfer_loss (torch.autograd) + loss.backward() + loss.item()"}, "timing": "one CUDA-event region over all K steps; every step copies its inputs from pinned host memory and ends with a host read of the loss"},
         "gpu_launches": 4 * args.steps,
         "gpu_launches_note": "per step: chamfer_fwd_kernel, chamfer_finalize_kernel, chamfer_bwd_kernel<0>, <1>",
         "clocks": clocks, "roofline": roofline,
-        "loss": {"device_leg": loss_dev, "e2e_leg": loss_e2e},
+        "loss": {"device_leg": loss_dev, "e2e_plugin_leg": loss_e2e, "e2e_graph_leg": loss_graph},
     }
 
     if world == 1 and not args.no_cpu_baseline:

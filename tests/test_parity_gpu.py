@@ -184,6 +184,32 @@ def test_sharded_loss_single_rank_on_gpu(pp):
     assert_grad_close(np32(b.grad), np32(b2.grad), "sharded grad b")
 
 
+def test_graphed_chamfer_step_and_prefetcher(pp):
+    """CUDA-graph step (pipeline.GraphedChamferStep) and the host prefetcher give the same loss and
+    gradients as the plain autograd path, also when the two host buffer sets hold different data."""
+    from pytorch_points_b200.pipeline import GraphedChamferStep, HostPrefetcher
+    pairs = [(uniform_cloud(4, 600, 80 + i).pin_memory(), uniform_cloud(4, 500, 90 + i).pin_memory()) for i in range(2)]
+    step = GraphedChamferStep(pairs)
+    for it in range(4):
+        a0, b0 = pairs[it % 2]
+        loss = step.run()
+        torch.cuda.synchronize()
+        a, b = dev(a0).requires_grad_(True), dev(b0).requires_grad_(True)
+        d1, d2, i1, i2 = pp.nndistance(a, b)
+        ref = d1.mean() + d2.mean()
+        ref.backward()
+        assert abs(loss - ref.item()) <= 1e-6 * abs(ref.item())
+        assert torch.equal(step.idx1, i1) and torch.equal(step.idx2, i2)
+        assert_grad_close(np32(step.grad1), np32(a.grad), "graph grad1")
+        assert_grad_close(np32(step.grad2), np32(b.grad), "graph grad2")
+    pf = HostPrefetcher("cuda:0")
+    pf.prefetch(pairs[0]); pf.prefetch(pairs[1])
+    x0, y0 = pf.get(); pf.release()
+    x1, y1 = pf.get(); pf.release()
+    torch.cuda.synchronize()
+    assert torch.equal(x0.cpu(), pairs[0][0]) and torch.equal(y1.cpu(), pairs[1][1])
+
+
 def test_labeled_chamfer(pp, oracle_mod):
     a, b = uniform_cloud(2, 700, 27), uniform_cloud(2, 900, 28)
     g = torch.Generator().manual_seed(29)
