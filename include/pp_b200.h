@@ -162,6 +162,17 @@ int pp_knn(const float *query, const float *points, int B, int M, int N, int c, 
 int pp_three_nn(const float *unknown, const float *known, int B, int N, int M, float *dist2,
                 int32_t *idx, int device, void *stream);
 
+/*
+ * three_interpolate forward / backward ("next" row N3).  Replace sampling.three_interpolate_wrapper /
+ * three_interpolate_grad_wrapper (_ext/sampling.cpp:176-203,214-215 -> _ext/interpolate_gpu.cu:77-160).
+ *   points (B,C,M), idx (B,N,3), weight (B,N,3) -> out (B,C,N) = sum_k weight[k] * points[idx[k]];
+ *   backward ACCUMULATES into grad_points (B,C,M) (caller zero-fills, network/pointnet2_utils.py:81).
+ */
+int pp_three_interpolate_fwd(const float *points, const int32_t *idx, const float *weight, int B, int C,
+                             int M, int N, float *out, int device, void *stream);
+int pp_three_interpolate_bwd(const float *grad_out, const int32_t *idx, const float *weight, int B, int C,
+                             int N, int M, float *grad_points, int device, void *stream);
+
 /* ------------------------------------------------------------- diagnostics */
 
 /*

@@ -188,3 +188,26 @@ def three_nn(unknown, known):
     i = np.empty((B, N, 3), np.int32)
     lib().oracle_three_nn(u, kn, B, N, M, d.ctypes.data_as(_f32p), i.ctypes.data_as(_i32p))
     return d, i
+
+
+def three_interpolate_fwd(features, idx, weight):
+    """features (B,C,M), idx (B,N,3), weight (B,N,3) -> (B,C,N).  interpolate_gpu.cu:77-97"""
+    features, p = _f(features)
+    idx, j = _i(idx)
+    weight, w = _f(weight)
+    B, C, M = features.shape
+    N = idx.shape[1]
+    out = np.empty((B, C, N), np.float32)
+    lib().oracle_three_interpolate_fwd(p, j, w, B, C, M, N, out.ctypes.data_as(_f32p))
+    return out
+
+
+def three_interpolate_bwd(grad_out, idx, weight, M):
+    """grad_out (B,C,N) -> grad_features (B,C,M).  interpolate_gpu.cu:120-142"""
+    grad_out, p = _f(grad_out)
+    idx, j = _i(idx)
+    weight, w = _f(weight)
+    B, C, N = grad_out.shape
+    g = np.empty((B, C, M), np.float32)
+    lib().oracle_three_interpolate_bwd(p, j, w, B, C, N, M, g.ctypes.data_as(_f32p))
+    return g

@@ -413,4 +413,39 @@ int oracle_three_nn(const float *unknown, const float *known, int B, int N, int 
     return 1;
 }
 
+/* three_interpolate fwd/bwd ("next" row N3). _ext/interpolate_gpu.cu:77-97,120-142.
+ * w0*p0 + w1*p1 + w2*p2 is contracted by nvcc to fma(w2,p2, fma(w0,p0, rn(w1*p1))) -- middle
+ * product first, like the 3-term distances; pinned by tests/golden/three_interpolate.npz. */
+int oracle_three_interpolate_fwd(const float *points, const int32_t *idx, const float *weight, int B, int C,
+                                 int M, int N, float *out)
+{
+    for (int b = 0; b < B; b++)
+        for (int c = 0; c < C; c++)
+            for (int i = 0; i < N; i++) {
+                const int32_t *id = idx + ((size_t)b * N + i) * 3;
+                const float *w = weight + ((size_t)b * N + i) * 3;
+                const float *p = points + ((size_t)b * C + c) * M;
+                out[((size_t)b * C + c) * N + i] = fmaf(w[2], p[id[2]], fmaf(w[0], p[id[0]], w[1] * p[id[1]]));
+            }
+    return 1;
+}
+
+int oracle_three_interpolate_bwd(const float *grad_out, const int32_t *idx, const float *weight, int B, int C,
+                                 int N, int M, float *grad_points)
+{
+    memset(grad_points, 0, sizeof(float) * (size_t)B * C * M);
+    for (int b = 0; b < B; b++)
+        for (int c = 0; c < C; c++)
+            for (int i = 0; i < N; i++) {
+                const int32_t *id = idx + ((size_t)b * N + i) * 3;
+                const float *w = weight + ((size_t)b * N + i) * 3;
+                float *g = grad_points + ((size_t)b * C + c) * M;
+                const float go = grad_out[((size_t)b * C + c) * N + i];
+                g[id[0]] += go * w[0];
+                g[id[1]] += go * w[1];
+                g[id[2]] += go * w[2];
+            }
+    return 1;
+}
+
 int oracle_version(void) { return 1; }

@@ -124,6 +124,30 @@ def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
     _C.check(rc, "pp_three_nn")
 
 
+def three_interpolate_wrapper(b, c, m, n, points, idx, weight, out):
+    """sampling.three_interpolate_wrapper(B, c, m, n, points (B,c,m), idx (B,n,3), weight (B,n,3), out (B,c,n))
+    (_ext/sampling.cpp:176-188,214)."""
+    dev = _C.require_cuda(points, idx, weight, out)
+    _C.require_contiguous(points, idx, weight, out)
+    _check(idx.dtype == torch.int32, "three_interpolate: idx must be int32")
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_three_interpolate_fwd(_C.ptr(points), _C.ptr(idx), _C.ptr(weight), b, c, m, n, _C.ptr(out),
+                                             dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_three_interpolate_fwd")
+
+
+def three_interpolate_grad_wrapper(b, c, n, m, grad_out, idx, weight, grad_points):
+    """sampling.three_interpolate_grad_wrapper(B, c, n, m, grad_out (B,c,n), idx, weight, grad_points (B,c,m))
+    (_ext/sampling.cpp:190-203,215); accumulates into grad_points."""
+    dev = _C.require_cuda(grad_out, idx, weight, grad_points)
+    _C.require_contiguous(grad_out, idx, weight, grad_points)
+    _check(idx.dtype == torch.int32, "three_interpolate_grad: idx must be int32")
+    with torch.cuda.device(dev):
+        rc = _C.lib.pp_three_interpolate_bwd(_C.ptr(grad_out), _C.ptr(idx), _C.ptr(weight), b, c, n, m,
+                                             _C.ptr(grad_points), dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_three_interpolate_bwd")
+
+
 def knn(k, query, points):
     """group_knn core (no reference counterpart): query (B,M,c), points (B,N,c)
     -> dist (B,M,k) ascending squared distances, idx (B,M,k) int32."""

@@ -424,6 +424,46 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
     }
 }
 
+// ===========================================================================
+// three_interpolate forward / backward (_ext/interpolate_gpu.cu:77-97,120-142): flat
+// one-element-per-thread kernels.  Forward rounding order = what nvcc makes of
+// w0*p0 + w1*p1 + w2*p2:  fma(w2,p2, fma(w0,p0, rn(w1*p1)))  -- middle product first, the same
+// pattern as the 3-term distances (verified bit for bit against the reference kernel).
+// ===========================================================================
+__global__ void __launch_bounds__(256)
+three_interpolate_fwd_kernel(const float *__restrict__ points, const int *__restrict__ idx,
+                             const float *__restrict__ weight, int C, int M, int N, long long total,
+                             float *__restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int i = (int)(t % N);
+    const long long bc = t / N;  // b*C + c
+    const int b = (int)(bc / C);
+    const int *id = idx + ((size_t)b * N + i) * 3;
+    const float *w = weight + ((size_t)b * N + i) * 3;
+    const float *p = points + bc * M;
+    out[t] = __fmaf_rn(__ldg(w + 2), __ldg(p + __ldg(id + 2)),
+                       __fmaf_rn(__ldg(w), __ldg(p + __ldg(id)), __fmul_rn(__ldg(w + 1), __ldg(p + __ldg(id + 1)))));
+}
+
+__global__ void __launch_bounds__(256)
+three_interpolate_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx,
+                             const float *__restrict__ weight, int C, int M, int N, long long total,
+                             float *__restrict__ grad_points) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int i = (int)(t % N);
+    const long long bc = t / N;
+    const int b = (int)(bc / C);
+    const int *id = idx + ((size_t)b * N + i) * 3;
+    const float *w = weight + ((size_t)b * N + i) * 3;
+    float *g = grad_points + bc * M;
+    const float go = __ldg(grad_out + t);
+    atomicAdd(g + __ldg(id), __fmul_rn(go, __ldg(w)));
+    atomicAdd(g + __ldg(id + 1), __fmul_rn(go, __ldg(w + 1)));
+    atomicAdd(g + __ldg(id + 2), __fmul_rn(go, __ldg(w + 2)));
+}
+
 template <int P, int C>
 int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
                        int bs_log2, cudaStream_t st, int *max_clusters) {
@@ -627,6 +667,32 @@ extern "C" int pp_three_nn(const float *unknown, const float *known, int B, int 
     PP_CUDA(guard.err);
     dim3 grid(ceil_div(N, 256), B);
     three_nn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(unknown, known, N, M, dist2, idx);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_three_interpolate_fwd(const float *points, const int32_t *idx, const float *weight, int B,
+                                        int C, int M, int N, float *out, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && C >= 0 && M >= 0 && N >= 0, "three_interpolate_fwd: bad sizes");
+    const long long total = (long long)B * C * N;
+    if (total == 0) return PP_OK;
+    PP_REQUIRE(points && idx && weight && out && M > 0, "three_interpolate_fwd: null pointer or empty source");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    three_interpolate_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(points, idx, weight, C, M, N, total, out);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_three_interpolate_bwd(const float *grad_out, const int32_t *idx, const float *weight, int B,
+                                        int C, int N, int M, float *grad_points, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && C >= 0 && M >= 0 && N >= 0, "three_interpolate_bwd: bad sizes");
+    const long long total = (long long)B * C * N;
+    if (total == 0) return PP_OK;
+    PP_REQUIRE(grad_out && idx && weight && grad_points && M > 0, "three_interpolate_bwd: null pointer or empty target");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    three_interpolate_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, weight, C, M, N, total, grad_points);
     PP_LAUNCH_CHECK();
     return PP_OK;
 }

@@ -5,3 +5,4 @@ from .model_loss import (NmDistanceFunction, LabeledNmdistanceFunction, nndistan
 from .geo_operations import FurthestPointSampling, furthest_point_sample  # noqa: F401
 from .operations import (GatherFunction, gather_points, BallQuery, ball_query, GroupingOperation,  # noqa: F401
                          grouping_operation, QueryAndGroup, group_knn, knn_points)
+from .pointnet2_utils import ThreeNN, three_nn, ThreeInterpolate, three_interpolate  # noqa: F401

@@ -138,6 +138,19 @@ def main(out_dir):
     rs.three_nn_wrapper(2, 777, 1300, u.cuda().contiguous(), k.cuda().contiguous(), d, i)
     torch.cuda.synchronize()
     np.savez_compressed(os.path.join(out_dir, "three_nn.npz"), unknown=n(u), known=n(k), dist2=n(d), idx=n(i))
+    # ---- three_interpolate (weights as pointnet2_modules.py:131-135 builds them)
+    dist = torch.sqrt(d)
+    w = 1.0 / (dist + 1e-8)
+    w = (w / w.sum(dim=2, keepdim=True)).contiguous()
+    feats = uniform_cloud(2, 1300, 142, c=6).transpose(1, 2).contiguous().cuda()
+    out = torch.empty(2, 6, 777, device="cuda")
+    rs.three_interpolate_wrapper(2, 6, 1300, 777, feats, i, w, out)
+    gout = uniform_cloud(2, 777, 143, c=6).transpose(1, 2).contiguous().cuda()
+    gin = torch.zeros(2, 6, 1300, device="cuda")
+    rs.three_interpolate_grad_wrapper(2, 6, 777, 1300, gout, i, w, gin)
+    torch.cuda.synchronize()
+    np.savez_compressed(os.path.join(out_dir, "three_interpolate.npz"), features=n(feats), idx=n(i), weight=n(w),
+                        out=n(out), grad_out=n(gout), grad_in=n(gin))
     print("golden vectors written to", out_dir, sorted(os.listdir(out_dir)))
 
 

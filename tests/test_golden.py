@@ -76,6 +76,14 @@ def test_oracle_three_nn_matches_reference(oracle_mod):
     assert np.array_equal(i, g["idx"]) and np.array_equal(d, g["dist2"])
 
 
+def test_oracle_three_interpolate_matches_reference(oracle_mod):
+    g = load("three_interpolate")
+    out = oracle_mod.three_interpolate_fwd(g["features"], g["idx"], g["weight"])
+    assert np.array_equal(out.view(np.uint32), g["out"].view(np.uint32))
+    gin = oracle_mod.three_interpolate_bwd(g["grad_out"], g["idx"], g["weight"], g["features"].shape[2])
+    assert rel_err(gin, g["grad_in"]) <= 1e-5
+
+
 # ------------------------------------------------------------------ our kernels vs reference (GPU)
 @pytest.fixture(scope="module")
 def pp():
@@ -129,3 +137,19 @@ def test_kernels_ball_query_match_reference(pp, name):
     assert np.array_equal(idx.cpu().numpy(), g["idx"])
     feats = cu(g["xyz"].transpose(0, 2, 1))
     assert np.array_equal(pp.grouping_operation(feats, idx).cpu().numpy(), g["grouped"])
+
+
+@pytest.mark.gpu
+def test_kernels_three_nn_interpolate_match_reference(pp):
+    import torch
+    g3 = load("three_nn")
+    dist, idx = pp.three_nn(cu(g3["unknown"]), cu(g3["known"]))
+    assert np.array_equal(idx.cpu().numpy(), g3["idx"])
+    assert np.array_equal((dist * dist).cpu().numpy().round(6).shape, g3["dist2"].shape)
+    assert np.array_equal(dist.cpu().numpy(), np.sqrt(g3["dist2"]))
+    g = load("three_interpolate")
+    f = cu(g["features"]).requires_grad_(True)
+    out = pp.three_interpolate(f, cu(g["idx"]), cu(g["weight"]))
+    assert np.array_equal(out.detach().cpu().numpy(), g["out"])
+    out.backward(cu(g["grad_out"]))
+    assert rel_err(f.grad.cpu().numpy(), g["grad_in"]) <= 1e-5

@@ -473,6 +473,51 @@ def test_three_nn(pp, oracle_mod):
     assert np.array_equal(np32(i), ei) and np.array_equal(np32(d), ed)
 
 
+def test_three_interpolate(pp, oracle_mod):
+    u, k = uniform_cloud(2, 500, 50), uniform_cloud(2, 300, 51)
+    dist, idx = pp.three_nn(dev(u), dev(k))
+    w = 1.0 / (dist + 1e-8)
+    w = (w / w.sum(dim=2, keepdim=True)).contiguous()
+    f = uniform_cloud(2, 300, 52, c=5).transpose(1, 2).contiguous()
+    fd = dev(f).requires_grad_(True)
+    out = pp.three_interpolate(fd, idx, w)
+    assert np.array_equal(np32(out), oracle_mod.three_interpolate_fwd(np32(f), np32(idx), np32(w)))
+    go = uniform_cloud(2, 500, 53, c=5).transpose(1, 2).contiguous()
+    out.backward(dev(go))
+    assert_grad_close(np32(fd.grad), oracle_mod.three_interpolate_bwd(np32(go), np32(idx), np32(w), 300), "interp grad")
+
+
+def test_pointnet2_sa_and_fp_stage_end_to_end(pp):
+    """the PointNet++ set-abstraction stage of the reference
+    (network/pointnet2_modules.py:21-54: FPS -> gather -> ball_query -> group -> shared MLP -> max
+    pool) followed by a feature-propagation stage (:115-153: three_nn -> three_interpolate -> MLP),
+    written against OUR ops exactly the way the reference's modules call theirs; forward and
+    backward run and the gradient reaches the input features and the MLP weights."""
+    torch.manual_seed(0)
+    B, N, C, npoint = 2, 2048, 8, 256
+    xyz = dev(uniform_cloud(B, N, 54))
+    feats = dev(uniform_cloud(B, N, 55, c=C)).transpose(1, 2).contiguous().requires_grad_(True)
+    mlp = torch.nn.Sequential(torch.nn.Conv2d(C + 3, 16, 1), torch.nn.ReLU(), torch.nn.Conv2d(16, 32, 1)).cuda()
+    fp_mlp = torch.nn.Sequential(torch.nn.Conv1d(32 + C, 16, 1), torch.nn.ReLU()).cuda()
+    # --- SA stage
+    xyz_flipped = xyz.transpose(1, 2).contiguous()
+    idx = pp.furthest_point_sample(xyz, npoint, NCHW=False)[0]
+    new_xyz = pp.gather_points(xyz_flipped, idx).transpose(1, 2).contiguous()
+    grouped = pp.QueryAndGroup(0.2, 16)(xyz, new_xyz, feats)            # (B, C+3, npoint, nsample)
+    new_feats = torch.nn.functional.max_pool2d(mlp(grouped), kernel_size=[1, grouped.size(3)]).squeeze(-1)
+    assert new_xyz.shape == (B, npoint, 3) and new_feats.shape == (B, 32, npoint)
+    # --- FP stage: propagate the 256 coarse features back to the 2048 points
+    dist, nn_idx = pp.three_nn(xyz, new_xyz)
+    w = 1.0 / (dist + 1e-8)
+    w = w / torch.sum(w, dim=2, keepdim=True)
+    interp = pp.three_interpolate(new_feats.contiguous(), nn_idx, w.contiguous())
+    out = fp_mlp(torch.cat([interp, feats], dim=1))
+    assert out.shape == (B, 16, N)
+    out.square().mean().backward()
+    assert feats.grad is not None and torch.isfinite(feats.grad).all() and feats.grad.abs().sum() > 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in mlp.parameters())
+
+
 # --------------------------------------------------------------------------- full-size properties
 def test_chamfer_target_shape_properties(pp, oracle_mod):
     """B=32, N=M=8192 (north-star target) is too big for the CPU oracle inside a unit test:

@@ -157,3 +157,24 @@ def test_three_nn_three_way(ref, oracle_mod):
     assert torch.equal(d2, d) and torch.equal(i2, i)
     od, oi = oracle_mod.three_nn(np32(u), np32(k))
     assert np.array_equal(od, np32(d)) and np.array_equal(oi, np32(i))
+
+
+def test_three_interpolate_three_way(ref, oracle_mod):
+    _, rs = ref
+    from pytorch_points_b200._ext import sampling
+    u, k = uniform_cloud(2, 600, 214), uniform_cloud(2, 900, 215)
+    d, i = sampling.three_nn(u.cuda(), k.cuda())
+    w = 1.0 / (torch.sqrt(d) + 1e-8)
+    w = (w / w.sum(dim=2, keepdim=True)).contiguous()
+    f = uniform_cloud(2, 900, 216, c=7).transpose(1, 2).contiguous().cuda()
+    want = torch.empty(2, 7, 600, device="cuda")
+    rs.three_interpolate_wrapper(2, 7, 900, 600, f, i, w, want)
+    got = torch.empty(2, 7, 600, device="cuda")
+    sampling.three_interpolate_wrapper(2, 7, 900, 600, f, i, w, got)
+    assert torch.equal(got, want)
+    assert np.array_equal(oracle_mod.three_interpolate_fwd(np32(f), np32(i), np32(w)), np32(want))
+    go = torch.rand(2, 7, 600, device="cuda")
+    g_ref = torch.zeros(2, 7, 900, device="cuda"); g_our = torch.zeros(2, 7, 900, device="cuda")
+    rs.three_interpolate_grad_wrapper(2, 7, 600, 900, go, i, w, g_ref)
+    sampling.three_interpolate_grad_wrapper(2, 7, 600, 900, go, i, w, g_our)
+    assert (g_our - g_ref).abs().max().item() <= 1e-5 * g_ref.abs().max().item()
