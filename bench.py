@@ -242,9 +242,11 @@ def main():
         # forward (+ fused partial sums) -> all-reduce of the 2 sums -> backward with the two
         # constant upstream weights d(loss)/d(dist) = 1/(B_total*N), 1/(B_total*M)
         losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
-        if world > 1:
-            dist.all_reduce(sums)
+        # the backward weights are constants, so the 8-byte all-reduce overlaps the backward
+        work = dist.all_reduce(sums, async_op=True) if world > 1 else None
         losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
+        if work is not None:
+            work.wait()
 
     from pytorch_points_b200.pipeline import HostPrefetcher
     prefetcher = HostPrefetcher(dev, depth=2)
@@ -260,10 +262,11 @@ def main():
         xd, yd = prefetcher.get()
         prefetcher.prefetch((a_host, b_host))
         losses.nmdistance_forward(xd, yd, d1, d2, i1, i2, sums=sums)
-        if world > 1:
-            dist.all_reduce(sums)
+        work = dist.all_reduce(sums, async_op=True) if world > 1 else None
         losses.nmdistance_backward_uniform(xd, yd, e_g1, e_g2, gw, i1, i2)
         prefetcher.release()
+        if work is not None:
+            work.wait()
         sums_host.copy_(sums, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(sums_host[0]) / (total_B * N) + float(sums_host[1]) / (total_B * M)
