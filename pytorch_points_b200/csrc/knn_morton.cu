@@ -133,7 +133,7 @@ __device__ __forceinline__ bool km_insert(float (&ld)[K], int (&li)[K], float d,
     return tie;
 }
 
-template <int K, int Q, int KM_CB, bool PRECHECK>
+template <int K, int Q, int KM_CB, bool PRECHECK, bool ESTIMATE>
 __global__ void __launch_bounds__(KM_THREADS)
 knn_morton_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, const unsigned long long *__restrict__ qkeys,
                   const float *__restrict__ sp, const int *__restrict__ spi, const unsigned long long *__restrict__ pkeys,
@@ -180,12 +180,13 @@ knn_morton_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, con
         if (tid == 0) s_start = min(ntiles - 1, lo / KM_TILE);
     }
 
-    float nqx[Q], nqy[Q], nqz[Q], tau[Q];
+    float nqx[Q], nqy[Q], nqz[Q], tau[Q], tau0[Q];
     int cnt[Q];
     float ld[Q][K];
     int li[Q][K];
 #pragma unroll
     for (int q = 0; q < Q; q++) {
+        tau0[q] = PP_INF;
         const int i = qbase + q * KM_THREADS + tid;
         float x = PP_INF, y = PP_INF, z = PP_INF;
         if (i < M) {
@@ -232,12 +233,68 @@ knn_morton_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, con
             float t = ld[q][0];
 #pragma unroll
             for (int s = 1; s < K; s++) t = (s < k) ? ld[q][s] : t;
-            tau[q] = t;
+            tau[q] = fminf(t, tau0[q]);
         }
     };
 
     __syncthreads();
     const int t0 = s_start;
+
+    // ---- threshold seed: a cheap UPPER BOUND tau0 on every query's k-th distance, taken from the
+    // home tile before the real sweep.  The tile is cut into G = ceil(k/2) groups; per group the
+    // two smallest distances are tracked with three FMNMX per pair; the largest "second
+    // smallest" over the groups has 2G >= k distinct points at or below it.  The sweep then
+    // starts with the filter d <= tau0 instead of d <= inf, which removes most of the warm-up
+    // candidates (the expensive part of a streaming top-k on a few thousand points).
+    if (ESTIMATE) {
+        const int tile0 = t0 * KM_TILE;
+        for (int u = tid; u < KM_TILE; u += KM_THREADS) {
+            const int j = tile0 + u;
+            float x = PP_INF, y = PP_INF, z = PP_INF;
+            if (j < N) {
+                x = __ldg(pp_ + (size_t)j * 3);
+                y = __ldg(pp_ + (size_t)j * 3 + 1);
+                z = __ldg(pp_ + (size_t)j * 3 + 2);
+            }
+            sX[u] = x; sY[u] = y; sZ[u] = z;
+        }
+        __syncthreads();
+        const int groups = (k + 1) / 2;
+        const int gsize = (KM_TILE / groups) & ~3;  // points per group, multiple of 4
+        float est[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) est[q] = 0.f;
+        for (int g = 0; g < groups; g++) {
+            float m1[Q], m2[Q];
+#pragma unroll
+            for (int q = 0; q < Q; q++) m1[q] = m2[q] = PP_INF;
+            for (int jj = g * gsize; jj < (g + 1) * gsize; jj += 4) {
+                const float4 X = *reinterpret_cast<const float4 *>(sX + jj);
+                const float4 Y = *reinterpret_cast<const float4 *>(sY + jj);
+                const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj);
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    const float2 a = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y),
+                                                 nqx[q], nqy[q], nqz[q]);
+                    const float2 c = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
+                                                 nqx[q], nqy[q], nqz[q]);
+                    const float dd[4] = {a.x, a.y, c.x, c.y};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        m2[q] = fminf(m2[q], fmaxf(m1[q], dd[r]));  // second smallest so far
+                        m1[q] = fminf(m1[q], dd[r]);                // smallest so far
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < Q; q++) est[q] = fmaxf(est[q], m2[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            tau0[q] = est[q];  // +inf when the home tile is too short: the seed is then simply unused
+            tau[q] = est[q];
+        }
+    }
     for (int s = 0; s < ntiles; s++) {
         // outward sweep: t0, t0+1, t0-1, t0+2, ... (wrapping), nearest tiles first
         int t = (s & 1) ? t0 + (s + 1) / 2 : t0 - s / 2;
@@ -409,11 +466,16 @@ int knn_morton_launch(const float *query, const float *points, int B, int M, int
 #define KM_LAUNCH(KK, QQ)                                                                                   \
     do {                                                                                                    \
         dim3 grid(ceil_div(M, KM_THREADS * QQ), B);                                                         \
-        if (small)                                                                                          \
-            knn_morton_kernel<KK, QQ, 16, true><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, M, N, k, dist, idx); \
+        if (small && est)                                                                                   \
+            knn_morton_kernel<KK, QQ, 16, true, true><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, M, N, k, dist, idx); \
+        else if (small)                                                                                     \
+            knn_morton_kernel<KK, QQ, 16, true, false><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, M, N, k, dist, idx); \
+        else if (est)                                                                                       \
+            knn_morton_kernel<KK, QQ, 8, false, true><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, M, N, k, dist, idx); \
         else                                                                                                \
-            knn_morton_kernel<KK, QQ, 8, false><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, M, N, k, dist, idx); \
+            knn_morton_kernel<KK, QQ, 8, false, false><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, M, N, k, dist, idx); \
     } while (0)
+    const bool est = get_option("knn_estimate", 1) != 0;
     if (k <= 8) KM_LAUNCH(8, 2);
     else if (k <= 16) KM_LAUNCH(16, 2);
     else KM_LAUNCH(32, 1);
