@@ -528,7 +528,51 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
             "kernel_frac_of_fp32_peak": 8.0 * B * N * N / (kms * 1e-3) / 1e12 / peak_tflops,
             "kernel_frac_of_op_mix_ceiling": float(B) * N * N / (kms * 1e-3) / pipe_pairs}
         del p
+    try:
+        out["reference_cuda_kernels"] = run_reference_cuda(dev, timeit)
+    except Exception as e:  # noqa: BLE001
+        out["reference_cuda_kernels"] = {"unavailable": repr(e)[:200]}
     return out
+
+
+def run_reference_cuda(dev, timeit):
+    """Baseline only: the reference's OWN CUDA kernels (unmodified sources compiled for sm_100a by
+    oracle/build_ref.sh into oracle/_ref/, prebuilt -- /root/reference is not read here) timed on
+    the same shapes, kernels only.  Shows what "recompile the reference for B200" gives."""
+    import torch
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "ref_losses.so")):
+        return {"unavailable": "oracle/_ref not built"}
+    sys.path.insert(0, ref_dir)
+    import ref_losses
+    import ref_sampling
+    from helpers import uniform_cloud
+    res = {}
+    for (B, N) in [(32, 2500), (32, 8192)]:
+        a, b = uniform_cloud(B, N, 1).to(dev), uniform_cloud(B, N, 2).to(dev)
+        d1 = torch.zeros(B, N, device=dev); d2 = torch.zeros(B, N, device=dev)
+        i1 = torch.zeros(B, N, dtype=torch.int32, device=dev); i2 = torch.zeros(B, N, dtype=torch.int32, device=dev)
+        gd = torch.full((B, N), 1.0 / (B * N), device=dev)
+        g1, g2 = torch.zeros_like(a), torch.zeros_like(b)
+
+        def step():
+            ref_losses.nmdistance_forward(a, b, d1, d2, i1, i2)
+            ref_losses.nmdistance_backward(a, b, g1, g2, gd, gd, i1, i2)
+        ms = timeit(step, iters=5, warm=2)
+        res["chamfer_fwd_bwd_B%d_N%d" % (B, N)] = {"ms_per_step": ms, "point_pairs_per_s": float(B) * N * N / (ms * 1e-3)}
+    x = uniform_cloud(16, 16384, 3).to(dev)
+    idx = torch.empty(16, 1024, dtype=torch.int32, device=dev)
+    temp = torch.empty(16, 16384, device=dev)
+
+    def fps_step():
+        temp.fill_(1e10)
+        ref_sampling.furthest_sampling(1024, 0, x, temp, idx)
+    ms = timeit(fps_step, iters=3, warm=1)
+    res["fps_B16_N16384_m1024"] = {"ms_per_step": ms, "samples_per_s": 16 * 1024 / (ms * 1e-3)}
+    ctr = torch.gather(x, 1, idx.long().unsqueeze(-1).expand(16, 1024, 3)).contiguous()
+    ms = timeit(lambda: ref_sampling.ball_query(ctr, x, 0.2, 32), iters=5, warm=2)
+    res["ball_query_B16_N16384_M1024_r0.2_ns32"] = {"ms_per_step": ms}
+    return res
 
 
 if __name__ == "__main__":
