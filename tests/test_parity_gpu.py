@@ -48,6 +48,8 @@ CHAMFER_CASES = [
     (2, 1000, 3000, sphere_cloud, 8),
     (2, 2048, 2048, lattice_cloud, 9),       # massive exact ties
     (1, 4097, 4099, uniform_cloud, 10),
+    (1, 20000, 17001, uniform_cloud, 11),    # one big odd-sized cloud pair: many query splits per reference block
+    (70, 300, 40, sphere_cloud, 12),         # many tiny clouds
 ]
 
 
@@ -386,6 +388,7 @@ KNN_CASES = [
     (2, 300, 700, 20, lattice_cloud),     # 16 < k <= 32: one query per thread
     (1, 200, 600, 40, lattice_cloud),     # k > 32: shared-memory list kernel
     (1, 100, 64, 64, uniform_cloud),      # k == N == PP_KNN_MAX_K
+    (1, 3000, 20001, 16, uniform_cloud),  # query != points, odd sizes, ordered-sweep path
 ]
 
 
