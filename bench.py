@@ -260,11 +260,11 @@ def main():
         during the previous step; the next step's copies are enqueued now so that they overlap
         this step's kernels.  Ends with a device->host read of the step's result (the loss)."""
         xd, yd = prefetcher.get()
-        prefetcher.prefetch((a_host, b_host))
         losses.nmdistance_forward(xd, yd, d1, d2, i1, i2, sums=sums)
         work = dist.all_reduce(sums, async_op=True) if world > 1 else None
         losses.nmdistance_backward_uniform(xd, yd, e_g1, e_g2, gw, i1, i2)
         prefetcher.release()
+        prefetcher.prefetch((a_host, b_host))  # host work hidden behind the kernels just launched
         if work is not None:
             work.wait()
         sums_host.copy_(sums, non_blocking=True)

@@ -1,5 +1,8 @@
 """Mirror of `pytorch_points._ext.losses` (_ext/nmdistance.cpp:30-34).
 
+The library switches to the tensors' device itself (DeviceGuard in csrc), so no Python-side
+device context is needed around the calls.
+
 Caller allocates every output, exactly like the reference; functions return 1 on success
 (the reference returns 1 / 0 and prints on failure -- here failures raise instead)."""
 import torch
@@ -44,10 +47,9 @@ def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None):
         raise RuntimeError("nmdistance_forward: idx tensors must be int32")
     nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
     key, ws = _workspace(dev, nbytes)
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_chamfer_fwd(_C.ptr(xyz1), _C.ptr(xyz2), B, N, M, c, _C.ptr(dist1), _C.ptr(dist2),
-                                   _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums), _C.ptr(ws), ws.numel(),
-                                   _C.PP_CHAMFER_WS_CLEAN, dev.index, _C.stream_of(dev))
+    rc = _C.lib.pp_chamfer_fwd(_C.ptr(xyz1), _C.ptr(xyz2), B, N, M, c, _C.ptr(dist1), _C.ptr(dist2),
+                               _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums), _C.ptr(ws), ws.numel(),
+                               _C.PP_CHAMFER_WS_CLEAN, dev.index, _C.stream_of(dev))
     if rc != 0:
         _workspaces.pop(key, None)  # state unknown after a failure: start from a fresh fill
     _C.check(rc, "pp_chamfer_fwd")
@@ -65,10 +67,9 @@ def labeled_nmdistance_forward(xyz1, xyz2, label1, label2, dist1, dist2, idx1, i
     M = xyz2.shape[1]
     if label1.numel() != B * N or label2.numel() != B * M:
         raise RuntimeError("labeled_nmdistance_forward: labels must be (B,N[,1]) and (B,M[,1])")
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_chamfer_labeled_fwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(label1), _C.ptr(label2), B, N, M, c,
-                                           _C.ptr(dist1), _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2),
-                                           dev.index, _C.stream_of(dev))
+    rc = _C.lib.pp_chamfer_labeled_fwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(label1), _C.ptr(label2), B, N, M, c,
+                                       _C.ptr(dist1), _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2),
+                                       dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_labeled_fwd")
     return 1
 
@@ -80,10 +81,9 @@ def nmdistance_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, id
     _check_f32(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2)
     B, N, c = xyz1.shape
     M = xyz2.shape[1]
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_chamfer_bwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(graddist1), _C.ptr(graddist2),
-                                   _C.ptr(idx1), _C.ptr(idx2), B, N, M, c, _C.ptr(gradxyz1), _C.ptr(gradxyz2),
-                                   dev.index, _C.stream_of(dev))
+    rc = _C.lib.pp_chamfer_bwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(graddist1), _C.ptr(graddist2),
+                               _C.ptr(idx1), _C.ptr(idx2), B, N, M, c, _C.ptr(gradxyz1), _C.ptr(gradxyz2),
+                               dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_bwd")
     return 1
 
@@ -99,9 +99,8 @@ def nmdistance_backward_uniform(xyz1, xyz2, gradxyz1, gradxyz2, gw, idx1, idx2):
         raise RuntimeError("nmdistance_backward_uniform: gw must hold 2 floats")
     B, N, c = xyz1.shape
     M = xyz2.shape[1]
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_chamfer_bwd_uniform(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(gw), _C.ptr(idx1), _C.ptr(idx2),
-                                           B, N, M, c, _C.ptr(gradxyz1), _C.ptr(gradxyz2), dev.index,
-                                           _C.stream_of(dev))
+    rc = _C.lib.pp_chamfer_bwd_uniform(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(gw), _C.ptr(idx1), _C.ptr(idx2),
+                                       B, N, M, c, _C.ptr(gradxyz1), _C.ptr(gradxyz2), dev.index,
+                                       _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_bwd_uniform")
     return 1

@@ -17,9 +17,8 @@ def furthest_sampling(m, seedIdx, input, temp, idx):
     _check(idx.dtype == torch.int32, "furthest_sampling: idx must be int32")
     B, N, c = input.shape
     _check(c == 3, "furthest sampling is implemented for 3D points")
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_fps(_C.ptr(input), B, N, int(m), int(seedIdx), _C.ptr(temp), _C.ptr(idx), dev.index,
-                           _C.stream_of(dev))
+    rc = _C.lib.pp_fps(_C.ptr(input), B, N, int(m), int(seedIdx), _C.ptr(temp), _C.ptr(idx), dev.index,
+                       _C.stream_of(dev))
     _C.check(rc, "pp_fps")
     return idx
 
@@ -29,9 +28,8 @@ def gather_forward(b, c, n, npoints, points, idx, out):
     dev = _C.require_cuda(points, idx, out)
     _C.require_contiguous(points, idx, out)
     _check(points.dtype == torch.float32 and idx.dtype == torch.int32, "gather_forward: float32 points, int32 idx")
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_gather_fwd(_C.ptr(points), _C.ptr(idx), b, c, n, npoints, _C.ptr(out), dev.index,
-                                  _C.stream_of(dev))
+    rc = _C.lib.pp_gather_fwd(_C.ptr(points), _C.ptr(idx), b, c, n, npoints, _C.ptr(out), dev.index,
+                              _C.stream_of(dev))
     _C.check(rc, "pp_gather_fwd")
     return 1
 
@@ -41,9 +39,8 @@ def gather_backward(b, c, n, npoints, grad_out, idx, grad_points):
     dev = _C.require_cuda(grad_out, idx, grad_points)
     _C.require_contiguous(grad_out, idx, grad_points)
     _check(grad_out.dtype == torch.float32 and idx.dtype == torch.int32, "gather_backward: float32 grads, int32 idx")
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_gather_bwd(_C.ptr(grad_out), _C.ptr(idx), b, c, n, npoints, _C.ptr(grad_points), dev.index,
-                                  _C.stream_of(dev))
+    rc = _C.lib.pp_gather_bwd(_C.ptr(grad_out), _C.ptr(idx), b, c, n, npoints, _C.ptr(grad_points), dev.index,
+                              _C.stream_of(dev))
     _C.check(rc, "pp_gather_bwd")
     return 1
 
@@ -57,9 +54,8 @@ def ball_query(new_xyz, xyz, radius, nsample):
     B, M, _ = new_xyz.shape
     N = xyz.shape[1]
     idx = torch.empty(B, M, int(nsample), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_ball_query(_C.ptr(new_xyz), _C.ptr(xyz), B, N, M, float(radius), int(nsample), _C.ptr(idx),
-                                  dev.index, _C.stream_of(dev))
+    rc = _C.lib.pp_ball_query(_C.ptr(new_xyz), _C.ptr(xyz), B, N, M, float(radius), int(nsample), _C.ptr(idx),
+                              dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_ball_query")
     return idx
 
@@ -74,9 +70,8 @@ def group_points(points, idx):
     B, C, N = points.shape
     _, npoint, nsample = idx.shape
     out = torch.empty(B, C, npoint, nsample, dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_group_fwd(_C.ptr(points), _C.ptr(idx), B, C, N, npoint, nsample, _C.ptr(out), dev.index,
-                                 _C.stream_of(dev))
+    rc = _C.lib.pp_group_fwd(_C.ptr(points), _C.ptr(idx), B, C, N, npoint, nsample, _C.ptr(out), dev.index,
+                             _C.stream_of(dev))
     _C.check(rc, "pp_group_fwd")
     return out
 
@@ -90,9 +85,8 @@ def group_points_grad(grad_out, idx, n):
     _check(idx.dtype == torch.int32, "idx must be an int tensor")
     B, C, npoint, nsample = grad_out.shape
     g = torch.zeros(B, C, int(n), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_group_bwd(_C.ptr(grad_out), _C.ptr(idx), B, C, int(n), npoint, nsample, _C.ptr(g), dev.index,
-                                 _C.stream_of(dev))
+    rc = _C.lib.pp_group_bwd(_C.ptr(grad_out), _C.ptr(idx), B, C, int(n), npoint, nsample, _C.ptr(g), dev.index,
+                             _C.stream_of(dev))
     _C.check(rc, "pp_group_bwd")
     return g
 
@@ -106,9 +100,8 @@ def three_nn(unknown, known):
     M = known.shape[1]
     dist2 = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
     idx = torch.empty(B, N, 3, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_three_nn(_C.ptr(unknown), _C.ptr(known), B, N, M, _C.ptr(dist2), _C.ptr(idx), dev.index,
-                                _C.stream_of(dev))
+    rc = _C.lib.pp_three_nn(_C.ptr(unknown), _C.ptr(known), B, N, M, _C.ptr(dist2), _C.ptr(idx), dev.index,
+                            _C.stream_of(dev))
     _C.check(rc, "pp_three_nn")
     return dist2, idx
 
@@ -118,9 +111,8 @@ def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
     the exact pybind signature of the reference (_ext/sampling.cpp:163-173,213)."""
     dev = _C.require_cuda(unknown, known, dist2, idx)
     _C.require_contiguous(unknown, known, dist2, idx)
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_three_nn(_C.ptr(unknown), _C.ptr(known), b, n, m, _C.ptr(dist2), _C.ptr(idx), dev.index,
-                                _C.stream_of(dev))
+    rc = _C.lib.pp_three_nn(_C.ptr(unknown), _C.ptr(known), b, n, m, _C.ptr(dist2), _C.ptr(idx), dev.index,
+                            _C.stream_of(dev))
     _C.check(rc, "pp_three_nn")
 
 
@@ -130,9 +122,8 @@ def three_interpolate_wrapper(b, c, m, n, points, idx, weight, out):
     dev = _C.require_cuda(points, idx, weight, out)
     _C.require_contiguous(points, idx, weight, out)
     _check(idx.dtype == torch.int32, "three_interpolate: idx must be int32")
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_three_interpolate_fwd(_C.ptr(points), _C.ptr(idx), _C.ptr(weight), b, c, m, n, _C.ptr(out),
-                                             dev.index, _C.stream_of(dev))
+    rc = _C.lib.pp_three_interpolate_fwd(_C.ptr(points), _C.ptr(idx), _C.ptr(weight), b, c, m, n, _C.ptr(out),
+                                         dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_three_interpolate_fwd")
 
 
@@ -142,9 +133,8 @@ def three_interpolate_grad_wrapper(b, c, n, m, grad_out, idx, weight, grad_point
     dev = _C.require_cuda(grad_out, idx, weight, grad_points)
     _C.require_contiguous(grad_out, idx, weight, grad_points)
     _check(idx.dtype == torch.int32, "three_interpolate_grad: idx must be int32")
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_three_interpolate_bwd(_C.ptr(grad_out), _C.ptr(idx), _C.ptr(weight), b, c, n, m,
-                                             _C.ptr(grad_points), dev.index, _C.stream_of(dev))
+    rc = _C.lib.pp_three_interpolate_bwd(_C.ptr(grad_out), _C.ptr(idx), _C.ptr(weight), b, c, n, m,
+                                         _C.ptr(grad_points), dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_three_interpolate_bwd")
 
 
@@ -161,8 +151,7 @@ def knn(k, query, points):
     idx = torch.empty(B, M, int(k), dtype=torch.int32, device=dev)
     nbytes = _C.lib.pp_knn_workspace_bytes(B, M, N, c, int(k))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev) if nbytes else None
-    with torch.cuda.device(dev):
-        rc = _C.lib.pp_knn(_C.ptr(query), _C.ptr(points), B, M, N, c, int(k), _C.ptr(dist), _C.ptr(idx),
-                           _C.ptr(ws), nbytes, dev.index, _C.stream_of(dev))
+    rc = _C.lib.pp_knn(_C.ptr(query), _C.ptr(points), B, M, N, c, int(k), _C.ptr(dist), _C.ptr(idx),
+                       _C.ptr(ws), nbytes, dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_knn")
     return dist, idx
