@@ -271,10 +271,11 @@ def main():
         torch.cuda.current_stream().synchronize()
         return float(sums_host[0]) / (total_B * N) + float(sums_host[1]) / (total_B * M)
 
-    graphed = None
-    if world == 1:
-        from pytorch_points_b200.pipeline import GraphedChamferStep
-        graphed = GraphedChamferStep([(a_host, b_host)], total_batch=total_B, device=dev)
+    from pytorch_points_b200.pipeline import GraphedChamferStep
+    if world > 1:
+        dist.all_reduce(sums)  # the communicator exists before the first replay
+        torch.cuda.synchronize()
+    graphed = GraphedChamferStep([(a_host, b_host)], total_batch=total_B, device=dev, world_size=world)
 
     def step_e2e_graph():
         """The whole step (H2D x2 from pinned host, forward, backward, D2H of the loss sums) as one
@@ -340,9 +341,10 @@ def main():
     ms_e2e_autograd = timed_e2e(step_e2e_autograd, min(args.steps, 50), 3)
     if graphed is not None:
         ms_e2e = timed_e2e(step_e2e_graph, args.steps, args.warmup)
-        e2e_api = ("pipeline.GraphedChamferStep.run(): compute graph (pp_chamfer_fwd + finalize with fused loss sums, "
-                   "pp_chamfer_bwd_uniform, D2H of the sums) on one stream, copy graph (H2D of the NEXT step's two clouds "
-                   "from pinned host) on a second stream, then sync + host read of the loss")
+        e2e_api = ("pipeline.GraphedChamferStep.run(): compute graph(s) (pp_chamfer_fwd + finalize with fused loss sums, "
+                   "[eager NCCL all-reduce of the sums when N>1,] pp_chamfer_bwd_uniform, D2H of the sums) on one stream, "
+                   "copy graph (H2D of the NEXT step's two clouds from pinned host) on a second stream, then sync + host "
+                   "read of the loss")
         loss_graph = step_e2e_graph()
     else:
         ms_e2e, e2e_api, loss_graph = ms_e2e_plugin, "see plugin_api (CUDA-graph step is single-GPU only)", None

@@ -71,8 +71,13 @@ class GraphedChamferStep:
     flight); results of the latest `run()`: `self.grad1`, `self.grad2`, `self.dist1` ...
     """
 
-    def __init__(self, host_pairs, total_batch=None, device=None):
+    def __init__(self, host_pairs, total_batch=None, device=None, group=None, world_size=1):
+        """With `world_size` > 1 every rank builds its own step over its shard of the batch.  The
+        8-byte NCCL all-reduce of the loss sums is NOT captured: the step is split into a forward
+        graph and a backward graph and the all-reduce is issued eagerly between the two replays
+        (asynchronously, so it overlaps the backward, whose weights are constants)."""
         from ._ext import losses
+        self.world_size, self.group = world_size, group
         dev = torch.device(device if device is not None else torch.cuda.current_device())
         if dev.type != "cuda":
             raise RuntimeError("GraphedChamferStep needs a CUDA device")
@@ -109,11 +114,17 @@ class GraphedChamferStep:
             self.xyz1[s].copy_(self.host_pairs[s][0], non_blocking=True)
             self.xyz2[s].copy_(self.host_pairs[s][1], non_blocking=True)
 
-        def compute_body(s):
+        def fwd_body(s):
             losses.nmdistance_forward(self.xyz1[s], self.xyz2[s], self.dist1, self.dist2, self.idx1, self.idx2,
                                       sums=self.sums)
+
+        def bwd_body(s):
             losses.nmdistance_backward_uniform(self.xyz1[s], self.xyz2[s], self.grad1, self.grad2, self.gw,
                                                self.idx1, self.idx2)
+
+        def compute_body(s):
+            fwd_body(s)
+            bwd_body(s)
             self.sums_host.copy_(self.sums, non_blocking=True)
 
         cur = torch.cuda.current_stream(dev)
@@ -133,10 +144,18 @@ class GraphedChamferStep:
             with torch.cuda.graph(g, stream=self.copy_stream):
                 copy_body(s)
             self.copy_graph.append(g)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=self.compute_stream):
-                compute_body(s)
-            self.compute_graph.append(g)
+            if world_size == 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.compute_stream):
+                    compute_body(s)
+                self.compute_graph.append(g)
+            else:
+                gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gf, stream=self.compute_stream):
+                    fwd_body(s)
+                with torch.cuda.graph(gb, stream=self.compute_stream):
+                    bwd_body(s)
+                self.compute_graph.append((gf, gb))
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
         self.slot = 0
         self._primed = False
@@ -155,7 +174,16 @@ class GraphedChamferStep:
             self._primed = True
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.copied[s])
-            self.compute_graph[s].replay()
+            if self.world_size == 1:
+                self.compute_graph[s].replay()
+            else:
+                import torch.distributed as dist
+                gf, gb = self.compute_graph[s]
+                gf.replay()
+                work = dist.all_reduce(self.sums, group=self.group, async_op=True)
+                gb.replay()
+                work.wait()
+                self.sums_host.copy_(self.sums, non_blocking=True)
         # the other set's previous consumer finished before the previous run() returned
         self._launch_copy(1 - s)
         self.compute_stream.synchronize()
