@@ -87,7 +87,9 @@ template <int P, int C>
 __global__ void __launch_bounds__(FPS_T, 1)
 fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float *__restrict__ temp,
                    int *__restrict__ idx, int bs_log2, long long *__restrict__ prof) {
-    // prof != nullptr: thread 0 of cluster 0 accumulates clock64() deltas per phase (debug only)
+    // -DPP_FPS_PROFILE: thread 0 of cluster 0 accumulates clock64() deltas per phase into `prof`
+    // (how the per-round breakdown in DESIGN.md was measured); compiled out otherwise.
+#ifdef PP_FPS_PROFILE
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long pc = 0;
 #define FPS_STAMP(i)                                   \
@@ -96,6 +98,9 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
         pt[i] += now - pc;                             \
         pc = now;                                      \
     }
+#else
+#define FPS_STAMP(i)
+#endif
     extern __shared__ __align__(16) unsigned char fps_smem[];
     float4 *sPts = reinterpret_cast<float4 *>(fps_smem);  // [P][FPS_T] this CTA's points
     __shared__ __align__(8) int2 wrec[2][FPS_W];           // per-warp (value, tie-key)
@@ -144,7 +149,9 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
     __syncthreads();
     if (C > 1) cg::this_cluster().sync();  // peers' shared memory and barriers are live before any remote store
 
+#ifdef PP_FPS_PROFILE
     if (prof != nullptr) pc = clock64();
+#endif
     for (int j = 1; j < m; j++) {
         const int par = j & 1;
         float best = -1.f;
@@ -224,8 +231,10 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
             FPS_STAMP(6)
         }
     }
+#ifdef PP_FPS_PROFILE
     if (prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
         for (int i = 0; i < 8; i++) prof[i] = pt[i];
+#endif
 #undef FPS_STAMP
 #pragma unroll
     for (int p = 0; p < P; p++) {

@@ -1,3 +1,4 @@
+# NOTE: needs libpp_b200.so built with -DPP_FPS_PROFILE (NVCC_FLAGS in _build.py)
 import sys, os, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
