@@ -157,14 +157,30 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
         float best = -1.f;
         int bp = 0;
         FPS_STAMP(7)
+        if (P >= 2) {
+            // packed pipe: two points per FADD2/FMUL2/FFMA2 (same y-first rounding order), the
+            // running maximum with FMNMX3, then the first p holding it (== strict '>' scan)
+            const float nox = -ox, noy = -oy, noz = -oz;
 #pragma unroll
-        for (int p = 0; p < P; p++) {
-            const float d = sqdist_yxz(__fsub_rn(px[p], ox), __fsub_rn(py[p], oy), __fsub_rn(pz[p], oz));
-            const float d2 = fminf(d, td[p]);
-            td[p] = d2;
-            if (d2 > best) {
-                best = d2;
-                bp = p;
+            for (int p = 0; p < P; p += 2) {
+                const float2 d = sqdist2_yxz(make_float2(px[p], px[p + 1]), make_float2(py[p], py[p + 1]),
+                                             make_float2(pz[p], pz[p + 1]), nox, noy, noz);
+                td[p] = fminf(d.x, td[p]);
+                td[p + 1] = fminf(d.y, td[p + 1]);
+                best = fmax3(best, td[p], td[p + 1]);
+            }
+#pragma unroll
+            for (int p = P - 1; p >= 0; p--) bp = (td[p] == best) ? p : bp;
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; p++) {
+                const float d = sqdist_yxz(__fsub_rn(px[p], ox), __fsub_rn(py[p], oy), __fsub_rn(pz[p], oz));
+                const float d2 = fminf(d, td[p]);
+                td[p] = d2;
+                if (d2 > best) {
+                    best = d2;
+                    bp = p;
+                }
             }
         }
         FPS_STAMP(0)
@@ -491,13 +507,18 @@ int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (max_clusters) {  // query only: how many such clusters can be co-resident on this GPU
+    if (max_clusters) {
+        // query only: how many such clusters can be co-resident with ONE CTA per SM (two CTAs
+        // sharing an SM's issue slots lengthen every round of the latency chain, measured
+        // 0.72 vs 0.65 ms).  Asking with more than half an SM's shared memory enforces that.
         if (C == 1) {
-            int per_sm = 0;
-            PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FPS_T, smem));
-            *max_clusters = per_sm * NUM_SMS_B200;
+            *max_clusters = NUM_SMS_B200;
         } else {
+            const size_t solo = smem > (size_t)120 * 1024 ? smem : (size_t)120 * 1024;
+            PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solo));
+            cfg.dynamicSmemBytes = solo;
             PP_CUDA(cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg));
+            PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         return PP_OK;
     }
