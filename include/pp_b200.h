@@ -103,6 +103,16 @@ int pp_fps(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t
            int device, void *stream);
 
 /*
+ * Farthest point sampling with the gather fused in ("next" row N2): as pp_fps, and additionally
+ * new_xyz (B,m,3) = xyz[b, idx[b,j], :].  Replaces the furthest_sampling -> transpose ->
+ * gather_points -> transpose sequence of furthest_point_sample(xyz, m, NCHW=False)
+ * (network/geo_operations.py:44-64), which is how PointnetSAModule obtains its centres
+ * (network/pointnet2_modules.py:34).
+ */
+int pp_fps_gather(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
+                  float *new_xyz, int device, void *stream);
+
+/*
  * gather_points forward / backward.  Replace sampling.gather_forward / gather_backward
  * (_ext/sampling.cpp:19-41,208-209 -> _ext/sampling_cuda.cu:9-84).
  *   points (B,C,N), idx (B,npoint) -> out (B,C,npoint);
@@ -134,6 +144,25 @@ int pp_group_fwd(const float *points, const int32_t *idx, int B, int C, int N, i
                  int nsample, float *out, int device, void *stream);
 int pp_group_bwd(const float *grad_out, const int32_t *idx, int B, int C, int N, int npoint,
                  int nsample, float *grad_points, int device, void *stream);
+
+/*
+ * QueryAndGroup in one kernel ("next" rows N1/N2).  Replaces the ball_query -> transpose ->
+ * group_points -> subtract centre -> group_points -> cat sequence of
+ * QueryAndGroup.forward (network/operations.py:166-213).
+ *   new_xyz (B,M,3), xyz (B,N,3), features (B,C,N) or NULL with C = 0 ->
+ *   idx (B,M,nsample) int32 exactly as pp_ball_query,
+ *   out (B, 3*use_xyz + C, M, nsample): channels 0..2 = xyz[idx] - new_xyz (one rounded
+ *   subtraction), then the C feature channels features[:, :, idx].
+ * Backward: grad_out (B, 3*use_xyz + C, M, nsample); ACCUMULATES into grad_features (B,C,N)
+ * and grad_xyz (B,N,3) (caller zero-fills; either may be NULL), and WRITES
+ * grad_new_xyz (B,M,3) = -sum over samples of the xyz channels (may be NULL).
+ */
+int pp_query_group_fwd(const float *new_xyz, const float *xyz, const float *features, int B, int N,
+                       int M, int C, float radius, int nsample, int use_xyz, int32_t *idx,
+                       float *out, int device, void *stream);
+int pp_query_group_bwd(const float *grad_out, const int32_t *idx, int B, int N, int M, int C,
+                       int nsample, int use_xyz, float *grad_features, float *grad_xyz,
+                       float *grad_new_xyz, int device, void *stream);
 
 /* --------------------------------------------------------------------- knn */
 

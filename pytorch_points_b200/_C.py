@@ -25,11 +25,14 @@ SIGNATURES = {
     "pp_chamfer_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_chamfer_bwd_uniform": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_fps": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "pp_fps_gather": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "pp_gather_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_gather_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_ball_query": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _i, _vp]),
     "pp_group_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_group_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "pp_query_group_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _i, _vp]),
+    "pp_query_group_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "pp_knn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "pp_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "pp_three_nn": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),

@@ -155,3 +155,66 @@ def knn(k, query, points):
                        _C.ptr(ws), nbytes, dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_knn")
     return dist, idx
+
+
+# ---------------------------------------------------------------------------
+# Fused set-abstraction stages (no counterpart in the reference extension: they replace
+# Python-level op sequences, see include/pp_b200.h).
+# ---------------------------------------------------------------------------
+def furthest_sampling_gather(m, seedIdx, input, temp, idx, new_xyz):
+    """furthest_sampling + gather of the sampled coordinates into new_xyz (B,m,3) in one launch
+    (the op sequence of furthest_point_sample(..., NCHW=False), network/geo_operations.py:44-64)."""
+    dev = _C.require_cuda(input, temp, idx, new_xyz)
+    _C.require_contiguous(input, temp, idx, new_xyz)
+    _check(input.dtype == torch.float32 and temp.dtype == torch.float32 and new_xyz.dtype == torch.float32,
+           "furthest_sampling_gather: float32 only")
+    _check(idx.dtype == torch.int32, "furthest_sampling_gather: idx must be int32")
+    B, N, c = input.shape
+    _check(c == 3, "furthest sampling is implemented for 3D points")
+    _check(tuple(new_xyz.shape) == (B, int(m), 3), "furthest_sampling_gather: new_xyz must be (B, m, 3)")
+    rc = _C.lib.pp_fps_gather(_C.ptr(input), B, N, int(m), int(seedIdx), _C.ptr(temp), _C.ptr(idx),
+                              _C.ptr(new_xyz), dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_fps_gather")
+    return idx
+
+
+def query_and_group(new_xyz, xyz, features, radius, nsample, use_xyz=True):
+    """ball_query + group xyz (centre-relative) + group features + concat in one kernel
+    (QueryAndGroup.forward, network/operations.py:166-213).
+    -> (out (B, 3*use_xyz + C, M, nsample), idx (B, M, nsample) int32)."""
+    tensors = (new_xyz, xyz) if features is None else (new_xyz, xyz, features)
+    dev = _C.require_cuda(*tensors)
+    _C.require_contiguous(*tensors)
+    _check(all(t.dtype == torch.float32 for t in tensors), "query_and_group: float32 only")
+    _check(features is not None or use_xyz, "Cannot have not features and not use xyz as a feature!")
+    B, M, _ = new_xyz.shape
+    N = xyz.shape[1]
+    C = 0 if features is None else features.shape[1]
+    if features is not None:
+        _check(features.shape[0] == B and features.shape[2] == N, "query_and_group: features must be (B, C, N)")
+    ch = (3 if use_xyz else 0) + C
+    idx = torch.empty(B, M, int(nsample), dtype=torch.int32, device=dev)
+    out = torch.empty(B, ch, M, int(nsample), dtype=torch.float32, device=dev)
+    rc = _C.lib.pp_query_group_fwd(_C.ptr(new_xyz), _C.ptr(xyz), _C.ptr(features) if C else None, B, N, M, C,
+                                   float(radius), int(nsample), int(bool(use_xyz)), _C.ptr(idx), _C.ptr(out),
+                                   dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_query_group_fwd")
+    return out, idx
+
+
+def query_and_group_grad(grad_out, idx, n, C, use_xyz, need_features, need_xyz, need_new_xyz):
+    """Backward of query_and_group -> (grad_features (B,C,n) | None, grad_xyz (B,n,3) | None,
+    grad_new_xyz (B,M,3) | None)."""
+    dev = _C.require_cuda(grad_out, idx)
+    _C.require_contiguous(grad_out, idx)
+    _check(grad_out.dtype == torch.float32 and idx.dtype == torch.int32, "query_and_group_grad: float32 grads, int32 idx")
+    B, M, nsample = idx.shape
+    gf = torch.zeros(B, C, n, dtype=torch.float32, device=dev) if (need_features and C) else None
+    gx = torch.zeros(B, n, 3, dtype=torch.float32, device=dev) if (need_xyz and use_xyz) else None
+    gn = torch.empty(B, M, 3, dtype=torch.float32, device=dev) if (need_new_xyz and use_xyz) else None
+    rc = _C.lib.pp_query_group_bwd(_C.ptr(grad_out), _C.ptr(idx), B, n, M, C, nsample,
+                                   int(bool(use_xyz)), _C.ptr(gf) if gf is not None else None,
+                                   _C.ptr(gx) if gx is not None else None, _C.ptr(gn) if gn is not None else None,
+                                   dev.index, _C.stream_of(dev))
+    _C.check(rc, "pp_query_group_bwd")
+    return gf, gx, gn

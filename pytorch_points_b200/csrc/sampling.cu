@@ -86,7 +86,8 @@ __device__ __forceinline__ unsigned fps_tiekey(int k, int bs_log2) {
 template <int P, int C>
 __global__ void __launch_bounds__(FPS_T, 1)
 fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float *__restrict__ temp,
-                   int *__restrict__ idx, int bs_log2, long long *__restrict__ prof) {
+                   int *__restrict__ idx, float *__restrict__ new_xyz, int bs_log2,
+                   long long *__restrict__ prof) {
     // -DPP_FPS_PROFILE: thread 0 of cluster 0 accumulates clock64() deltas per phase into `prof`
     // (how the per-round breakdown in DESIGN.md was measured); compiled out otherwise.
 #ifdef PP_FPS_PROFILE
@@ -116,6 +117,8 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
     const float *pts = xyz + (size_t)b * N * 3;
     float *tp = temp + (size_t)b * N;
     int *out = idx + (size_t)b * m;
+    // optional fused gather: the winner's coordinates are already in hand every round
+    float *oxyz = new_xyz != nullptr ? new_xyz + (size_t)b * m * 3 : nullptr;
 
     float px[P], py[P], pz[P], td[P];
 #pragma unroll
@@ -138,7 +141,10 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
     // coordinates of the seed point, first output
     float ox = __ldg(pts + (size_t)seed * 3 + 0), oy = __ldg(pts + (size_t)seed * 3 + 1),
           oz = __ldg(pts + (size_t)seed * 3 + 2);
-    if (tg == 0) out[0] = seed;
+    if (tg == 0) {
+        out[0] = seed;
+        if (oxyz != nullptr) { oxyz[0] = ox; oxyz[1] = oy; oxyz[2] = oz; }
+    }
     if (C > 1 && tid == 0) {
         mbar_init(&cbar[0], 1);
         mbar_init(&cbar[1], 1);
@@ -205,7 +211,10 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
             const int slot = (ck / TT) * FPS_T + (ck % TT);
             const float4 w = sPts[slot];
             ox = w.x; oy = w.y; oz = w.z;
-            if (tid == 0) out[j] = ck;
+            if (tid == 0) {
+                out[j] = ck;
+                if (oxyz != nullptr) { oxyz[j * 3] = ox; oxyz[j * 3 + 1] = oy; oxyz[j * 3 + 2] = oz; }
+            }
         } else {
             if (warp == 0) {
                 // only warp 0 needs this CTA's winner: it ships it to every CTA of the cluster
@@ -243,7 +252,10 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
             const unsigned who = __ballot_sync(FULL_MASK, v == bv && t == bt);  // tie-keys are unique
             const float4 w = *(reinterpret_cast<const float4 *>(&crec[par][__ffs(who) - 1]) + 1);
             ox = w.x; oy = w.y; oz = w.z;
-            if (tg == 0) out[j] = __float_as_int(w.w);
+            if (tg == 0) {
+                out[j] = __float_as_int(w.w);
+                if (oxyz != nullptr) { oxyz[j * 3] = ox; oxyz[j * 3 + 1] = oy; oxyz[j * 3 + 2] = oz; }
+            }
             FPS_STAMP(6)
         }
     }
@@ -265,18 +277,23 @@ fps_cluster_kernel(const float *__restrict__ xyz, int N, int m, int seed, float 
 // same tie-key; only meant to keep every size correct.
 __global__ void __launch_bounds__(1024, 1)
 fps_stream_kernel(const float *__restrict__ xyz, int N, int m, int seed, float *__restrict__ temp,
-                  int *__restrict__ idx, int bs_log2) {
+                  int *__restrict__ idx, float *__restrict__ new_xyz, int bs_log2) {
     __shared__ __align__(8) int2 wrec[2][32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *pts = xyz + (size_t)b * N * 3;
     float *tp = temp + (size_t)b * N;
     int *out = idx + (size_t)b * m;
+    float *oxyz = new_xyz != nullptr ? new_xyz + (size_t)b * m * 3 : nullptr;
     int old = seed;
     if (tid == 0) out[0] = seed;
-    for (int j = 1; j < m; j++) {
+    for (int j = 1; j <= m; j++) {
         const int par = j & 1;
         const float ox = __ldg(pts + (size_t)old * 3), oy = __ldg(pts + (size_t)old * 3 + 1),
                     oz = __ldg(pts + (size_t)old * 3 + 2);
+        if (tid == 0 && oxyz != nullptr) {  // coordinates of sample j-1
+            oxyz[(j - 1) * 3] = ox; oxyz[(j - 1) * 3 + 1] = oy; oxyz[(j - 1) * 3 + 2] = oz;
+        }
+        if (j == m) break;
         float best = -1.f;
         unsigned btk = 0xffffffffu;
         // 1024 is a multiple of bs, so (k mod bs) is constant per thread and k ascends
@@ -491,7 +508,7 @@ three_interpolate_bwd_kernel(const float *__restrict__ grad_out, const int *__re
 
 template <int P, int C>
 int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
-                       int bs_log2, cudaStream_t st, int *max_clusters) {
+                       float *new_xyz, int bs_log2, cudaStream_t st, int *max_clusters) {
     const size_t smem = sizeof(float4) * P * FPS_T;
     auto kern = fps_cluster_kernel<P, C>;
     PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -527,27 +544,27 @@ int launch_fps_cluster(const float *xyz, int B, int N, int m, int seed, float *t
     if (prof != nullptr)
         prof = (long long *)(((unsigned long long)(unsigned)get_option("fps_prof_ptr_hi", 0) << 32) |
                              (unsigned long long)(unsigned)get_option("fps_prof_ptr_lo", 0));
-    PP_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, seed, temp, idx, bs_log2, prof));
+    PP_CUDA(cudaLaunchKernelEx(&cfg, kern, xyz, N, m, seed, temp, idx, new_xyz, bs_log2, prof));
     return PP_OK;
 }
 
 template <int C>
 int dispatch_fps_p(int P, const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
-                   int bs_log2, cudaStream_t st, int *max_clusters) {
-    if (P <= 1) return launch_fps_cluster<1, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
-    if (P <= 2) return launch_fps_cluster<2, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
-    if (P <= 4) return launch_fps_cluster<4, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
-    if (P <= 8) return launch_fps_cluster<8, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
-    return launch_fps_cluster<16, C>(xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+                   float *new_xyz, int bs_log2, cudaStream_t st, int *max_clusters) {
+    if (P <= 1) return launch_fps_cluster<1, C>(xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
+    if (P <= 2) return launch_fps_cluster<2, C>(xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
+    if (P <= 4) return launch_fps_cluster<4, C>(xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
+    if (P <= 8) return launch_fps_cluster<8, C>(xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
+    return launch_fps_cluster<16, C>(xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
 }
 
 int dispatch_fps(int C, int P, const float *xyz, int B, int N, int m, int seed, float *temp, int *idx,
-                 int bs_log2, cudaStream_t st, int *max_clusters) {
+                 float *new_xyz, int bs_log2, cudaStream_t st, int *max_clusters) {
     switch (C) {
-        case 1: return dispatch_fps_p<1>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
-        case 2: return dispatch_fps_p<2>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
-        case 4: return dispatch_fps_p<4>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
-        case 8: return dispatch_fps_p<8>(P, xyz, B, N, m, seed, temp, idx, bs_log2, st, max_clusters);
+        case 1: return dispatch_fps_p<1>(P, xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
+        case 2: return dispatch_fps_p<2>(P, xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
+        case 4: return dispatch_fps_p<4>(P, xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
+        case 8: return dispatch_fps_p<8>(P, xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, max_clusters);
         default: break;
     }
     set_error("fps: unsupported cluster width %d", C);
@@ -559,8 +576,8 @@ int dispatch_fps(int C, int P, const float *xyz, int B, int N, int m, int seed, 
 
 using namespace pp;
 
-extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
-                      int device, void *stream) {
+static int fps_impl(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
+                    float *new_xyz, int device, void *stream) {
     PP_REQUIRE(B >= 0 && N >= 1, "fps: bad sizes B=%d N=%d", B, N);
     if (m <= 0 || B == 0) return PP_OK;  // _ext/sampling_cuda.cu:166
     PP_REQUIRE(xyz && temp && idx, "fps: null pointer");
@@ -589,7 +606,7 @@ extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *te
             int &slot = fit_cache[device & 15][ci][pb];
             if (slot == 0) {
                 int fit = 0;
-                const int rc = dispatch_fps(c, p, xyz, B, N, m, seed, temp, idx, bs_log2, st, &fit);
+                const int rc = dispatch_fps(c, p, xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, &fit);
                 if (rc != PP_OK) return rc;
                 slot = fit + 1;
             }
@@ -609,11 +626,22 @@ extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *te
     const int P = ceil_div(N, C * FPS_T);
     if (P > 16 || get_option("fps_stream", 0)) {
         KernelTimer timer("fps", st);
-        fps_stream_kernel<<<B, 1024, 0, st>>>(xyz, N, m, seed, temp, idx, bs_log2);
+        fps_stream_kernel<<<B, 1024, 0, st>>>(xyz, N, m, seed, temp, idx, new_xyz, bs_log2);
         PP_LAUNCH_CHECK();
         return PP_OK;
     }
-    return dispatch_fps(C, P, xyz, B, N, m, seed, temp, idx, bs_log2, st, nullptr);
+    return dispatch_fps(C, P, xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, nullptr);
+}
+
+extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
+                      int device, void *stream) {
+    return fps_impl(xyz, B, N, m, seed, temp, idx, nullptr, device, stream);
+}
+
+extern "C" int pp_fps_gather(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
+                             float *new_xyz, int device, void *stream) {
+    PP_REQUIRE(new_xyz || m <= 0 || B == 0, "fps_gather: null new_xyz");
+    return fps_impl(xyz, B, N, m, seed, temp, idx, new_xyz, device, stream);
 }
 
 extern "C" int pp_gather_fwd(const float *points, const int32_t *idx, int B, int C, int N, int npoint,

@@ -29,6 +29,35 @@ class FurthestPointSampling(torch.autograd.Function):
 __furthest_point_sample = FurthestPointSampling.apply  # type: ignore
 
 
+class FurthestPointSampleGather(torch.autograd.Function):
+    """FPS with the gather of the sampled coordinates fused into the sampling kernel."""
+
+    @staticmethod
+    def forward(ctx, xyz, npoint, seedIdx):
+        """xyz (B, N, 3) contiguous -> (idx (B, npoint) int32, new_xyz (B, npoint, 3))."""
+        B, N, _ = xyz.size()
+        idx = torch.empty([B, npoint], dtype=torch.int32, device=xyz.device)
+        new_xyz = torch.empty([B, npoint, 3], dtype=torch.float32, device=xyz.device)
+        temp = torch.full([B, N], 1e10, dtype=torch.float32, device=xyz.device)
+        sampling.furthest_sampling_gather(npoint, seedIdx, xyz, temp, idx, new_xyz)
+        ctx.save_for_backward(idx)
+        ctx.N = N
+        ctx.mark_non_differentiable(idx)
+        return idx, new_xyz
+
+    @staticmethod
+    def backward(ctx, grad_idx, grad_new_xyz):
+        # same scatter as GatherFunction.backward on the (B, 3, N) view (network/operations.py:68-85)
+        idx, = ctx.saved_tensors
+        B, npoint = idx.size()
+        g = torch.zeros(B, 3, ctx.N, dtype=torch.float32, device=grad_new_xyz.device)
+        sampling.gather_backward(B, 3, ctx.N, npoint, grad_new_xyz.transpose(1, 2).contiguous(), idx, g)
+        return g.transpose(1, 2).contiguous(), None, None
+
+
+__furthest_point_sample_gather = FurthestPointSampleGather.apply  # type: ignore
+
+
 def furthest_point_sample(xyz, npoint, NCHW=True, seedIdx=0):
     """xyz (B, 3, N) if NCHW else (B, N, 3) -> (idx (B, npoint) int32,
     sampled points (B, 3, npoint) if NCHW else (B, npoint, 3))."""
@@ -38,8 +67,9 @@ def furthest_point_sample(xyz, npoint, NCHW=True, seedIdx=0):
     else:
         xyz = xyz.contiguous()
     assert xyz.size(2) == 3, "furthest sampling is implemented for 3D points"
-    idx = __furthest_point_sample(xyz, npoint, seedIdx)
-    sampled_pc = gather_points(xyz.transpose(2, 1).contiguous(), idx)
-    if not NCHW:
+    # the reference gathers the samples with a second kernel and two transposes
+    # (geo_operations.py:60-63); the sampling kernel already holds each winner's coordinates
+    idx, sampled_pc = __furthest_point_sample_gather(xyz, npoint, seedIdx)
+    if NCHW:
         sampled_pc = sampled_pc.transpose(2, 1).contiguous()
     return idx, sampled_pc

@@ -71,20 +71,56 @@ class GroupingOperation(torch.autograd.Function):
 grouping_operation = GroupingOperation.apply  # type: ignore
 
 
-class QueryAndGroup(torch.nn.Module):
-    """Ball query around `new_xyz`, then group (centre-relative) coordinates and features."""
+class QueryAndGroupFunction(torch.autograd.Function):
+    """The whole QueryAndGroup stage as one kernel each way (csrc/sa_group.cu)."""
 
-    def __init__(self, radius, nsample, use_xyz=True):
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, features, radius, nsample, use_xyz):
+        xyz = xyz.contiguous()
+        new_xyz = new_xyz.contiguous()
+        feats = None if features is None else features.contiguous()
+        out, idx = sampling.query_and_group(new_xyz, xyz, feats, radius, nsample, use_xyz)
+        ctx.save_for_backward(idx)
+        ctx.meta = (xyz.size(1), 0 if feats is None else feats.size(1), bool(use_xyz))
+        ctx.mark_non_differentiable(idx)
+        return out, idx
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_idx=None):
+        idx, = ctx.saved_tensors
+        N, C, use_xyz = ctx.meta
+        need = ctx.needs_input_grad
+        gf, gx, gn = sampling.query_and_group_grad(grad_out.contiguous(), idx, N, C, use_xyz,
+                                                   need_features=need[2], need_xyz=need[0], need_new_xyz=need[1])
+        return gx, gn, gf, None, None, None
+
+
+def query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True):
+    """-> (new_features (B, 3*use_xyz + C, npoint, nsample), idx (B, npoint, nsample) int32)."""
+    return QueryAndGroupFunction.apply(xyz, new_xyz, features, radius, nsample, use_xyz)
+
+
+class QueryAndGroup(torch.nn.Module):
+    """Ball query around `new_xyz`, then group (centre-relative) coordinates and features.
+
+    Same result as the reference's op sequence (network/operations.py:166-213: ball_query,
+    grouping_operation on xyz and on features, centre subtraction, cat), computed by one fused
+    kernel; `fused=False` runs the op-by-op sequence instead (kept for parity tests)."""
+
+    def __init__(self, radius, nsample, use_xyz=True, fused=True):
         super().__init__()
-        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+        self.radius, self.nsample, self.use_xyz, self.fused = radius, nsample, use_xyz, fused
 
     def forward(self, xyz, new_xyz, features=None):
         """xyz (B, N, 3), new_xyz (B, npoint, 3), features (B, C, N) -> (B, 3 + C, npoint, nsample)."""
+        if features is None:
+            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
+        if self.fused:
+            return query_and_group(xyz, new_xyz, features, self.radius, self.nsample, self.use_xyz)[0]
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
         grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
         grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
         if features is None:
-            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
             return grouped_xyz
         grouped_features = grouping_operation(features, idx)
         if self.use_xyz:

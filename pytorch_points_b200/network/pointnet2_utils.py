@@ -60,3 +60,21 @@ class ThreeInterpolate(torch.autograd.Function):
 
 
 three_interpolate = ThreeInterpolate.apply  # type: ignore
+
+
+class GroupAll(torch.nn.Module):
+    """Groups the whole cloud into one set (network/pointnet2_utils.py:127-150)."""
+
+    def __init__(self, use_xyz: bool = True):
+        super().__init__()
+        self.use_xyz = use_xyz
+
+    def forward(self, xyz, new_xyz, features=None):
+        """xyz (B, N, 3), new_xyz ignored, features (B, C, N) -> (B, C + 3, 1, N)."""
+        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+        if features is None:
+            return grouped_xyz
+        grouped_features = features.unsqueeze(2)
+        if self.use_xyz:
+            return torch.cat([grouped_xyz, grouped_features], dim=1)
+        return grouped_features

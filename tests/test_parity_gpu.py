@@ -521,6 +521,180 @@ def test_pointnet2_sa_and_fp_stage_end_to_end(pp):
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in mlp.parameters())
 
 
+# --------------------------------------------------------------------------- fused SA stages
+@pytest.mark.parametrize("B,N,m,seed_idx,stream", [(2, 100, 30, 0, 0), (3, 2048, 256, 5, 0), (2, 16384, 300, 0, 0),
+                                                   (2, 9000, 100, 17, 0), (2, 3000, 64, 1, 1)])
+def test_fps_gather_fused(pp, oracle_mod, B, N, m, seed_idx, stream):
+    """pp_fps_gather: the sampling kernel also emits the sampled coordinates (what
+    furthest_point_sample's gather_points + transposes produce, geo_operations.py:60-63)."""
+    from pytorch_points_b200 import _C
+    xyz = uniform_cloud(B, N, 600 + N)
+    _C.set_option("fps_stream", stream)
+    try:
+        idx, new_xyz = pp.furthest_point_sample(dev(xyz), m, NCHW=False, seedIdx=seed_idx)
+        idx_t, new_t = pp.furthest_point_sample(dev(xyz).transpose(1, 2).contiguous(), m, NCHW=True, seedIdx=seed_idx)
+    finally:
+        _C.set_option("fps_stream", 0)
+    want = oracle_mod.fps(np32(xyz), m, seed=seed_idx)
+    assert np.array_equal(np32(idx), want) and np.array_equal(np32(idx_t), want)
+    gathered = np.take_along_axis(np32(xyz), want[..., None].astype(np.int64), axis=1)
+    assert new_xyz.shape == (B, m, 3) and np.array_equal(np32(new_xyz), gathered)
+    assert new_t.shape == (B, 3, m) and np.array_equal(np32(new_t), gathered.transpose(0, 2, 1))
+
+
+def test_fps_gather_backward_scatters_into_xyz(pp):
+    xyz = dev(uniform_cloud(2, 500, 611)).requires_grad_(True)
+    idx, new_xyz = pp.furthest_point_sample(xyz, 40, NCHW=False)
+    w = torch.rand_like(new_xyz)
+    (new_xyz * w).sum().backward()
+    want = torch.zeros_like(xyz)
+    want.scatter_add_(1, idx.long()[..., None].expand(-1, -1, 3), w)
+    assert torch.equal(xyz.grad, want)  # FPS indices are distinct here: no summation-order freedom
+
+
+QG_CASES = [
+    # (B, N, M, C, radius, nsample, use_xyz, maker)
+    (2, 1024, 64, 6, 0.2, 16, True, uniform_cloud),
+    (2, 4096, 203, 13, 0.2, 32, True, uniform_cloud),     # M not a multiple of the CTA's 8 centres
+    (2, 3000, 100, 0, 0.2, 32, True, sphere_cloud),       # no features
+    (2, 1000, 77, 5, 0.05, 16, False, uniform_cloud),     # features only; many empty / padded balls
+    (1, 2000, 50, 3, 0.3, 64, True, uniform_cloud),       # nsample > one warp
+    (2, 777, 33, 4, 0.25, 5, True, lattice_cloud),        # exact-radius ties, odd nsample
+    (16, 16384, 1024, 16, 0.2, 32, True, uniform_cloud),  # config 3 shape
+]
+
+
+def _oracle_query_group(oracle_mod, xyz, centres, feats, radius, nsample, use_xyz):
+    bq = oracle_mod.ball_query(radius, nsample, np32(xyz), np32(centres))
+    parts = []
+    if use_xyz:
+        parts.append(oracle_mod.group_fwd(np32(xyz.transpose(1, 2).contiguous()), bq)
+                     - np32(centres).transpose(0, 2, 1)[..., None])
+    if feats is not None:
+        parts.append(oracle_mod.group_fwd(np32(feats), bq))
+    return np.concatenate(parts, 1), bq
+
+
+@pytest.mark.parametrize("B,N,M,C,radius,nsample,use_xyz,maker", QG_CASES)
+def test_query_and_group_fused_bit_exact(pp, oracle_mod, B, N, M, C, radius, nsample, use_xyz, maker):
+    xyz = maker(B, N, 620 + N)
+    centres = xyz[:, :M].clone() if maker is lattice_cloud else maker(B, M, 630 + M)
+    feats = uniform_cloud(B, N, 640 + N, c=C).transpose(1, 2).contiguous() if C else None
+    out, idx = pp.query_and_group(dev(xyz), dev(centres), dev(feats) if C else None, radius, nsample, use_xyz)
+    assert out.shape == (B, (3 if use_xyz else 0) + C, M, nsample) and idx.dtype == torch.int32
+    # op-by-op path through the single kernels must agree exactly at every size
+    ref_module = pp.QueryAndGroup(radius, nsample, use_xyz=use_xyz, fused=False)
+    assert torch.equal(out, ref_module(dev(xyz), dev(centres), dev(feats) if C else None))
+    assert torch.equal(idx, pp.ball_query(radius, nsample, dev(xyz), dev(centres)))
+    if B * N * M <= 2 * 4096 * 256:
+        want, bq = _oracle_query_group(oracle_mod, xyz, centres, feats, radius, nsample, use_xyz)
+        assert np.array_equal(np32(idx), bq)
+        assert np.array_equal(np32(out), want)
+
+
+@pytest.mark.parametrize("C,use_xyz", [(6, True), (0, True), (5, False)])
+def test_query_and_group_fused_backward(pp, oracle_mod, C, use_xyz):
+    B, N, M, ns = 2, 1500, 120, 16
+    xyz = uniform_cloud(B, N, 651)
+    centres = uniform_cloud(B, M, 652)
+    feats = uniform_cloud(B, N, 653, c=C).transpose(1, 2).contiguous() if C else None
+    xd = dev(xyz).requires_grad_(True)
+    cd = dev(centres).requires_grad_(True)
+    fd = dev(feats).requires_grad_(True) if C else None
+    out, idx = pp.query_and_group(xd, cd, fd, 0.2, ns, use_xyz)
+    go = torch.rand_like(out)
+    out.backward(go)
+    gon, bq = np32(go), np32(idx)
+    x0 = 3 if use_xyz else 0
+    if C:
+        assert_grad_close(np32(fd.grad), oracle_mod.group_bwd(np.ascontiguousarray(gon[:, x0:]), bq, N), "grad features")
+    if use_xyz:
+        gx = oracle_mod.group_bwd(np.ascontiguousarray(gon[:, :3]), bq, N).transpose(0, 2, 1)
+        assert_grad_close(np32(xd.grad), gx, "grad xyz")
+        assert_grad_close(np32(cd.grad), -gon[:, :3].astype(np.float64).sum(-1).transpose(0, 2, 1), "grad new_xyz")
+    else:
+        assert xd.grad is None and cd.grad is None
+    # and the op-by-op autograd path gives the same gradients
+    x2 = dev(xyz).requires_grad_(True)
+    c2 = dev(centres).requires_grad_(True)
+    f2 = dev(feats).requires_grad_(True) if C else None
+    pp.QueryAndGroup(0.2, ns, use_xyz=use_xyz, fused=False)(x2, c2, f2).backward(go)
+    if C:
+        assert_grad_close(np32(fd.grad), np32(f2.grad), "fused vs composed: features")
+    if use_xyz:
+        assert_grad_close(np32(xd.grad), np32(x2.grad), "fused vs composed: xyz")
+        assert_grad_close(np32(cd.grad), np32(c2.grad), "fused vs composed: new_xyz")
+
+
+def test_pointnet_sa_module_matches_op_by_op_restatement(pp, oracle_mod):
+    """PointnetSAModuleMSG (network/pointnet2_modules.py:21-93) on the fused kernels vs the
+    reference's op-by-op sequence on the single kernels with the same weights; centres are also
+    checked against the oracle's FPS."""
+    torch.manual_seed(1)
+    B, N, C, npoint = 2, 4096, 8, 256
+    xyz_c = uniform_cloud(B, N, 661)
+    xyz = dev(xyz_c)
+    feats = dev(uniform_cloud(B, N, 662, c=C)).transpose(1, 2).contiguous().requires_grad_(True)
+    sa = pp.PointnetSAModuleMSG(npoint=npoint, radii=[0.1, 0.2], nsamples=[16, 32], mlps=[[C, 16, 32], [C, 16, 48]]).cuda()
+    new_xyz, new_feats = sa(xyz, feats)
+    assert new_xyz.shape == (B, npoint, 3) and new_feats.shape == (B, 80, npoint)
+    want_idx = oracle_mod.fps(np32(xyz_c), npoint)
+    assert np.array_equal(np32(new_xyz), np.take_along_axis(np32(xyz_c), want_idx[..., None].astype(np.int64), axis=1))
+    new_feats.square().mean().backward()
+    g_fused = feats.grad.clone()
+    w_fused = [p.grad.clone() for p in sa.parameters()]
+    # --- restatement: FPS, gather_points, ball_query, grouping_operation x2, cat (reference sequence)
+    feats.grad = None
+    sa.zero_grad()
+    idx = pp.FurthestPointSampling.apply(xyz, npoint, 0)
+    ctr = pp.gather_points(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+    assert torch.equal(ctr, new_xyz)
+    outs = []
+    for g, mlp in zip(sa.groupers, sa.mlps):
+        grouped = pp.QueryAndGroup(g.radius, g.nsample, use_xyz=True, fused=False)(xyz, ctr, feats)
+        y = mlp(grouped)
+        outs.append(torch.nn.functional.max_pool2d(y, kernel_size=[1, y.size(3)]).squeeze(-1))
+    ref_feats = torch.cat(outs, dim=1)
+    assert torch.allclose(new_feats, ref_feats, rtol=1e-6, atol=1e-7)
+    ref_feats.square().mean().backward()
+    assert_grad_close(np32(g_fused), np32(feats.grad), "SA module: grad features")
+    for a, b_ in zip(w_fused, [p.grad for p in sa.parameters()]):
+        assert torch.allclose(a, b_, rtol=1e-4, atol=1e-6)
+
+
+def test_pointnet_sa_group_all_and_fp_module(pp, oracle_mod):
+    """npoint=None -> GroupAll (pointnet2_utils.py:127-150); PointnetFPModule
+    (pointnet2_modules.py:115-153) against an oracle three_nn / three_interpolate restatement."""
+    torch.manual_seed(2)
+    B, N, C, m = 2, 1024, 6, 128
+    xyz_c, known_c = uniform_cloud(B, N, 671), uniform_cloud(B, m, 672)
+    xyz, known = dev(xyz_c), dev(known_c)
+    feats = dev(uniform_cloud(B, N, 673, c=C)).transpose(1, 2).contiguous()
+    sa = pp.PointnetSAModule(mlp=[C, 32], npoint=None).cuda()
+    new_xyz, glob = sa(xyz, feats)
+    assert new_xyz is None and glob.shape == (B, 32, 1)
+    known_feats = dev(uniform_cloud(B, m, 674, c=10)).transpose(1, 2).contiguous().requires_grad_(True)
+    fp = pp.PointnetFPModule(mlp=[10 + C, 24], normalization=None).cuda()
+    out = fp(xyz, known, feats, known_feats)
+    assert out.shape == (B, 24, N)
+    d2, i3 = oracle_mod.three_nn(np32(xyz_c), np32(known_c))
+    dist = torch.sqrt(torch.from_numpy(d2))
+    w = 1.0 / (dist + 1e-8)
+    w = w / torch.sum(w, dim=2, keepdim=True)
+    interp = torch.from_numpy(oracle_mod.three_interpolate_fwd(np32(known_feats), i3, w.numpy()))
+    # the interpolation itself (weights formed on the device vs on the host: few-ulp differences)
+    dist_d, idx_d = pp.three_nn(xyz, known)
+    assert np.array_equal(np32(idx_d), i3)
+    wd = 1.0 / (dist_d + 1e-8)
+    wd = wd / torch.sum(wd, dim=2, keepdim=True)
+    assert torch.allclose(pp.three_interpolate(known_feats.detach(), idx_d, wd.contiguous()), dev(interp), rtol=1e-5, atol=1e-6)
+    # through the MLP (cuDNN may use TF32 for the 1x1 convolution: loose tolerance)
+    want = fp.mlp(torch.cat([dev(interp), feats], dim=1).unsqueeze(-1)).squeeze(-1)
+    assert torch.allclose(out, want, rtol=5e-3, atol=5e-3)
+    out.sum().backward()
+    assert known_feats.grad is not None and torch.isfinite(known_feats.grad).all()
+
+
 # --------------------------------------------------------------------------- full-size properties
 def test_chamfer_target_shape_properties(pp, oracle_mod):
     """B=32, N=M=8192 (north-star target) is too big for the CPU oracle inside a unit test:

@@ -136,6 +136,14 @@ def test_ball_query_group_three_way(ref, pp, oracle_mod, B, N, M, r, ns, maker):
         assert np.array_equal(oracle_mod.ball_query(r, ns, np32(xyz), np32(ctr)), np32(want))
     feats = xd.transpose(1, 2).contiguous()
     assert torch.equal(pp.grouping_operation(feats, got), rs.group_points(feats, want))
+    # the fused QueryAndGroup kernel vs the reference's op sequence on the reference's kernels
+    # (network/operations.py:193-205)
+    extra = uniform_cloud(B, N, 212, c=5).transpose(1, 2).contiguous().cuda()
+    grouped_xyz = rs.group_points(feats, want)
+    grouped_xyz -= cd.transpose(1, 2).unsqueeze(-1)
+    ref_out = torch.cat([grouped_xyz, rs.group_points(extra, want)], dim=1)
+    out, idx = pp.query_and_group(xd, cd, extra, r, ns, True)
+    assert torch.equal(idx, want) and torch.equal(out, ref_out)
 
 
 def test_gather_three_way(ref, pp):
