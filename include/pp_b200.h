@@ -220,6 +220,13 @@ int pp_microbench(int which, int iters, float *ms, double *work, int device);
  */
 int pp_timing_collect(const char *name, double *total_ms, int *count);
 
+/*
+ * With pp_set_option("knn_stats", 1) the ordered-sweep KNN path counts the (query block, point
+ * tile) pairs it actually evaluated (this synchronises the stream).  Returns the counts of the
+ * last such call: visited and total.  The rest were skipped by exact bounding-box pruning.
+ */
+int pp_knn_stats(double *tiles_visited, double *tiles_total);
+
 /* Tuning knob for experiments: selects a kernel variant (0 = default). */
 int pp_set_option(const char *name, int value);
 

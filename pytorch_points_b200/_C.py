@@ -35,6 +35,7 @@ SIGNATURES = {
     "pp_query_group_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "pp_knn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "pp_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "pp_knn_stats": (_i, [_vp, _vp]),
     "pp_three_nn": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_three_interpolate_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_three_interpolate_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
@@ -119,3 +120,11 @@ def timing_collect(name):
     count = _i(0)
     check(lib.pp_timing_collect(name.encode(), ctypes.byref(total), ctypes.byref(count)), "pp_timing_collect")
     return total.value, count.value
+
+
+def knn_stats():
+    """(tiles_visited, tiles_total) of the last ordered-sweep KNN call made with
+    set_option("knn_stats", 1)."""
+    v, t = ctypes.c_double(0), ctypes.c_double(0)
+    check(lib.pp_knn_stats(ctypes.byref(v), ctypes.byref(t)), "pp_knn_stats")
+    return v.value, t.value
