@@ -21,7 +21,6 @@
 namespace pp {
 namespace {
 
-constexpr int KM_THREADS = 32;
 constexpr int KM_TILE = 64;
 constexpr int KM_SUB = 1;                   // sub-tiles per tile, each with its own bounding box
 constexpr int KM_SUBLEN = KM_TILE / KM_SUB;  // 64 points = two warps of the box kernel
@@ -179,241 +178,184 @@ __device__ __forceinline__ bool km_can_skip(float gap2, float taumax) {
     return gap2 * 0.9999f > taumax && gap2 > 1e-30f;
 }
 
-// Insertion of (d0,j0) into the ascending list: it enters in front of the first slot that is
-// larger; from there on every slot takes its predecessor (pure shift).  LEX = false compares
-// distances only (5 instructions per slot) and reports whether an exactly equal distance was
-// met; LEX = true uses the full (distance, original index) key (8 per slot).
-template <int K, bool LEX>
-__device__ __forceinline__ bool km_insert(float (&ld)[K], int (&li)[K], float d, int j) {
-    const float d0 = d;
-    const int j0 = j;
-    bool tie = false;
-#pragma unroll
-    for (int s = 0; s < K; s++) {
-        const float td = ld[s];
-        const int ti = li[s];
-        bool sw;
-        if (LEX) {
-            sw = d0 < td || (d0 == td && j0 < ti);
-        } else {
-            sw = d0 < td;
-            tie |= d0 == td;
-        }
-        ld[s] = sw ? d : td;
-        li[s] = sw ? j : ti;
-        d = sw ? td : d;
-        j = sw ? ti : j;
-    }
-    return tie;
-}
+// ---------------------------------------------------------------------------------------------
+// The sweep.  One WARP per CTA owns 32 consecutive queries of the sorted query cloud (one per
+// lane) and walks over the 64-point tiles of the sorted point cloud:
+//   * pruning -- 32 tiles at a time, lane l tests "box of tile l vs the warp's query box vs the
+//     largest k-th distance in the warp"; only tiles that survive are loaded.  Pass 0 takes
+//     the tiles touching the query box (where the neighbours are, wherever the curve put them),
+//     pass 1 whatever is still not provably too far.  Exact: a skipped tile cannot hold a point
+//     any list would accept, and evaluation order never changes the result because selection is
+//     by the total order (distance, original index);
+//   * hot loop -- 4 points per LDS.128 triple, packed FADD2/FMUL2/FFMA2 distances in the
+//     reference rounding order, FMNMX3 + one vote per 4 points; lanes that see a distance <=
+//     their current k-th push (distance, original index) into a small per-lane buffer;
+//   * selection -- the k-best lists live in SHARED memory as 64-bit keys
+//     (distance bits << 32 | original index; unsigned order == the (distance, index) order) and
+//     insertion is warp-cooperative: slot s of a list sits in lane s of a half-warp, a candidate
+//     is compared against all slots at once, one ballot finds its position and one shuffle
+//     shifts the tail.  Cost is proportional to the TOTAL number of candidates of the warp; a
+//     per-lane register list pays max-over-lanes x K per drain, 5x more on these sweeps.
+// ---------------------------------------------------------------------------------------------
+constexpr int KM_CB = 8;  // per-lane candidate buffer depth
 
-template <int K, int Q, int KM_CB, bool PRECHECK, bool ESTIMATE>
-__global__ void __launch_bounds__(KM_THREADS)
-knn_morton_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, const unsigned long long *__restrict__ qkeys,
-                  const float *__restrict__ sp, const int *__restrict__ spi, const unsigned long long *__restrict__ pkeys,
-                  const float4 *__restrict__ tileboxes, int prune, int M, int N, int k, float *__restrict__ dist,
-                  int *__restrict__ idx, unsigned long long *__restrict__ visited) {
+constexpr unsigned long long KM_EMPTY = 0x7f8000007fffffffull;  // (+inf, no index)
+
+template <int K>
+__global__ void __launch_bounds__(32)
+knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, const unsigned long long *__restrict__ qkeys,
+                 const float *__restrict__ sp, const int *__restrict__ spi, const unsigned long long *__restrict__ pkeys,
+                 const float4 *__restrict__ tileboxes, int prune, int seed, int M, int N, int k,
+                 float *__restrict__ dist, int *__restrict__ idx, unsigned long long *__restrict__ visited) {
+    constexpr int W = K <= 16 ? 16 : 32;  // lanes per list
+    constexpr int LP = K + 1;             // padded row length (keys)
     __shared__ __align__(16) float sX[KM_TILE];
     __shared__ __align__(16) float sY[KM_TILE];
     __shared__ __align__(16) float sZ[KM_TILE];
     __shared__ int sI[KM_TILE];
-    __shared__ float sBD[Q][KM_CB][KM_THREADS];
-    __shared__ int sBI[Q][KM_CB][KM_THREADS];
-    __shared__ int s_start;
-    __shared__ int s_wtau[2][KM_THREADS / 32];   // per-warp max k-th distance (float bits), double buffered
-    __shared__ float s_qbox[KM_THREADS / 32][6];  // per-warp query bounding boxes
+    __shared__ float sBD[KM_CB][32];
+    __shared__ int sBI[KM_CB][32];
+    __shared__ unsigned long long sL[32][LP];
 
     const int b = blockIdx.y;
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x;
     const float *qp = sq + (size_t)b * M * 3;
     const float *pp_ = sp + (size_t)b * N * 3;
     const int *pi = spi + (size_t)b * N;
-    const int qbase = blockIdx.x * (KM_THREADS * Q);
+    const int qbase = blockIdx.x * 32;
     const int ntiles = ceil_div(N, KM_TILE);
 
-    // where on the points' curve do this CTA's queries sit?  lower_bound of the CTA's middle
-    // query key among the sorted point keys of this cloud (warp 0, 32-ary search)
-    if (tid < 32) {
-        const int mid = min(M - 1, qbase + (KM_THREADS * Q) / 2);
+    // where on the points' curve do these queries sit?  lower_bound of the middle query's key
+    // among the sorted point keys of this cloud (32-ary search)
+    int t0;
+    {
+        const int mid = min(M - 1, qbase + 16);
         const unsigned long long want = qkeys[(size_t)b * M + mid];
         const unsigned long long *pk = pkeys + (size_t)b * N;
         int lo = 0, hi = N;  // answer in [lo, hi]
         while (hi - lo > 0) {
             const int span = hi - lo;
             const int step = (span + 31) / 32;
-            const int probe = lo + tid * step;
+            const int probe = lo + lane * step;
             const bool below = probe < hi && pk[probe] < want;
-            const unsigned m = __ballot_sync(FULL_MASK, below);
-            const int nb = __popc(m);  // probes 0..nb-1 are below (keys sorted)
+            const int nb = __popc(__ballot_sync(FULL_MASK, below));  // probes 0..nb-1 are below (keys sorted)
             if (nb == 0) {
                 hi = lo;
             } else {
                 const int nlo = lo + (nb - 1) * step + 1;
-                const int nhi = min(hi, lo + nb * step);
+                hi = min(hi, lo + nb * step);
                 lo = nlo;
-                hi = nhi;
             }
         }
-        if (tid == 0) s_start = min(ntiles - 1, lo / KM_TILE);
+        t0 = min(ntiles - 1, lo / KM_TILE);
     }
 
-    float nqx[Q], nqy[Q], nqz[Q], tau[Q], tau0[Q];
-    int cnt[Q];
-    float ld[Q][K];
-    int li[Q][K];
-    bool active[Q];
-    float wlo[3] = {PP_INF, PP_INF, PP_INF}, whi[3] = {-PP_INF, -PP_INF, -PP_INF};  // this warp's query box
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        tau0[q] = PP_INF;
-        // a warp's 32*Q queries are consecutive on the curve: its bounding box stays small
-        const int i = qbase + (tid >> 5) * (32 * Q) + q * 32 + (tid & 31);
-        float x = PP_INF, y = PP_INF, z = PP_INF;
-        if (i < M) {
-            x = __ldg(qp + (size_t)i * 3);
-            y = __ldg(qp + (size_t)i * 3 + 1);
-            z = __ldg(qp + (size_t)i * 3 + 2);
-        }
-        active[q] = i < M;
-        {
-            const float c3[3] = {x, y, z};
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (i < M && c3[c] == c3[c] && fabsf(c3[c]) != PP_INF) {
-                    wlo[c] = fminf(wlo[c], c3[c]);
-                    whi[c] = fmaxf(whi[c], c3[c]);
-                }
-        }
-        nqx[q] = -x; nqy[q] = -y; nqz[q] = -z;
-        tau[q] = PP_INF;
-        cnt[q] = 0;
-#pragma unroll
-        for (int s = 0; s < K; s++) {
-            ld[q][s] = s < k ? PP_INF : -PP_INF;  // slots >= k never accept anything
-            li[q][s] = s < k ? 0x7fffffff : -1;
-        }
+    // this lane's query, the warp's query box, the empty lists
+    const int qi_ = qbase + lane;
+    const bool active = qi_ < M;
+    float qx = PP_INF, qy = PP_INF, qz = PP_INF;
+    if (active) {
+        qx = __ldg(qp + (size_t)qi_ * 3);
+        qy = __ldg(qp + (size_t)qi_ * 3 + 1);
+        qz = __ldg(qp + (size_t)qi_ * 3 + 2);
     }
-
-    unsigned n_iter = 0, n_cand = 0, n_stale = 0;
-    auto drain = [&]() {
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const int most = __reduce_max_sync(FULL_MASK, cnt[q]);
-            n_iter += most; n_cand += cnt[q];
-            for (int e = 0; e < most; e++) {
-                float d = PP_INF;
-                int j = 0x7fffffff;
-                if (e < cnt[q]) {
-                    d = sBD[q][e][tid];
-                    j = sBI[q][e][tid];
-                }
-                // buffered against an older threshold: by now it may be beaten already (k-th
-                // entry of the list); if that holds for every lane the insertion is a no-op
-                float kth = ld[q][K - 1];
-                if (k < K) {
-#pragma unroll
-                    for (int s = 0; s < K - 1; s++) kth = (s == k - 1) ? ld[q][s] : kth;
-                }
-                if (!__any_sync(FULL_MASK, d <= kth)) { n_stale++; continue; }
-                // An exactly equal distance already in some lane's list?  Only then does the
-                // original index decide and the (more expensive) full-key insertion run.
-                if (PRECHECK) {
-                    bool tie = false;
-#pragma unroll
-                    for (int s = 0; s < K; s++) tie |= d == ld[q][s];
-                    if (__any_sync(FULL_MASK, tie && d < PP_INF))
-                        km_insert<K, true>(ld[q], li[q], d, j);
-                    else
-                        km_insert<K, false>(ld[q], li[q], d, j);
-                } else {
-                    km_insert<K, true>(ld[q], li[q], d, j);
-                }
-            }
-            cnt[q] = 0;
-            float t = ld[q][0];
-#pragma unroll
-            for (int s = 1; s < K; s++) t = (s < k) ? ld[q][s] : t;
-            tau[q] = fminf(t, tau0[q]);
-        }
-    };
-
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            wlo[c] = fminf(wlo[c], __shfl_xor_sync(FULL_MASK, wlo[c], o));
-            whi[c] = fmaxf(whi[c], __shfl_xor_sync(FULL_MASK, whi[c], o));
-        }
-    }
-    if ((tid & 31) == 0) {
+    const float nqx = -qx, nqy = -qy, nqz = -qz;
+    float clo[3], chi[3];
+    {
+        const float c3[3] = {qx, qy, qz};
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            s_qbox[tid >> 5][c] = wlo[c];
-            s_qbox[tid >> 5][3 + c] = whi[c];
+            const bool fin = active && c3[c] == c3[c] && fabsf(c3[c]) != PP_INF;
+            float lo = fin ? c3[c] : PP_INF, hi = fin ? c3[c] : -PP_INF;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(FULL_MASK, lo, o));
+                hi = fmaxf(hi, __shfl_xor_sync(FULL_MASK, hi, o));
+            }
+            clo[c] = lo;
+            chi[c] = hi;
         }
     }
-    __syncthreads();
-    const int t0 = s_start;
-    float clo[3], chi[3];  // the CTA's query box
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        clo[c] = s_qbox[0][c];
-        chi[c] = s_qbox[0][3 + c];
-#pragma unroll
-        for (int w = 1; w < KM_THREADS / 32; w++) {
-            clo[c] = fminf(clo[c], s_qbox[w][c]);
-            chi[c] = fmaxf(chi[c], s_qbox[w][3 + c]);
-        }
-    }
-    const float4 *boxes = tileboxes + (size_t)b * ntiles * (1 + KM_SUB) * 2;
-    const float4 *subboxes = boxes + (size_t)ntiles * 2;
-    float wtaumax = PP_INF;  // this warp's largest k-th distance, refreshed by block_taumax()
-    int tau_par = 0;
-    // largest k-th distance over the CTA's live queries (block-uniform result; one barrier)
-    auto block_taumax = [&]() -> float {
-        float m = 0.f;
-#pragma unroll
-        for (int q = 0; q < Q; q++) m = fmaxf(m, active[q] ? tau[q] : 0.f);
-        const int wm = __reduce_max_sync(FULL_MASK, __float_as_int(m));  // non-negative floats order as ints
-        wtaumax = __int_as_float(wm);
-        if ((tid & 31) == 0) s_wtau[tau_par][tid >> 5] = wm;
-        __syncthreads();
-        int bm = s_wtau[tau_par][0];
-#pragma unroll
-        for (int w = 1; w < KM_THREADS / 32; w++) bm = max(bm, s_wtau[tau_par][w]);
-        tau_par ^= 1;
-        return __int_as_float(bm);
-    };
+    for (int e = lane; e < 32 * LP; e += 32) (&sL[0][0])[e] = KM_EMPTY;
+    __syncwarp();
+
+    float tau = PP_INF, tau0 = PP_INF;  // accept d <= tau; tau0 = seed (upper bound of the k-th distance)
+    int cnt = 0;
     unsigned long long n_visited = 0;
 
-    // ---- threshold seed: a cheap UPPER BOUND tau0 on every query's k-th distance, taken from the
-    // home tile before the real sweep.  The tile is cut into G = K/2 groups; per group the
-    // two smallest distances are tracked with three FMNMX per pair; the largest "second
-    // smallest" over the groups has 2G >= k distinct points at or below it.  The sweep then
-    // starts with the filter d <= tau0 instead of d <= inf, which removes most of the warm-up
-    // candidates (the expensive part of a streaming top-k on a few thousand points).
-    if (ESTIMATE) {
-        const int tile0 = t0 * KM_TILE;
-        for (int u = tid; u < KM_TILE; u += KM_THREADS) {
-            const int j = tile0 + u;
-            float x = PP_INF, y = PP_INF, z = PP_INF;
+    // Drain the per-lane buffers into the shared lists.  K <= 16: the two half-warps serve two
+    // source lanes at once.
+    auto drain = [&]() {
+        __syncwarp();
+        unsigned have = __ballot_sync(FULL_MASK, cnt > 0);
+        const int half = W == 16 ? (lane >> 4) : 0;
+        const int sl = lane & (W - 1);
+        while (have != 0u) {
+            const int a = __ffs(have) - 1;
+            have &= have - 1u;
+            int bsrc = -1;
+            if (W == 16 && have != 0u) {
+                bsrc = __ffs(have) - 1;
+                have &= have - 1u;
+            }
+            const int na = __shfl_sync(FULL_MASK, cnt, a);
+            const int nb = __shfl_sync(FULL_MASK, cnt, bsrc < 0 ? 0 : bsrc);
+            const int src = half == 0 ? a : (bsrc < 0 ? a : bsrc);
+            const int n = half == 0 ? na : (bsrc < 0 ? 0 : nb);
+            const int steps = max(na, bsrc < 0 ? 0 : nb);
+            const bool slot = sl < k;
+            unsigned long long my = slot ? sL[src][sl] : 0ull;  // 0 never compares greater: inert lanes
+            for (int e = 0; e < steps; e++) {
+                unsigned long long key = ~0ull;  // nothing to insert: greater than every entry
+                if (e < n)
+                    key = ((unsigned long long)__float_as_uint(sBD[e][src]) << 32) | (unsigned)sBI[e][src];
+                const unsigned m = __ballot_sync(FULL_MASK, key < my);
+                if (m == 0u) continue;  // warp-uniform: both candidates already beaten
+                const unsigned mh = W == 16 ? ((m >> (16 * half)) & 0xffffu) : m;
+                const unsigned plo = __shfl_up_sync(FULL_MASK, (unsigned)my, 1, W);
+                const unsigned phi = __shfl_up_sync(FULL_MASK, (unsigned)(my >> 32), 1, W);
+                if (mh != 0u && slot) {
+                    const int pos = __ffs(mh) - 1;  // first slot that is larger: the candidate goes here
+                    if (sl == pos) my = key;
+                    else if (sl > pos) my = ((unsigned long long)phi << 32) | plo;
+                }
+            }
+            if (slot && n > 0) sL[src][sl] = my;
+        }
+        __syncwarp();
+        cnt = 0;
+        tau = fminf(tau0, __uint_as_float((unsigned)(sL[lane][k - 1] >> 32)));
+    };
+
+    auto load_tile = [&](int t, bool with_index) {
+#pragma unroll
+        for (int u = lane; u < KM_TILE; u += 32) {
+            const int j = t * KM_TILE + u;
+            float x = PP_INF, y = PP_INF, z = PP_INF;  // padding: d = inf
+            int oi = 0x7fffffff;
             if (j < N) {
                 x = __ldg(pp_ + (size_t)j * 3);
                 y = __ldg(pp_ + (size_t)j * 3 + 1);
                 z = __ldg(pp_ + (size_t)j * 3 + 2);
+                if (with_index) oi = __ldg(pi + j);
             }
-            sX[u] = x; sY[u] = y; sZ[u] = z;
+            sX[u] = x; sY[u] = y; sZ[u] = z; sI[u] = oi;
         }
-        __syncthreads();
-        // K/2 interleaved groups (point u -> group u mod G): every group is a uniform sample of the
-        // tile, so each group's second-smallest distance is already close to the k-th distance
-        // (consecutive groups would be dominated by the group farthest from the query)
+    };
+
+    // ---- threshold seed: a cheap UPPER BOUND tau0 on every query's k-th distance, taken from the
+    // home tile before the real sweep.  The tile is cut into G = K/2 interleaved groups (point u
+    // -> group u mod G: every group is a uniform sample of the tile); per group the two smallest
+    // distances are tracked with three FMNMX per pair; the largest "second smallest" over the
+    // groups has 2G >= k distinct points at or below it.  The sweep then starts with the filter
+    // d <= tau0 instead of d <= inf, which removes most of the warm-up candidates.
+    if (seed) {
+        load_tile(t0, false);
+        __syncwarp();
         constexpr int G = K / 2;
-        float m1[Q][G], m2[Q][G];
+        float m1[G], m2[G];
 #pragma unroll
-        for (int q = 0; q < Q; q++)
-#pragma unroll
-            for (int g = 0; g < G; g++) m1[q][g] = m2[q][g] = PP_INF;
+        for (int g = 0; g < G; g++) m1[g] = m2[g] = PP_INF;
 #pragma unroll 1
         for (int jj0 = 0; jj0 < KM_TILE; jj0 += G) {
 #pragma unroll
@@ -422,165 +364,112 @@ knn_morton_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, con
                 const float4 X = *reinterpret_cast<const float4 *>(sX + jj);
                 const float4 Y = *reinterpret_cast<const float4 *>(sY + jj);
                 const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj);
+                const float2 a2 = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), nqx, nqy, nqz);
+                const float2 c2 = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), nqx, nqy, nqz);
+                const float dd[4] = {a2.x, a2.y, c2.x, c2.y};
 #pragma unroll
-                for (int q = 0; q < Q; q++) {
-                    const float2 a = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y),
-                                                 nqx[q], nqy[q], nqz[q]);
-                    const float2 c = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
-                                                 nqx[q], nqy[q], nqz[q]);
-                    const float dd[4] = {a.x, a.y, c.x, c.y};
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        m2[q][4 * v + r] = fminf(m2[q][4 * v + r], fmaxf(m1[q][4 * v + r], dd[r]));  // second smallest
-                        m1[q][4 * v + r] = fminf(m1[q][4 * v + r], dd[r]);                            // smallest
-                    }
+                for (int r = 0; r < 4; r++) {
+                    m2[4 * v + r] = fminf(m2[4 * v + r], fmaxf(m1[4 * v + r], dd[r]));  // second smallest
+                    m1[4 * v + r] = fminf(m1[4 * v + r], dd[r]);                        // smallest
                 }
             }
         }
-        float est[Q];
+        float est = 0.f;
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            est[q] = 0.f;
-#pragma unroll
-            for (int g = 0; g < G; g++) est[q] = fmaxf(est[q], m2[q][g]);
-        }
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            tau0[q] = est[q];  // +inf when the home tile is too short: the seed is then simply unused
-            tau[q] = est[q];
-        }
+        for (int g = 0; g < G; g++) est = fmaxf(est, m2[g]);
+        tau0 = est;  // +inf when the home tile is too short: the seed is then simply unused
+        tau = est;
+        __syncwarp();
     }
-    // outward sweep: t0, t0+1, t0-1, t0+2, ... (wrapping), nearest tiles first
+
+    const float4 *boxes = tileboxes + (size_t)b * ntiles * (1 + KM_SUB) * 2;
+    // largest k-th distance over the warp's live queries (non-negative floats order as ints)
+    auto warp_taumax = [&]() -> float {
+        return __int_as_float(__reduce_max_sync(FULL_MASK, __float_as_int(active ? tau : 0.f)));
+    };
+    // outward along the curve: t0, t0+1, t0-1, t0+2, ... (wrapping)
     auto tile_of = [&](int s) -> int {
         int t = (s & 1) ? t0 + (s + 1) / 2 : t0 - s / 2;
         t %= ntiles;
         return t < 0 ? t + ntiles : t;
     };
-    // Exact pruning.  Pass 0 visits the tiles whose box touches the queries' box (that is where the
-    // neighbours are, wherever the curve put them), pass 1 the rest -- by then the thresholds
-    // are tight and nearly all of them are provably too far.  Evaluation order never changes the
-    // result (selection is by the total order (distance, original index)).
+
     for (int pass = 0; pass < (prune ? 2 : 1); pass++) {
-    for (int s0 = 0; s0 < ntiles; s0 += 32) {
-      // 32 sweep steps at a time: lane l tests the box of step s0+l against the CTA's query box
-      // and the largest k-th distance so far.  Thresholds only shrink, so a tile that is provably
-      // too far now stays too far; survivors are re-tested with the fresh threshold right before
-      // they are loaded (their gap is fetched from the lane that computed it).
-      unsigned todo = 0xffffffffu;
-      float gap = 0.f;
-      if (prune) {
-          const float taumax = block_taumax();
-          const int s = s0 + (tid & 31);
-          bool need = false;
-          if (s < ntiles) {
-              const int t = tile_of(s);
-              gap = km_box_gap2(clo, chi, __ldg(boxes + t * 2), __ldg(boxes + t * 2 + 1));
-              const bool touching = !(gap > 0.f);  // NaN counts as touching: visit early, never skip
-              need = pass == 0 ? touching : (!touching && !km_can_skip(gap, taumax));
-          }
-          todo = __ballot_sync(FULL_MASK, need);
-      } else if (ntiles - s0 < 32) {
-          todo = (1u << (ntiles - s0)) - 1u;
-      }
-      while (todo != 0u) {
-        const int bit = __ffs(todo) - 1;
-        const int s = s0 + bit;
-        todo &= todo - 1u;
-        const int t = tile_of(s);
-        const int tile0 = t * KM_TILE;
-        if (prune && pass == 1) {
-            const float taumax = block_taumax();  // also the barrier that frees the tile buffers
-            if (km_can_skip(__shfl_sync(FULL_MASK, gap, bit), taumax)) continue;
-        } else {
-            __syncthreads();
-        }
-        for (int u = tid; u < KM_TILE; u += KM_THREADS) {
-            const int j = tile0 + u;
-            float x = PP_INF, y = PP_INF, z = PP_INF;  // padding: d = inf
-            int oi = 0x7fffffff;
-            if (j < N) {
-                x = __ldg(pp_ + (size_t)j * 3);
-                y = __ldg(pp_ + (size_t)j * 3 + 1);
-                z = __ldg(pp_ + (size_t)j * 3 + 2);
-                oi = __ldg(pi + j);
+        for (int s0 = 0; s0 < ntiles; s0 += 32) {
+            // Thresholds only shrink, so a tile that is provably too far now stays too far;
+            // survivors are re-tested with the fresh threshold right before they are loaded
+            // (their gap is fetched from the lane that computed it).
+            unsigned todo = 0xffffffffu;
+            float gap = 0.f;
+            if (prune) {
+                const float taumax = warp_taumax();
+                const int s = s0 + lane;
+                bool need = false;
+                if (s < ntiles) {
+                    const int t = tile_of(s);
+                    gap = km_box_gap2(clo, chi, __ldg(boxes + t * 2), __ldg(boxes + t * 2 + 1));
+                    const bool touching = !(gap > 0.f);  // NaN counts as touching: visit early, never skip
+                    need = pass == 0 ? touching : (!touching && !km_can_skip(gap, taumax));
+                }
+                todo = __ballot_sync(FULL_MASK, need);
+            } else if (ntiles - s0 < 32) {
+                todo = (1u << (ntiles - s0)) - 1u;
             }
-            sX[u] = x; sY[u] = y; sZ[u] = z; sI[u] = oi;
-        }
-        __syncthreads();
-        // the tile is here because SOME warp may need it; each warp now tests its own (smaller)
-        // query box against the tile's sub-boxes and sweeps only the sub-tiles it cannot rule out
-        unsigned sub = (1u << KM_SUB) - 1u;
-        if (prune && KM_SUB > 1) {
-            bool need = false;
-            if ((tid & 31) < KM_SUB) {
-                const float4 *sb = subboxes + ((size_t)t * KM_SUB + (tid & 31)) * 2;
-                need = !km_can_skip(km_box_gap2(wlo, whi, __ldg(sb), __ldg(sb + 1)), wtaumax);
-            }
-            sub = __ballot_sync(FULL_MASK, need);
-        }
-        if ((tid & 31) == 0) n_visited += __popc(sub);
+            while (todo != 0u) {
+                const int bit = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const int t = tile_of(s0 + bit);
+                if (prune && pass == 1 && km_can_skip(__shfl_sync(FULL_MASK, gap, bit), warp_taumax())) continue;
+                n_visited++;
+                __syncwarp();
+                load_tile(t, true);
+                __syncwarp();
 #pragma unroll 1
-        for (; sub != 0u; sub &= sub - 1u) {
-        const int j0 = (__ffs(sub) - 1) * KM_SUBLEN;
-#pragma unroll 1
-        for (int jj = j0; jj < j0 + KM_SUBLEN; jj += 4) {
-            const float4 X = *reinterpret_cast<const float4 *>(sX + jj);
-            const float4 Y = *reinterpret_cast<const float4 *>(sY + jj);
-            const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj);
-            float2 d01[Q], d23[Q];
-            bool cand = false;
+                for (int jj = 0; jj < KM_TILE; jj += 8) {
+                    // 8 points per trip: two LDS.128 triples, four packed distance pairs, ONE vote
+                    float2 d[4];
 #pragma unroll
-            for (int q = 0; q < Q; q++) {
-                d01[q] = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y),
-                                     nqx[q], nqy[q], nqz[q]);
-                d23[q] = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w),
-                                     nqx[q], nqy[q], nqz[q]);
-                // '<=': an equal distance with a lower original index still has to get in
-                cand |= fminf(fmin3(d01[q].x, d01[q].y, d23[q].x), d23[q].y) <= tau[q];
-            }
-            if (__any_sync(FULL_MASK, cand)) {
-                bool full = false;
+                    for (int h = 0; h < 2; h++) {
+                        const float4 X = *reinterpret_cast<const float4 *>(sX + jj + 4 * h);
+                        const float4 Y = *reinterpret_cast<const float4 *>(sY + jj + 4 * h);
+                        const float4 Z = *reinterpret_cast<const float4 *>(sZ + jj + 4 * h);
+                        d[2 * h] = sqdist2_xyz(make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y), nqx, nqy, nqz);
+                        d[2 * h + 1] = sqdist2_xyz(make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w), nqx, nqy, nqz);
+                    }
+                    // '<=': an equal distance with a lower original index still has to get in
+                    const float lo8 = fmin3(fmin3(d[0].x, d[0].y, d[1].x), fmin3(d[1].y, d[2].x, d[2].y), fminf(d[3].x, d[3].y));
+                    if (__any_sync(FULL_MASK, lo8 <= tau)) {
+                        const float dd[8] = {d[0].x, d[0].y, d[1].x, d[1].y, d[2].x, d[2].y, d[3].x, d[3].y};
 #pragma unroll
-                for (int q = 0; q < Q; q++) {
-                    const float dd[4] = {d01[q].x, d01[q].y, d23[q].x, d23[q].y};
+                        for (int h = 0; h < 2; h++) {
 #pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        if (dd[r] <= tau[q] && dd[r] < PP_INF) {
-                            sBD[q][cnt[q]][tid] = dd[r];
-                            sBI[q][cnt[q]][tid] = sI[jj + r];
-                            cnt[q]++;
+                            for (int r = 0; r < 4; r++) {
+                                if (dd[4 * h + r] <= tau && dd[4 * h + r] < PP_INF) {
+                                    sBD[cnt][lane] = dd[4 * h + r];
+                                    sBI[cnt][lane] = sI[jj + 4 * h + r];
+                                    cnt++;
+                                }
+                            }
+                            // a lane can add 4 per half-trip: drain while 4 more still fit everywhere
+                            if (__any_sync(FULL_MASK, cnt > KM_CB - 4)) drain();
                         }
                     }
-                    full |= cnt[q] > KM_CB - 4;
                 }
-                if (__any_sync(FULL_MASK, full)) drain();
             }
         }
-        }
-      }
-    }
     }
     drain();
-    if (visited != nullptr) {
-        if ((tid & 31) == 0) { atomicAdd(visited, n_visited); atomicAdd(visited + 1, (unsigned long long)n_iter); atomicAdd(visited + 3, (unsigned long long)n_stale); }
-        atomicAdd(visited + 2, (unsigned long long)n_cand);
-    }
+    if (visited != nullptr && lane == 0) atomicAdd(visited, n_visited);
 
-    const int *qi = sqi + (size_t)b * M;
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        const int i = qbase + (tid >> 5) * (32 * Q) + q * 32 + (tid & 31);
-        if (i < M) {
-            const int orig = __ldg(qi + i);
-            float *od = dist + ((size_t)b * M + orig) * k;
-            int *oi = idx + ((size_t)b * M + orig) * k;
-#pragma unroll
-            for (int s = 0; s < K; s++) {
-                if (s < k) {
-                    od[s] = ld[q][s];
-                    oi[s] = li[q][s] == 0x7fffffff ? -1 : li[q][s];
-                }
-            }
+    if (active) {
+        const int orig = __ldg(sqi + (size_t)b * M + qi_);
+        float *od = dist + ((size_t)b * M + orig) * k;
+        int *oi = idx + ((size_t)b * M + orig) * k;
+        for (int s = 0; s < k; s++) {
+            const unsigned long long key = sL[lane][s];
+            const int j = (int)(unsigned)key;
+            od[s] = __uint_as_float((unsigned)(key >> 32));
+            oi[s] = j == 0x7fffffff ? -1 : j;
         }
     }
 }
@@ -686,44 +575,26 @@ int knn_morton_launch(const float *query, const float *points, int B, int M, int
     unsigned long long *visited = nullptr;
     if (get_option("knn_stats", 0)) {
         visited = (unsigned long long *)(wsP + L.bbox + 32);
-        PP_CUDA(cudaMemsetAsync(visited, 0, 4 * sizeof(unsigned long long), st));
+        PP_CUDA(cudaMemsetAsync(visited, 0, sizeof(unsigned long long), st));
     }
     {
-    KernelTimer timer("knn", st);
-    // Two tunings of the same kernel (measured on B200, k=16): small clouds sweep few points per
-    // candidate, so selection dominates -> deeper candidate buffers and the cheaper
-    // distances-only insertion with a tie pre-check (1.39 vs 1.51 ms at B=32 N=8192); large
-    // clouds live in the hot loop, where the leaner full-key-only variant wins (18.6 vs 20.6 ms
-    // at B=4 N=131072).
-    const bool small = get_option("knn_small_tuning", N <= 32768 ? 1 : 0) != 0;
-#define KM_LAUNCH(KK, QQ)                                                                                   \
-    do {                                                                                                    \
-        dim3 grid(ceil_div(M, KM_THREADS * QQ), B);                                                         \
-        if (small && est)                                                                                   \
-            knn_morton_kernel<KK, QQ, 16, true, true><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, boxes, prune, M, N, k, dist, idx, visited); \
-        else if (small)                                                                                     \
-            knn_morton_kernel<KK, QQ, 16, true, false><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, boxes, prune, M, N, k, dist, idx, visited); \
-        else if (est)                                                                                       \
-            knn_morton_kernel<KK, QQ, 8, false, true><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, boxes, prune, M, N, k, dist, idx, visited); \
-        else                                                                                                \
-            knn_morton_kernel<KK, QQ, 8, false, false><<<grid, KM_THREADS, 0, st>>>(sq, sqi, qk, sp, spi, pk, boxes, prune, M, N, k, dist, idx, visited); \
-    } while (0)
-    const bool est = get_option("knn_estimate", 1) != 0;
-    if (k <= 8) KM_LAUNCH(8, 2);
-    else if (k <= 16) { if (get_option("knn_q1", 1)) KM_LAUNCH(16, 1); else KM_LAUNCH(16, 2); }
-    else KM_LAUNCH(32, 1);
-#undef KM_LAUNCH
-    PP_LAUNCH_CHECK();
+        KernelTimer timer("knn", st);
+        const int seed = get_option("knn_estimate", 1);
+        dim3 grid(ceil_div(M, 32), B);
+        if (k <= 8)
+            knn_sweep_kernel<8><<<grid, 32, 0, st>>>(sq, sqi, qk, sp, spi, pk, boxes, prune, seed, M, N, k, dist, idx, visited);
+        else if (k <= 16)
+            knn_sweep_kernel<16><<<grid, 32, 0, st>>>(sq, sqi, qk, sp, spi, pk, boxes, prune, seed, M, N, k, dist, idx, visited);
+        else
+            knn_sweep_kernel<32><<<grid, 32, 0, st>>>(sq, sqi, qk, sp, spi, pk, boxes, prune, seed, M, N, k, dist, idx, visited);
+        PP_LAUNCH_CHECK();
     }
     if (visited != nullptr) {  // diagnostics only: synchronises the stream
-        unsigned long long v4[4] = {0, 0, 0, 0};
-        PP_CUDA(cudaMemcpyAsync(v4, visited, sizeof(v4), cudaMemcpyDeviceToHost, st));
+        unsigned long long v = 0;
+        PP_CUDA(cudaMemcpyAsync(&v, visited, sizeof(v), cudaMemcpyDeviceToHost, st));
         PP_CUDA(cudaStreamSynchronize(st));
-        const unsigned long long v = v4[0];
-        fprintf(stderr, "[knn stats] warp drain iterations %llu (per warp-query %.1f), lane candidates %llu (per query %.1f), stale-skipped %llu\n", v4[1], (double)v4[1] / ((double)B * M / 32), v4[2], (double)v4[2] / ((double)B * M), v4[3]);
         g_knn_tiles_visited = (double)v;
-        const int qper = KM_THREADS * ((k <= 16 && !(k > 8 && get_option("knn_q1", 1))) ? 2 : 1);
-        g_knn_tiles_total = (double)B * ceil_div(M, qper) * (KM_THREADS / 32) * ceil_div(N, KM_TILE) * KM_SUB;
+        g_knn_tiles_total = (double)B * ceil_div(M, 32) * ceil_div(N, KM_TILE);
     }
     return PP_OK;
 }
