@@ -371,7 +371,9 @@ static bool knn_use_morton(int B, int M, int N, int c, int k) {
     if (c != 3 || k > 32) return false;
     const int opt = get_option("knn_morton", -1);
     if (opt >= 0) return opt != 0;
-    return N >= 4096 && (long long)B * M >= 4096;
+    // measured crossover on B200 (k = 16): the sort + box preparation costs ~0.12 ms, the streaming
+    // kernel ~0.3 ms at N = 4096 whatever the batch, and at N = 2500 once the batch fills the GPU
+    return N >= 4096 || (N >= 2304 && (long long)B * M >= 65536);
 }
 
 extern "C" size_t pp_knn_workspace_bytes(int B, int M, int N, int c, int k) {

@@ -1,19 +1,19 @@
-// knn_morton.cu -- spatially ordered sweep for group_knn on large clouds.
+// knn_morton.cu -- spatially ordered, exactly pruned sweep for group_knn on large clouds.
 //
-// Why: the streaming top-k of knn.cu is dominated, on unordered clouds, by its "rare" path --
-// with 32 lanes x Q queries looking at unrelated neighbourhoods, some lane finds a candidate
-// in most 4-point steps, so the warp keeps leaving the FP32-bound hot loop.  Here both clouds
-// are first sorted along a Morton (Z-order) curve, a CTA's queries are therefore spatial
-// neighbours, and the sweep over the (sorted) points STARTS at the CTA's own position on the
-// curve and works outwards.  After the first tiles every query's k-th distance is nearly final,
-// candidates become rare AND coincide across lanes, and the rest of the sweep stays in the
-// hot loop.  The result is exactly the same as the unordered sweep: selection and final order
-// use the lexicographic key (distance, ORIGINAL index), distances are evaluated in the same
-// rounding order, and the permutation is undone when rows are written.
+// Why: a brute-force top-k evaluates B*M*N distances (8 flop each) and, on unordered clouds,
+// spends even more in its selection path.  Here both clouds are first sorted along a Morton
+// (Z-order) curve.  A warp's 32 queries are then spatial neighbours and every 64 consecutive
+// points form a compact tile with a small bounding box, so a tile whose box is farther from the
+// warp's query box than the largest current k-th distance cannot contribute and is never
+// loaded.  On uniform clouds 2 % (N = 131072) to 25 % (N = 8192) of the tiles survive.
+// The result is bit-identical to the unordered brute-force sweep: distances are evaluated in the
+// same rounding order, selection and final order use the total order (distance, ORIGINAL
+// index), a tile is only skipped when that is provably safe in floating point, and the
+// permutation is undone when rows are written.
 //
 // Pipeline (all on the caller's stream, scratch in the caller's workspace):
 //   bbox (atomic min/max) -> 30-bit Morton keys tagged with the batch index -> cub radix sort
-//   -> gather sorted coordinates + original indices -> knn_morton_kernel.
+//   -> gather sorted coordinates + original indices -> per-tile bounding boxes -> knn_sweep_kernel.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "pp_common.cuh"
@@ -22,8 +22,6 @@ namespace pp {
 namespace {
 
 constexpr int KM_TILE = 64;
-constexpr int KM_SUB = 1;                   // sub-tiles per tile, each with its own bounding box
-constexpr int KM_SUBLEN = KM_TILE / KM_SUB;  // 64 points = two warps of the box kernel
 
 __device__ __forceinline__ int float_to_ordered(float f) {
     const int i = __float_as_int(f);
@@ -138,22 +136,15 @@ km_tilebox_kernel(const float *__restrict__ sorted_xyz, int N, int ntiles, float
         }
     }
     __syncthreads();
-    // thread 0: the whole tile; threads 1..KM_SUB: sub-tile u-1 (KM_SUBLEN/32 warps each)
-    if (u <= KM_SUB) {
-        const int w0 = u == 0 ? 0 : (u - 1) * (KM_SUBLEN / 32);
-        const int w1 = u == 0 ? KM_TILE / 32 : w0 + KM_SUBLEN / 32;
+    if (u == 0) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            lo[c] = PP_INF;
-            hi[c] = -PP_INF;
-            for (int w = w0; w < w1; w++) {
+            for (int w = 1; w < KM_TILE / 32; w++) {
                 lo[c] = fminf(lo[c], red[w][c]);
                 hi[c] = fmaxf(hi[c], red[w][3 + c]);
             }
         }
-        // per cloud: [ntiles] tile boxes, then [ntiles][KM_SUB] sub-tile boxes
-        const size_t slot = u == 0 ? (size_t)t : (size_t)ntiles + (size_t)t * KM_SUB + (u - 1);
-        float4 *o = boxes + ((size_t)b * ntiles * (1 + KM_SUB) + slot) * 2;
+        float4 *o = boxes + ((size_t)b * ntiles + t) * 2;
         o[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
         o[1] = make_float4(hi[1], hi[2], 0.f, 0.f);
     }
@@ -280,16 +271,48 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
     __syncwarp();
 
     float tau = PP_INF, tau0 = PP_INF;  // accept d <= tau; tau0 = seed (upper bound of the k-th distance)
-    int cnt = 0;
+    int cnt = 0;          // candidates waiting in this lane's buffer
+    int fill = 0;         // entries appended to this lane's list while it is not yet full (unsorted)
+    bool sorted = false;  // list complete and in order: from here on candidates go through the buffer
     unsigned long long n_visited = 0;
 
     // Drain the per-lane buffers into the shared lists.  K <= 16: the two half-warps serve two
     // source lanes at once.
-    auto drain = [&]() {
+    auto drain = [&](bool final) {
         __syncwarp();
-        unsigned have = __ballot_sync(FULL_MASK, cnt > 0);
         const int half = W == 16 ? (lane >> 4) : 0;
         const int sl = lane & (W - 1);
+        // Lists that just became complete were filled by plain appends (the first k accepted
+        // candidates need no ordering to be kept): order them now, one bitonic network per list
+        // across its lanes -- about 100 instructions instead of k insertions.
+        unsigned unsorted = __ballot_sync(FULL_MASK, !sorted && (fill >= k || (final && fill > 0)));
+        if (!sorted && (fill >= k || final)) sorted = true;
+        while (unsorted != 0u) {
+            const int a = __ffs(unsorted) - 1;
+            unsorted &= unsorted - 1u;
+            int bsrc = -1;
+            if (W == 16 && unsorted != 0u) {
+                bsrc = __ffs(unsorted) - 1;
+                unsorted &= unsorted - 1u;
+            }
+            const int src = half == 0 ? a : (bsrc < 0 ? a : bsrc);
+            const bool mine = sl < k && (half == 0 || bsrc >= 0);
+            unsigned long long my = sl < k ? sL[src][sl] : ~0ull;  // ~0 sorts behind every real key
+#pragma unroll
+            for (int size = 2; size <= W; size <<= 1) {
+#pragma unroll
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    const unsigned olo = __shfl_xor_sync(FULL_MASK, (unsigned)my, stride);
+                    const unsigned ohi = __shfl_xor_sync(FULL_MASK, (unsigned)(my >> 32), stride);
+                    const unsigned long long other = ((unsigned long long)ohi << 32) | olo;
+                    const bool take_min = ((sl & size) == 0) == ((sl & stride) == 0);
+                    my = (other < my) == take_min ? other : my;
+                }
+            }
+            if (mine) sL[src][sl] = my;
+        }
+        __syncwarp();
+        unsigned have = __ballot_sync(FULL_MASK, cnt > 0);
         while (have != 0u) {
             const int a = __ffs(have) - 1;
             have &= have - 1u;
@@ -324,7 +347,7 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
         }
         __syncwarp();
         cnt = 0;
-        tau = fminf(tau0, __uint_as_float((unsigned)(sL[lane][k - 1] >> 32)));
+        if (sorted) tau = fminf(tau0, __uint_as_float((unsigned)(sL[lane][k - 1] >> 32)));
     };
 
     auto load_tile = [&](int t, bool with_index) {
@@ -382,7 +405,7 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
         __syncwarp();
     }
 
-    const float4 *boxes = tileboxes + (size_t)b * ntiles * (1 + KM_SUB) * 2;
+    const float4 *boxes = tileboxes + (size_t)b * ntiles * 2;
     // largest k-th distance over the warp's live queries (non-negative floats order as ints)
     auto warp_taumax = [&]() -> float {
         return __int_as_float(__reduce_max_sync(FULL_MASK, __float_as_int(active ? tau : 0.f)));
@@ -445,20 +468,27 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
 #pragma unroll
                             for (int r = 0; r < 4; r++) {
                                 if (dd[4 * h + r] <= tau && dd[4 * h + r] < PP_INF) {
-                                    sBD[cnt][lane] = dd[4 * h + r];
-                                    sBI[cnt][lane] = sI[jj + 4 * h + r];
-                                    cnt++;
+                                    if (fill < k) {  // list not full yet: append, order comes later
+                                        sL[lane][fill] = ((unsigned long long)__float_as_uint(dd[4 * h + r]) << 32) |
+                                                         (unsigned)sI[jj + 4 * h + r];
+                                        fill++;
+                                    } else {
+                                        sBD[cnt][lane] = dd[4 * h + r];
+                                        sBI[cnt][lane] = sI[jj + 4 * h + r];
+                                        cnt++;
+                                    }
                                 }
                             }
-                            // a lane can add 4 per half-trip: drain while 4 more still fit everywhere
-                            if (__any_sync(FULL_MASK, cnt > KM_CB - 4)) drain();
+                            // a lane can add 4 per half-trip: drain while 4 more still fit everywhere,
+                            // and as soon as a list is complete (its k-th distance becomes the filter)
+                            if (__any_sync(FULL_MASK, cnt > KM_CB - 4 || (fill >= k && !sorted))) drain(false);
                         }
                     }
                 }
             }
         }
     }
-    drain();
+    drain(true);
     if (visited != nullptr && lane == 0) atomicAdd(visited, n_visited);
 
     if (active) {
@@ -491,9 +521,9 @@ KmLayout km_layout(size_t n) {
     L.vals_out = off; off = align_up(off + n * 4, 256);
     L.sorted_xyz = off; off = align_up(off + n * 12, 256);
     L.sorted_idx = off; off = align_up(off + n * 4, 256);
-    // one 32-byte box per tile and per sub-tile; clouds on this path hold >= 4096 points, so there are at most
+    // one 32-byte box per tile; clouds on this path hold >= 4096 points, so there are at most
     // n/KM_TILE + n/4096 tiles
-    L.boxes = off; off = align_up(off + (n / KM_TILE + n / 4096 + 2) * (1 + KM_SUB) * 32, 256);
+    L.boxes = off; off = align_up(off + (n / KM_TILE + n / 4096 + 2) * 32, 256);
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (const unsigned *)nullptr, (unsigned *)nullptr, (long long)n, 0, 64);
