@@ -499,10 +499,15 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
     _C.set_option("timing", 0)
     kms = tot / max(cnt, 1)
     alg_bytes = 20.0 * N * (m - 1) * B
+    smem_ms, smem_bytes = _C.microbench(4, 2048, dev.index)  # shared-memory read bandwidth, all 148 SMs
+    smem_per_sm = smem_bytes / (smem_ms * 1e-3) / 1e9 / 148.0
+    sms_used = B * 4  # the occupancy query picks 4-CTA clusters for 16 clouds: 64 SMs hold the job
     out["fps_B16_N16384_m1024"] = {
         "ms_per_step": ms, "samples_per_s": B * m / (ms * 1e-3), "kernel_ms": kms,
         "us_per_round": kms * 1e3 / (m - 1),
         "algorithmic_GBps": alg_bytes / (kms * 1e-3) / 1e9,
+        "smem_GBps_per_sm_measured": smem_per_sm, "sms_holding_the_clouds": sms_used,
+        "frac_of_smem_roofline": alg_bytes / (kms * 1e-3) / 1e9 / (smem_per_sm * sms_used),
         "note": "cloud and running minima are register-resident across a thread-block cluster: no per-round "
                 "memory traffic; algorithmic bytes = 20*N per selected sample (SURVEY.md 8d)"}
     ctr = torch.gather(x, 1, idx.long().unsqueeze(-1).expand(B, m, 3)).contiguous()
@@ -513,7 +518,30 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
     gout = torch.empty(B, 3, m, device=dev)
     ms = timeit(lambda: sampling.gather_forward(B, 3, N, m, feats, idx, gout))
     out["gather_B16_C3_m1024"] = {"ms_per_step": ms}
-    del x, ctr, feats
+    # the whole sampling + grouping work of a set-abstraction level:
+    # FPS with fused gather, then ONE fused ball-query + grouping kernel, C = 64 feature channels
+    from pytorch_points_b200 import network as ppn
+    f64 = uniform_cloud(B, N, 5, c=64).transpose(1, 2).contiguous().to(dev)
+    grouper, grouper_ops = ppn.QueryAndGroup(0.2, 32), ppn.QueryAndGroup(0.2, 32, fused=False)
+
+    def sa_fused():
+        ctr_ = ppn.furthest_point_sample(x, m, NCHW=False)[1]
+        return grouper(x, ctr_, f64)
+
+    def sa_ops():
+        i_ = ppn.FurthestPointSampling.apply(x, m, 0)
+        ctr_ = ppn.gather_points(feats, i_).transpose(1, 2).contiguous()
+        return grouper_ops(x, ctr_, f64)
+    ms_f, ms_o = timeit(sa_fused, iters=5, warm=2), timeit(sa_ops, iters=5, warm=2)
+    ms_g = timeit(lambda: grouper(x, ctr, f64))
+    ms_go = timeit(lambda: grouper_ops(x, ctr, f64))
+    out_bytes = 4.0 * B * (3 + 64) * m * 32
+    out["sa_stage_B16_N16384_m1024_r0.2_ns32_C64"] = {
+        "fused_ms": ms_f, "op_by_op_ms": ms_o, "query_and_group_fused_ms": ms_g,
+        "query_and_group_op_by_op_ms": ms_go, "query_and_group_output_GBps": out_bytes / (ms_g * 1e-3) / 1e9,
+        "note": "op_by_op = the reference's kernel sequence (FPS, gather, ball_query, 2x group_points, "
+                "subtract, cat) on this repo's single kernels"}
+    del x, ctr, feats, f64
 
     # group_knn k=16: target shape and config 4
     for (B, N, iters) in [(32, 8192, 5), (4, 131072, 2)]:
@@ -524,11 +552,22 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
         tot, cnt = _C.timing_collect("knn")
         _C.set_option("timing", 0)
         kms = tot / max(cnt, 1)
+        _C.set_option("knn_stats", 1)
+        sampling.knn(16, p, p)
+        visited, total = _C.knn_stats()
+        _C.set_option("knn_stats", 0)
+        _C.set_option("knn_prune", 0)
+        ms_dense = timeit(lambda: sampling.knn(16, p, p), iters=2, warm=1)
+        _C.set_option("knn_prune", 1)
         out["knn_k16_B%d_N%d" % (B, N)] = {
-            "ms_per_step": ms, "point_pairs_per_s": float(B) * N * N / (ms * 1e-3), "kernel_ms": kms,
-            "kernel_tflops": 8.0 * B * N * N / (kms * 1e-3) / 1e12,
-            "kernel_frac_of_fp32_peak": 8.0 * B * N * N / (kms * 1e-3) / 1e12 / peak_tflops,
-            "kernel_frac_of_op_mix_ceiling": float(B) * N * N / (kms * 1e-3) / pipe_pairs}
+            "ms_per_step": ms, "point_pairs_per_s": float(B) * N * N / (ms * 1e-3), "sweep_kernel_ms": kms,
+            "algorithmic_tflops": 8.0 * B * N * N / (ms * 1e-3) / 1e12,
+            "algorithmic_frac_of_fp32_peak": 8.0 * B * N * N / (ms * 1e-3) / 1e12 / peak_tflops,
+            "tiles_evaluated_frac": visited / max(total, 1.0),
+            "evaluated_pairs_per_s_in_sweep_kernel": float(B) * N * N * visited / max(total, 1.0) / (kms * 1e-3),
+            "ms_per_step_without_pruning": ms_dense,
+            "note": "algorithmic pairs = B*M*N (SURVEY.md 8d); exact bounding-box pruning skips the tiles that "
+                    "cannot hold a neighbour, so the algorithmic rate may exceed the FP32 pipe"}
         del p
     try:
         out["reference_cuda_kernels"] = run_reference_cuda(dev, timeit)

@@ -13,13 +13,13 @@
 // the nsample indices in shared memory, and streams the (3 + C) x nsample output tile
 // straight into its final place -- each value is written exactly once, nsample contiguous
 // floats per channel.  idx is also written (the backward pass scatters through it).
+#include "ball_scan.cuh"
 #include "pp_common.cuh"
 
 namespace pp {
 namespace {
 
 constexpr int QG_WARPS = 8;
-constexpr int QG_UNROLL = 4;
 
 __global__ void __launch_bounds__(QG_WARPS * 32)
 query_group_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz,
@@ -34,34 +34,10 @@ query_group_kernel(const float *__restrict__ new_xyz, const float *__restrict__ 
     const float *q = new_xyz + ((size_t)b * M + j) * 3;
     const float nx = __ldg(q), ny = __ldg(q + 1), nz = __ldg(q + 2);
     const float *p = xyz + (size_t)b * N * 3;
-    const unsigned lt = (1u << lane) - 1u;
 
     // ---- ball query (_ext/sampling_cuda.cu:346-375): ascending scan, strict d2 < r2 ----
-    int cnt = 0, first = 0;
-    for (int base = 0; base < N && cnt < nsample; base += 32 * QG_UNROLL) {
-        float d2[QG_UNROLL];
-#pragma unroll
-        for (int u = 0; u < QG_UNROLL; u++) {
-            const int k = base + u * 32 + lane;
-            d2[u] = PP_INF;
-            if (k < N) {
-                const float x = __ldg(p + (size_t)k * 3), y = __ldg(p + (size_t)k * 3 + 1),
-                            z = __ldg(p + (size_t)k * 3 + 2);
-                d2[u] = sqdist_yxz(__fsub_rn(nx, x), __fsub_rn(ny, y), __fsub_rn(nz, z));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < QG_UNROLL; u++) {
-            const bool hit = d2[u] < r2;
-            const unsigned mask = __ballot_sync(FULL_MASK, hit);
-            if (mask != 0u && cnt < nsample) {
-                if (cnt == 0) first = base + u * 32 + __ffs(mask) - 1;
-                const int pos = cnt + __popc(mask & lt);
-                if (hit && pos < nsample) mine[pos] = base + u * 32 + lane;
-                cnt += __popc(mask);
-            }
-        }
-    }
+    int first;
+    int cnt = ball_scan(p, N, nx, ny, nz, r2, nsample, first, [&](int pos, int k) { mine[pos] = k; });
     if (cnt > nsample) cnt = nsample;
     for (int l = cnt + lane; l < nsample; l += 32) mine[l] = first;  // first-hit padding / empty ball -> 0
     __syncwarp();

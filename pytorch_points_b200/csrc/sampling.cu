@@ -3,6 +3,7 @@
 // Replaces _ext/sampling_cuda.cu + _ext/interpolate_gpu.cu (three_nn) of the reference.
 #include <cooperative_groups.h>
 
+#include "ball_scan.cuh"
 #include "pp_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -377,7 +378,6 @@ group_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx
 // all-zero empty ball are written by the same warp, so no pre-zeroed output is needed.
 // ===========================================================================
 constexpr int BQ_WARPS = 8;
-constexpr int BQ_UNROLL = 4;
 
 __global__ void __launch_bounds__(BQ_WARPS * 32)
 ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz, int N, int M,
@@ -388,34 +388,10 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
     const int lane = threadIdx.x & 31;
     const float *q = new_xyz + ((size_t)b * M + j) * 3;
     const float nx = __ldg(q), ny = __ldg(q + 1), nz = __ldg(q + 2);
-    const float *p = xyz + (size_t)b * N * 3;
     int *out = idx + ((size_t)b * M + j) * nsample;
-    const unsigned lt = (1u << lane) - 1u;
-    int cnt = 0, first = 0;
-    for (int base = 0; base < N && cnt < nsample; base += 32 * BQ_UNROLL) {
-        float d2[BQ_UNROLL];
-#pragma unroll
-        for (int u = 0; u < BQ_UNROLL; u++) {
-            const int k = base + u * 32 + lane;
-            d2[u] = PP_INF;
-            if (k < N) {
-                const float x = __ldg(p + (size_t)k * 3), y = __ldg(p + (size_t)k * 3 + 1),
-                            z = __ldg(p + (size_t)k * 3 + 2);
-                d2[u] = sqdist_yxz(__fsub_rn(nx, x), __fsub_rn(ny, y), __fsub_rn(nz, z));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < BQ_UNROLL; u++) {
-            const bool hit = d2[u] < r2;  // strict, NaN never matches (:365)
-            const unsigned mask = __ballot_sync(FULL_MASK, hit);
-            if (mask != 0u && cnt < nsample) {
-                if (cnt == 0) first = base + u * 32 + __ffs(mask) - 1;
-                const int pos = cnt + __popc(mask & lt);
-                if (hit && pos < nsample) out[pos] = base + u * 32 + lane;
-                cnt += __popc(mask);
-            }
-        }
-    }
+    int first;
+    int cnt = ball_scan(xyz + (size_t)b * N * 3, N, nx, ny, nz, r2, nsample, first,
+                        [&](int pos, int k) { out[pos] = k; });
     if (cnt > nsample) cnt = nsample;
     // slots cnt.. hold the first hit (:366-370); an empty ball stays all zero (sampling.cpp:93-94)
     for (int l = cnt + lane; l < nsample; l += 32) out[l] = first;
