@@ -66,6 +66,7 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
     __shared__ __align__(16) float sZ[RB];
     __shared__ __align__(16) unsigned sW[RB];  // filter: best column value seen (bits)
 
+    pdl_launch_dependents();  // the finalize kernel may take the SM slots this grid's tail frees
     constexpr int TQ = Q * THREADS;
     const int b = blockIdx.y;
     const int ref_begin = blockIdx.x * RB;
@@ -232,6 +233,8 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
                         float *__restrict__ sums, int row_blocks) {
     const int lane = threadIdx.x & 31;
     float s1 = 0.f, s2 = 0.f;
+    pdl_wait();                // keys are complete and visible
+    pdl_launch_dependents();   // a following backward kernel may queue up behind us
     if ((int)blockIdx.x < row_blocks) {
         // ---- rows: 256 queries per block, 32 per warp, never straddling a cloud's end badly:
         // t indexes the flattened (B*N) query array; lanes past the end idle.
@@ -416,6 +419,8 @@ chamfer_bwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
                    const float *__restrict__ gw) {
     const long long total1 = (long long)B * N, total = total1 + (long long)B * M;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();  // indices (phase 0) / the stored own terms (phase 1) are complete and visible
+    pdl_launch_dependents();
     if (t >= total) return;
     const float *a, *bb, *gd;
     const int *idx;
@@ -487,8 +492,8 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     const int col_blocks = (int)ceil_div_ll((long long)B * M, 256);
     {
         KernelTimer timer("chamfer_finalize", st);
-        chamfer_finalize_kernel<Q><<<row_blocks + col_blocks, 256, 0, st>>>(
-            xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks);
+        PP_CUDA(launch_pdl(chamfer_finalize_kernel<Q>, dim3(row_blocks + col_blocks), dim3(256), 0, st, xyz1, xyz2, B,
+                           N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks));
     }
     PP_LAUNCH_CHECK();
     return PP_OK;
@@ -559,16 +564,6 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     switch (pick) {
         case 1: return launch_chamfer_fwd<8, 128, 256, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 2: return launch_chamfer_fwd<8, 128, 128, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 3: return launch_chamfer_fwd<8, 64, 256, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 4: return launch_chamfer_fwd<16, 128, 256, 3>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 5: return launch_chamfer_fwd<4, 128, 256, 8>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 6: return launch_chamfer_fwd<8, 256, 512, 2>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 7: return launch_chamfer_fwd<8, 128, 256, 6>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 8: return launch_chamfer_fwd<8, 128, 256, 7>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 9: return launch_chamfer_fwd<8, 128, 256, 8>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 10: return launch_chamfer_fwd<8, 128, 128, 6>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 11: return launch_chamfer_fwd<8, 256, 256, 3>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 12: return launch_chamfer_fwd<4, 128, 256, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 13: return launch_chamfer_fwd<8, 128, 256, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 14: return launch_chamfer_fwd<8, 128, 128, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         default: break;
@@ -612,9 +607,11 @@ static int chamfer_bwd_impl(const float *xyz1, const float *xyz2, const float *g
     const long long total = (long long)B * N + (long long)B * M;
     const unsigned blocks = (unsigned)ceil_div_ll(total, 256);
     KernelTimer timer("chamfer_bwd", st);
-    chamfer_bwd_kernel<0><<<blocks, 256, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, N, M, c, gradxyz1, gradxyz2, gw);
+    PP_CUDA(launch_pdl(chamfer_bwd_kernel<0>, dim3(blocks), dim3(256), 0, st, xyz1, xyz2, graddist1, graddist2, idx1,
+                       idx2, B, N, M, c, gradxyz1, gradxyz2, gw));
     PP_LAUNCH_CHECK();
-    chamfer_bwd_kernel<1><<<blocks, 256, 0, st>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, B, N, M, c, gradxyz1, gradxyz2, gw);
+    PP_CUDA(launch_pdl(chamfer_bwd_kernel<1>, dim3(blocks), dim3(256), 0, st, xyz1, xyz2, graddist1, graddist2, idx1,
+                       idx2, B, N, M, c, gradxyz1, gradxyz2, gw));
     PP_LAUNCH_CHECK();
     return PP_OK;
 }

@@ -69,6 +69,32 @@ struct DeviceGuard {
         }                                                                                  \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------
+// The hot path at the headline shape is four short kernels back to back (75 + 17 + 8 + 8 us).  A
+// kernel launched with launch_pdl() may become resident while its predecessor in the stream is
+// still draining; it must call pdl_wait() before touching anything the predecessor wrote (the
+// wait returns once all prerequisite grids have completed and their memory is visible), and a
+// predecessor lets it in early by calling pdl_launch_dependents().  Without either call the
+// behaviour is that of an ordinary launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = get_option("pdl", 1) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define PP_LAUNCH_CHECK()                                                                     \
     do {                                                                                      \
         cudaError_t _e = cudaGetLastError();                                                  \

@@ -12,7 +12,8 @@ def t(fn, iters=20):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return sorted(ts)[len(ts)//2]
 variants = [int(v) for v in sys.argv[1].split(",")]
-for (B,N) in [(32,2500),(32,8192)]:
+sizes = [(32,2500),(32,8192)] if len(sys.argv) < 3 else [tuple(int(v) for v in x.split('x')) for x in sys.argv[2].split(',')]
+for (B,N) in sizes:
     a, b = uniform_cloud(B, N, 1).cuda(), uniform_cloud(B, N, 2).cuda()
     bufs = (torch.empty(B, N, device="cuda"), torch.empty(B, N, device="cuda"),
             torch.empty(B, N, dtype=torch.int32, device="cuda"), torch.empty(B, N, dtype=torch.int32, device="cuda"))
