@@ -23,4 +23,11 @@ elif which == "knn":
     p = uniform_cloud(int(sys.argv[2]), int(sys.argv[3]), 4).cuda()
     for _ in range(2):
         sampling.knn(16, p, p)
+elif which == "qg":
+    from pytorch_points_b200 import network as pp
+    x = uniform_cloud(16, 16384, 3).cuda()
+    f = uniform_cloud(16, 16384, 5, c=64).transpose(1, 2).contiguous().cuda()
+    ctr = pp.furthest_point_sample(x, 1024, NCHW=False)[1]
+    for _ in range(2):
+        pp.query_and_group(x, ctr, f, 0.2, 32, True)
 torch.cuda.synchronize()
