@@ -282,6 +282,22 @@ def main():
         CUDA-graph replay followed by the host read of the loss."""
         return graphed.run()
 
+    in_flight = []
+    losses_read = [0]
+
+    def step_e2e_pipelined():
+        """Same graphs, software-pipelined two deep: enqueue step i+1 (its H2D copy was started during
+        step i), then read step i's loss on the host while i+1 runs."""
+        in_flight.append(graphed.submit())
+        if len(in_flight) > 1:
+            graphed.loss(in_flight.pop(0))
+            losses_read[0] += 1
+
+    def finish_pipelined():
+        while in_flight:
+            graphed.loss(in_flight.pop(0))
+            losses_read[0] += 1
+
     def step_e2e_autograd():
         """Same step through the autograd API a PyTorch user calls."""
         x = a_host.to(dev, non_blocking=True).requires_grad_(True)
@@ -315,16 +331,21 @@ def main():
             total_ms = float(t.item())
         return total_ms / steps
 
-    def timed_e2e(step, steps, warmup, stream_sync=None):
+    def timed_e2e(step, steps, warmup, finish=None):
         """One timed region over all K steps (every step's inputs arrive fresh over PCIe, so there is
-        nothing to flush): CUDA events on the current stream, every step ends with a host read."""
+        nothing to flush): CUDA events on the current stream, every step's loss is read on the host
+        inside the region (`finish` collects the one still in flight of a pipelined step)."""
         for _ in range(warmup):
             step()
+        if finish is not None:
+            finish()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             step()
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         total_ms = e0.elapsed_time(e1)
@@ -340,14 +361,19 @@ def main():
     ms_e2e_plugin = timed_e2e(step_e2e, args.steps, args.warmup)
     ms_e2e_autograd = timed_e2e(step_e2e_autograd, min(args.steps, 50), 3)
     if graphed is not None:
-        ms_e2e = timed_e2e(step_e2e_graph, args.steps, args.warmup)
-        e2e_api = ("pipeline.GraphedChamferStep.run(): compute graph(s) (pp_chamfer_fwd + finalize with fused loss sums, "
-                   "[eager NCCL all-reduce of the sums when N>1,] pp_chamfer_bwd_uniform, D2H of the sums) on one stream, "
-                   "copy graph (H2D of the NEXT step's two clouds from pinned host) on a second stream, then sync + host "
-                   "read of the loss")
+        ms_e2e_blocking = timed_e2e(step_e2e_graph, args.steps, args.warmup)
+        losses_read[0] = 0
+        ms_e2e = timed_e2e(step_e2e_pipelined, args.steps, args.warmup, finish=finish_pipelined)
+        assert losses_read[0] == args.steps + args.warmup, "every step's loss must be read on the host"
+        e2e_api = ("pipeline.GraphedChamferStep.submit()/loss(): compute graph(s) (pp_chamfer_fwd + finalize with fused loss "
+                   "sums, [eager NCCL all-reduce of the sums when N>1,] pp_chamfer_bwd_uniform, D2H of the sums) on one "
+                   "stream, copy graph (H2D of the NEXT step's two clouds from pinned host) on a second stream; "
+                   "software-pipelined two deep: the host reads step i's loss while step i+1 runs -- every step copies "
+                   "its inputs in and has its loss read on the host inside the timed region")
         loss_graph = step_e2e_graph()
     else:
         ms_e2e, e2e_api, loss_graph = ms_e2e_plugin, "see plugin_api (CUDA-graph step is single-GPU only)", None
+        ms_e2e_blocking = ms_e2e_plugin
     # separate short pass with the library's per-kernel CUDA events switched on, so the event
     # records do not perturb the two timed legs above
     _C.set_option("timing", 1)
@@ -409,6 +435,9 @@ def main():
         "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3), "unit": "point-pairs/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": world * (a_host.numel() + b_host.numel()) * 4, "d2h_bytes_per_step": world * 8,
                 "api": e2e_api,
+                "blocking_api": {"value": pairs_per_step / (ms_e2e_blocking * 1e-3), "ms_per_step": ms_e2e_blocking,
+                                 "api": "pipeline.GraphedChamferStep.run(): same graphs, the host waits for each step's loss "
+                                        "before enqueueing the next step"},
                 "plugin_api": {"value": pairs_per_step / (ms_e2e_plugin * 1e-3), "ms_per_step": ms_e2e_plugin,
                                "api": "pipeline.HostPrefetcher (pinned host -> device, double buffered) + _ext.losses.nmdistance_forward / "
                                       "nmdistance_backward_uniform (the reference-shaped plugin boundary) + D2H of the loss sums"},

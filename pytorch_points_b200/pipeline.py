@@ -68,7 +68,12 @@ class GraphedChamferStep:
     host work.  Two buffer sets alternate: while the compute graph of step i runs, the copy graph
     of step i+1 moves the next clouds over PCIe on a second stream.  `host_pairs` is one or two
     (xyz1, xyz2) pairs of PINNED host tensors (two = the loader fills one while the other is in
-    flight); results of the latest `run()`: `self.grad1`, `self.grad2`, `self.dist1` ...
+    flight); results of the latest step: `self.grad1`, `self.grad2`, `self.dist1` ... (valid in
+    `compute_stream` order).
+
+    Two ways to drive it: `run()` = one step, blocks until its loss is on the host; or
+    `t = submit()` / `loss(t)` = software pipeline of depth two -- enqueue step i+1, then read step
+    i's loss while i+1 runs (each step still copies its inputs in and its loss out).
     """
 
     def __init__(self, host_pairs, total_batch=None, device=None, group=None, world_size=1):
@@ -105,7 +110,7 @@ class GraphedChamferStep:
         self.gw = torch.tensor(self.scale, device=dev)
         self.grad1 = torch.empty(B, N, 3, device=dev)
         self.grad2 = torch.empty(B, M, 3, device=dev)
-        self.sums_host = torch.zeros(2).pin_memory()
+        self.sums_host = [torch.zeros(2).pin_memory() for _ in range(2)]  # per buffer set
         self.compute_stream = torch.cuda.Stream(dev)
         self.copy_stream = torch.cuda.Stream(dev)
         self.launches = 4  # chamfer_fwd, chamfer_finalize, chamfer_bwd<0>, chamfer_bwd<1>
@@ -125,7 +130,7 @@ class GraphedChamferStep:
         def compute_body(s):
             fwd_body(s)
             bwd_body(s)
-            self.sums_host.copy_(self.sums, non_blocking=True)
+            self.sums_host[s].copy_(self.sums, non_blocking=True)
 
         cur = torch.cuda.current_stream(dev)
         self.copy_stream.wait_stream(cur)
@@ -157,17 +162,20 @@ class GraphedChamferStep:
                     bwd_body(s)
                 self.compute_graph.append((gf, gb))
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
         self.slot = 0
         self._primed = False
 
     def _launch_copy(self, s):
         with torch.cuda.stream(self.copy_stream):
+            # set s was last read by the compute enqueued two submits ago (no-op before that)
+            self.copy_stream.wait_event(self.done[s])
             self.copy_graph[s].replay()
             self.copied[s].record(self.copy_stream)
 
-    def run(self):
-        """Run one step on the current buffer set and start moving the next set's clouds; returns the
-        loss (host float).  Blocks until the loss is on the host."""
+    def submit(self):
+        """Enqueue one step on the current buffer set and start moving the next set's clouds.
+        Returns a ticket for `loss()`; does not block."""
         s = self.slot
         if not self._primed:
             self._launch_copy(s)
@@ -183,9 +191,19 @@ class GraphedChamferStep:
                 work = dist.all_reduce(self.sums, group=self.group, async_op=True)
                 gb.replay()
                 work.wait()
-                self.sums_host.copy_(self.sums, non_blocking=True)
-        # the other set's previous consumer finished before the previous run() returned
+                self.sums_host[s].copy_(self.sums, non_blocking=True)
+            self.done[s].record(self.compute_stream)
         self._launch_copy(1 - s)
-        self.compute_stream.synchronize()
         self.slot = 1 - s
-        return float(self.sums_host[0]) * self.scale[0] + float(self.sums_host[1]) * self.scale[1]
+        return s
+
+    def loss(self, ticket):
+        """Wait for the step behind `ticket` and return its loss (host float).  A ticket is valid
+        until the second `submit()` after it."""
+        self.done[ticket].synchronize()
+        h = self.sums_host[ticket]
+        return float(h[0]) * self.scale[0] + float(h[1]) * self.scale[1]
+
+    def run(self):
+        """One step, blocking: returns the loss (host float) once it is on the host."""
+        return self.loss(self.submit())

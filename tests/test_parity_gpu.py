@@ -212,6 +212,33 @@ def test_graphed_chamfer_step_and_prefetcher(pp):
     assert torch.equal(x0.cpu(), pairs[0][0]) and torch.equal(y1.cpu(), pairs[1][1])
 
 
+def test_graphed_chamfer_step_pipelined(pp):
+    """submit()/loss(): two steps in flight; each ticket returns the loss of ITS step even though the
+    pinned host buffers are rewritten with new clouds as soon as their copy has been consumed."""
+    from pytorch_points_b200.pipeline import GraphedChamferStep
+    pairs = [(uniform_cloud(4, 700, 180 + i).pin_memory(), uniform_cloud(4, 650, 190 + i).pin_memory()) for i in range(2)]
+    clouds = [(uniform_cloud(4, 700, 300 + i), uniform_cloud(4, 650, 400 + i)) for i in range(7)]
+    want = []
+    for a0, b0 in clouds:
+        d1, d2, _, _ = pp.nndistance(dev(a0), dev(b0))
+        want.append((d1.mean() + d2.mean()).item())
+    step = GraphedChamferStep(pairs)
+    for s_ in range(2):
+        pairs[s_][0].copy_(clouds[s_][0]); pairs[s_][1].copy_(clouds[s_][1])
+    got, tickets = [], []
+    for i in range(len(clouds)):
+        tickets.append(step.submit())  # enqueues step i and the H2D copy for step i + 1
+        if i + 2 < len(clouds):
+            # host set i % 2 has been consumed by the copy for step i: refill it for step i + 2
+            step.copied[i % 2].synchronize()
+            pairs[i % 2][0].copy_(clouds[i + 2][0]); pairs[i % 2][1].copy_(clouds[i + 2][1])
+        if len(tickets) > 1:
+            got.append(step.loss(tickets.pop(0)))  # loss of step i - 1 while step i runs
+    got.append(step.loss(tickets.pop(0)))
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 1e-6 * abs(w), (got, want)
+
+
 def test_labeled_chamfer(pp, oracle_mod):
     a, b = uniform_cloud(2, 700, 27), uniform_cloud(2, 900, 28)
     g = torch.Generator().manual_seed(29)
