@@ -371,9 +371,10 @@ static bool knn_use_morton(int B, int M, int N, int c, int k) {
     if (c != 3 || k > 32) return false;
     const int opt = get_option("knn_morton", -1);
     if (opt >= 0) return opt != 0;
-    // measured crossover on B200 (k = 16): the sort + box preparation costs ~0.12 ms, the streaming
-    // kernel ~0.3 ms at N = 4096 whatever the batch, and at N = 2500 once the batch fills the GPU
-    return N >= 4096 || (N >= 2304 && (long long)B * M >= 65536);
+    // measured crossover on B200 (k = 16): with the one-launch preparation (clouds <= 16384 points)
+    // the ordered sweep wins from N = 2048 on, whatever the batch (0.196 vs 0.200 ms at B = 2,
+    // 0.236 vs 0.265 ms at B = 32); at N = 1024 the streaming kernel is still ahead
+    return N >= 2048;
 }
 
 extern "C" size_t pp_knn_workspace_bytes(int B, int M, int N, int c, int k) {

@@ -14,6 +14,7 @@
 // Pipeline (all on the caller's stream, scratch in the caller's workspace):
 //   bbox (atomic min/max) -> 30-bit Morton keys tagged with the batch index -> cub radix sort
 //   -> gather sorted coordinates + original indices -> per-tile bounding boxes -> knn_sweep_kernel.
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 #include "pp_common.cuh"
@@ -147,6 +148,161 @@ km_tilebox_kernel(const float *__restrict__ sorted_xyz, int N, int ntiles, float
         float4 *o = boxes + ((size_t)b * ntiles + t) * 2;
         o[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
         o[1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole preparation in ONE launch for clouds of up to 16384 points: a 1024-thread CTA per cloud
+// computes the batch element's bounding box, the Morton keys, sorts them in shared memory
+// (cub::BlockRadixSort), gathers the sorted coordinates / original indices and reduces the tile
+// boxes.  Replaces the 12 dependent launches of the general path (memsets, bbox, keys, cub device
+// sort, gather, boxes: ~0.14 ms at B*N = 262144, mostly launch latency) by ~30 us.
+// The order of equal keys and the exact box used for the keys only influence speed, never results.
+// ---------------------------------------------------------------------------------------------
+constexpr int KP_THREADS = 1024;
+constexpr int KP_RADIX = 5;      // digits of 5 bits: 19 key bits in 4 passes
+constexpr int KP_AXIS_BITS = 6;
+
+template <int ITEMS>
+__global__ void __launch_bounds__(KP_THREADS)
+km_prepare_small_kernel(const float *__restrict__ points, const float *__restrict__ query, int N, int M, int self,
+                        unsigned char *__restrict__ wsP, unsigned char *__restrict__ wsQ, size_t off_keys,
+                        size_t off_xyz, size_t off_idx, size_t off_boxes) {
+    // 6 bits per axis are plenty for <= 16384 points (262144 cells); bit 18 flags padding
+    using Sort = cub::BlockRadixSort<unsigned, KP_THREADS, ITEMS, int, KP_RADIX>;
+    extern __shared__ __align__(16) unsigned char kp_smem[];
+    typename Sort::TempStorage &temp = *reinterpret_cast<typename Sort::TempStorage *>(kp_smem);
+    __shared__ float red[KP_THREADS / 32][6];
+    __shared__ float box[6];
+
+    const int b = blockIdx.x;
+    const bool is_query = blockIdx.y == 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *mine = (is_query ? query + (size_t)b * M * 3 : points + (size_t)b * N * 3);
+    const int n_mine = is_query ? M : N;
+
+    // 1. bounding box of this batch element over both clouds (finite coordinates only)
+    float lo[3] = {PP_INF, PP_INF, PP_INF}, hi[3] = {-PP_INF, -PP_INF, -PP_INF};
+    for (int pass = 0; pass < (self ? 1 : 2); pass++) {
+        const float *src = pass == 0 ? points + (size_t)b * N * 3 : query + (size_t)b * M * 3;
+        const int cnt3 = (pass == 0 ? N : M) * 3;
+        // thread t reads elements t, t + 1024, ...: 1024 = 1 (mod 3), so the component advances by one
+        // each step and three unrolled steps cover x, y, z with compile-time indices
+        const int cnt = pass == 0 ? N : M;
+        const int c0 = tid % 3;
+#pragma unroll 4
+        for (int e = tid; e < cnt3; e += 3 * KP_THREADS) {
+            float v[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) v[u] = (e + u * KP_THREADS < cnt3) ? __ldg(src + e + u * KP_THREADS) : __int_as_float(0x7fc00000);
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                if (v[u] == v[u] && fabsf(v[u]) != PP_INF) {  // NaN/inf (and the out-of-range filler) are skipped
+#pragma unroll
+                    for (int cc = 0; cc < 3; cc++)
+                        if (cc == (c0 + u) % 3) {
+                            lo[cc] = fminf(lo[cc], v[u]);
+                            hi[cc] = fmaxf(hi[cc], v[u]);
+                        }
+                }
+            }
+        }
+        (void)cnt;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(FULL_MASK, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(FULL_MASK, hi[c], o));
+        }
+        if (lane == 0) {
+            red[warp][c] = lo[c];
+            red[warp][3 + c] = hi[c];
+        }
+    }
+    __syncthreads();
+    if (tid < 6) {
+        float v = red[0][tid];
+        for (int w = 1; w < KP_THREADS / 32; w++) v = tid < 3 ? fminf(v, red[w][tid]) : fmaxf(v, red[w][tid]);
+        box[tid] = v;
+    }
+    __syncthreads();
+
+    // 2. keys (blocked arrangement: thread t owns items t*ITEMS ..)
+    unsigned keys[ITEMS];
+    int vals[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const int e = tid * ITEMS + i;
+        keys[i] = 1u << (3 * KP_AXIS_BITS);  // padding sorts behind every real key
+        vals[i] = -1;
+        if (e < n_mine) {
+            unsigned q[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float ext = box[3 + c] - box[c];
+                const float v = __ldg(mine + (size_t)e * 3 + c);
+                float t = ext > 0.f ? (v - box[c]) / ext * 1023.f : 0.f;
+                t = (t == t) ? fminf(fmaxf(t, 0.f), 1023.f) : 0.f;
+                q[c] = (unsigned)t;
+            }
+            keys[i] = (spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2)) >> (3 * (10 - KP_AXIS_BITS));
+            vals[i] = e;
+        }
+    }
+    // 3. sort; striped output (item i of thread t = position i*1024 + t) keeps the stores coalesced
+    Sort(temp).SortBlockedToStriped(keys, vals, 0, 3 * KP_AXIS_BITS + 1);
+
+    // 4. sorted coordinates, original indices, keys
+    unsigned char *ws = is_query ? wsQ : wsP;
+    unsigned long long *keys_out = (unsigned long long *)(ws + off_keys) + (size_t)b * n_mine;
+    float *sxyz = (float *)(ws + off_xyz) + (size_t)b * n_mine * 3;
+    int *sidx = (int *)(ws + off_idx) + (size_t)b * n_mine;
+#pragma unroll
+    for (int i = 0; i < ITEMS; i++) {
+        const int pos = i * KP_THREADS + tid;
+        if (pos < n_mine) {
+            const int src = vals[i];
+            keys_out[pos] = ((unsigned long long)b << 32) | keys[i];
+            sidx[pos] = src;
+#pragma unroll
+            for (int c = 0; c < 3; c++) sxyz[(size_t)pos * 3 + c] = __ldg(mine + (size_t)src * 3 + c);
+        }
+    }
+    if (is_query) return;
+    // 5. tile boxes from the rows this CTA has just written (visible after the barrier)
+    __syncthreads();
+    const int ntiles = ceil_div(N, KM_TILE);
+    for (int t = warp; t < ntiles; t += KP_THREADS / 32) {
+        float tlo[3] = {PP_INF, PP_INF, PP_INF}, thi[3] = {-PP_INF, -PP_INF, -PP_INF};
+#pragma unroll
+        for (int h = 0; h < KM_TILE / 32; h++) {
+            const int pos = t * KM_TILE + h * 32 + lane;
+            if (pos < N) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float v = sxyz[(size_t)pos * 3 + c];
+                    if (v == v && fabsf(v) != PP_INF) {
+                        tlo[c] = fminf(tlo[c], v);
+                        thi[c] = fmaxf(thi[c], v);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                tlo[c] = fminf(tlo[c], __shfl_xor_sync(FULL_MASK, tlo[c], o));
+                thi[c] = fmaxf(thi[c], __shfl_xor_sync(FULL_MASK, thi[c], o));
+            }
+        }
+        if (lane == 0) {
+            float4 *o = (float4 *)(ws + off_boxes) + ((size_t)b * ntiles + t) * 2;
+            o[0] = make_float4(tlo[0], tlo[1], tlo[2], thi[0]);
+            o[1] = make_float4(thi[1], thi[2], 0.f, 0.f);
+        }
     }
 }
 
@@ -578,24 +734,44 @@ int knn_morton_launch(const float *query, const float *points, int B, int M, int
         return PP_ENOSPC;
     }
     unsigned char *wsP = ws, *wsQ = ws + L.total;
-    int *bbox = (int *)(wsP + L.bbox);
-    // bbox over both clouds: min <- big positive ints (0x7f7f7f7f), max <- big negative (0x80808080)
-    PP_CUDA(cudaMemsetAsync(bbox, 0x7f, 3 * sizeof(int), st));
-    PP_CUDA(cudaMemsetAsync(bbox + 3, 0x80, 3 * sizeof(int), st));
     const bool self = (query == points && M == N);
-    km_bbox_kernel<<<NUM_SMS_B200 * 2, 256, 0, st>>>(points, (long long)B * N, bbox);
-    PP_LAUNCH_CHECK();
-    if (!self) {
-        km_bbox_kernel<<<NUM_SMS_B200 * 2, 256, 0, st>>>(query, (long long)B * M, bbox);
+    const int big = M > N ? M : N;
+    if (big <= 16 * KP_THREADS && get_option("knn_fused_prep", 1)) {
+        // one launch: a CTA per cloud does bbox, keys, sort, gather and tile boxes
+        if (self) wsQ = wsP;
+        dim3 grid(B, self ? 1 : 2);
+#define KP_LAUNCH(ITEMS)                                                                                       \
+    do {                                                                                                       \
+        auto kern = km_prepare_small_kernel<ITEMS>;                                                            \
+        const size_t smem = sizeof(cub::BlockRadixSort<unsigned, KP_THREADS, ITEMS, int, KP_RADIX>::TempStorage);        \
+        PP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        kern<<<grid, KP_THREADS, smem, st>>>(points, query, N, M, self ? 1 : 0, wsP, wsQ, L.keys_out, L.sorted_xyz, \
+                                             L.sorted_idx, L.boxes);                                           \
+    } while (0)
+        if (big <= 4 * KP_THREADS) KP_LAUNCH(4);
+        else if (big <= 8 * KP_THREADS) KP_LAUNCH(8);
+        else KP_LAUNCH(16);
+#undef KP_LAUNCH
         PP_LAUNCH_CHECK();
-    }
-    int rc = km_sort_cloud(points, B, N, wsP, L, bbox, true, st);
-    if (rc != PP_OK) return rc;
-    if (!self) {
-        rc = km_sort_cloud(query, B, M, wsQ, L, bbox, false, st);
-        if (rc != PP_OK) return rc;
     } else {
-        wsQ = wsP;
+        int *bbox = (int *)(wsP + L.bbox);
+        // bbox over both clouds: min <- big positive ints (0x7f7f7f7f), max <- big negative (0x80808080)
+        PP_CUDA(cudaMemsetAsync(bbox, 0x7f, 3 * sizeof(int), st));
+        PP_CUDA(cudaMemsetAsync(bbox + 3, 0x80, 3 * sizeof(int), st));
+        km_bbox_kernel<<<NUM_SMS_B200 * 2, 256, 0, st>>>(points, (long long)B * N, bbox);
+        PP_LAUNCH_CHECK();
+        if (!self) {
+            km_bbox_kernel<<<NUM_SMS_B200 * 2, 256, 0, st>>>(query, (long long)B * M, bbox);
+            PP_LAUNCH_CHECK();
+        }
+        int rc = km_sort_cloud(points, B, N, wsP, L, bbox, true, st);
+        if (rc != PP_OK) return rc;
+        if (!self) {
+            rc = km_sort_cloud(query, B, M, wsQ, L, bbox, false, st);
+            if (rc != PP_OK) return rc;
+        } else {
+            wsQ = wsP;
+        }
     }
     const float *sp = (const float *)(wsP + L.sorted_xyz), *sq = (const float *)(wsQ + L.sorted_xyz);
     const int *spi = (const int *)(wsP + L.sorted_idx), *sqi = (const int *)(wsQ + L.sorted_idx);
