@@ -238,14 +238,37 @@ def main():
 
     gw = torch.tensor([1.0 / (total_B * N), 1.0 / (total_B * M)], device=dev)
 
+    # The one collective: global [sum(dist1), sum(dist2)].  Default = the peer-memory exchange
+    # (pp_loss_exchange_send / _wait: NVLink P2P stores into the peers' mailboxes); NCCL all-reduce
+    # if the mailboxes cannot be mapped or PP_LOSS_EXCHANGE=nccl.
+    exchange, exchange_note = None, "none (single GPU)"
+    total = sums if world == 1 else torch.zeros(2, device=dev)
+    if world > 1:
+        exchange_note = "NCCL all-reduce of the 2 partial sums"
+        if os.environ.get("PP_LOSS_EXCHANGE", "p2p") != "nccl":
+            try:
+                from pytorch_points_b200.dist import LossExchange
+                exchange = LossExchange(dev)
+                exchange_note = ("peer-memory exchange of the 2 partial sums (pp_loss_exchange_send/_wait: NVLink P2P "
+                                 "stores into every rank's mailbox, summed in rank order; no collective call per step)")
+            except Exception as e:  # noqa: BLE001
+                exchange_note += " (peer exchange unavailable: %s)" % (repr(e)[:120],)
+
     def step_device():
-        # forward (+ fused partial sums) -> all-reduce of the 2 sums -> backward with the two
+        # forward (+ fused partial sums) -> exchange of the 2 sums -> backward with the two
         # constant upstream weights d(loss)/d(dist) = 1/(B_total*N), 1/(B_total*M)
         losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
-        # the backward weights are constants, so the 8-byte all-reduce overlaps the backward
-        work = dist.all_reduce(sums, async_op=True) if world > 1 else None
+        # the backward weights are constants, so the exchange overlaps the backward
+        work = None
+        if exchange is not None:
+            exchange.send(sums)
+        elif world > 1:
+            total.copy_(sums)
+            work = dist.all_reduce(total, async_op=True)
         losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
-        if work is not None:
+        if exchange is not None:
+            exchange.wait(total)
+        elif work is not None:
             work.wait()
 
     from pytorch_points_b200.pipeline import HostPrefetcher
@@ -261,13 +284,20 @@ def main():
         this step's kernels.  Ends with a device->host read of the step's result (the loss)."""
         xd, yd = prefetcher.get()
         losses.nmdistance_forward(xd, yd, d1, d2, i1, i2, sums=sums)
-        work = dist.all_reduce(sums, async_op=True) if world > 1 else None
+        work = None
+        if exchange is not None:
+            exchange.send(sums)
+        elif world > 1:
+            total.copy_(sums)
+            work = dist.all_reduce(total, async_op=True)
         losses.nmdistance_backward_uniform(xd, yd, e_g1, e_g2, gw, i1, i2)
         prefetcher.release()
         prefetcher.prefetch((a_host, b_host))  # host work hidden behind the kernels just launched
-        if work is not None:
+        if exchange is not None:
+            exchange.wait(total)
+        elif work is not None:
             work.wait()
-        sums_host.copy_(sums, non_blocking=True)
+        sums_host.copy_(total, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(sums_host[0]) / (total_B * N) + float(sums_host[1]) / (total_B * M)
 
@@ -275,7 +305,7 @@ def main():
     if world > 1:
         dist.all_reduce(sums)  # the communicator exists before the first replay
         torch.cuda.synchronize()
-    graphed = GraphedChamferStep([(a_host, b_host)], total_batch=total_B, device=dev, world_size=world)
+    graphed = GraphedChamferStep([(a_host, b_host)], total_batch=total_B, device=dev, world_size=world, exchange=exchange)
 
     def step_e2e_graph():
         """The whole step (H2D x2 from pinned host, forward, backward, D2H of the loss sums) as one
@@ -383,7 +413,7 @@ def main():
     kt = {nm: _C.timing_collect(nm) for nm in ("chamfer_fwd", "chamfer_finalize", "chamfer_bwd")}
     _C.set_option("timing", 0)
     clocks = sampler.stop()
-    loss_dev = float((sums[0] / (total_B * N) + sums[1] / (total_B * M)).item())
+    loss_dev = float((total[0] / (total_B * N) + total[1] / (total_B * M)).item())
     loss_e2e = step_e2e()
 
     if rank != 0:
@@ -429,7 +459,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s: Chamfer (nndistance) fwd+bwd, B=%d clouds per GPU, N=M=%d, uniform [0,1)^3, "
                                "loss = mean(dist1)+mean(dist2)%s" % (
-                                   args.workload, B, N, ", NCCL all-reduce of the 2 partial sums" if world > 1 else ""),
+                                   args.workload, B, N, (", " + exchange_note) if world > 1 else ""),
                    "global_batch": total_B, "l2": "flushed between timed steps (256 MiB write); inputs 1.9 MB < L2",
                    "timing": "per-step CUDA events on the current stream, max over ranks"},
         "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3), "unit": "point-pairs/s", "ms_per_step": ms_e2e,
@@ -443,8 +473,9 @@ def main():
                                       "nmdistance_backward_uniform (the reference-shaped plugin boundary) + D2H of the loss sums"},
                 "autograd_api": {"value": pairs_per_step / (ms_e2e_autograd * 1e-3), "ms_per_step": ms_e2e_autograd,
                                  "api": "host .to(device) + dist.sharded_chamfer_loss (torch.autograd) + loss.backward() + loss.item()"}, "timing": "one CUDA-event region over all K steps; every step copies its inputs from pinned host memory and ends with a host read of the loss"},
-        "gpu_launches": 4 * args.steps,
-        "gpu_launches_note": "per step: chamfer_fwd_kernel, chamfer_finalize_kernel, chamfer_bwd_kernel<0>, <1>",
+        "gpu_launches": (4 + (2 if exchange is not None else 0)) * args.steps,
+        "gpu_launches_note": "per step: chamfer_fwd_kernel, chamfer_finalize_kernel, chamfer_bwd_kernel<0>, <1>"
+                             + (", lx_send_kernel, lx_wait_kernel" if exchange is not None else ""),
         "clocks": clocks, "roofline": roofline,
         "loss": {"device_leg": loss_dev, "e2e_plugin_leg": loss_e2e, "e2e_graph_leg": loss_graph},
     }
@@ -570,6 +601,19 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
         "query_and_group_op_by_op_ms": ms_go, "query_and_group_output_GBps": out_bytes / (ms_g * 1e-3) / 1e9,
         "note": "op_by_op = the reference's kernel sequence (FPS, gather, ball_query, 2x group_points, "
                 "subtract, cat) on this repo's single kernels"}
+    # feature propagation: three_nn of all 16384 points against the 1024
+    # sampled centres, then three_interpolate of C = 64 coarse features back onto the 16384 points
+    d3 = torch.empty(B, N, 3, device=dev); i3 = torch.empty(B, N, 3, dtype=torch.int32, device=dev)
+    ms_nn = timeit(lambda: sampling.three_nn_wrapper(B, N, m, x, ctr, d3, i3))
+    w3 = torch.rand(B, N, 3, device=dev)
+    w3 = (w3 / w3.sum(-1, keepdim=True)).contiguous()
+    coarse = uniform_cloud(B, m, 6, c=64).transpose(1, 2).contiguous().to(dev)
+    interp = torch.empty(B, 64, N, device=dev)
+    ms_it = timeit(lambda: sampling.three_interpolate_wrapper(B, 64, m, N, coarse, i3, w3, interp))
+    out["fp_stage_B16_n16384_m1024_C64"] = {
+        "three_nn_ms": ms_nn, "three_nn_pairs_per_s": float(B) * N * m / (ms_nn * 1e-3),
+        "three_interpolate_ms": ms_it,
+        "three_interpolate_GBps": (4.0 * B * 64 * N + 24.0 * B * N) / (ms_it * 1e-3) / 1e9}
     del x, ctr, feats, f64
 
     # group_knn k=16: target shape and config 4

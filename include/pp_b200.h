@@ -202,6 +202,36 @@ int pp_three_interpolate_fwd(const float *points, const int32_t *idx, const floa
 int pp_three_interpolate_bwd(const float *grad_out, const int32_t *idx, const float *weight, int B, int C,
                              int N, int M, float *grad_points, int device, void *stream);
 
+/* ------------------------------------------------------- multi-GPU exchange */
+
+/*
+ * The one collective of the batch-sharded Chamfer step: the global
+ * [sum(dist1), sum(dist2)] over all ranks, exchanged through NVLink peer memory instead of a
+ * collective-library call.  No reference counterpart (the reference is single-GPU,
+ * SURVEY.md D7); replaces `torch.distributed.all_reduce(sums)` in the sharded step.
+ *
+ *   create : allocates this rank's mailbox and returns its CUDA IPC handle
+ *            (pp_loss_exchange_handle_bytes() bytes) for the host side to distribute;
+ *   open   : maps a PEER's mailbox (from its handle) into this process;
+ *   bind   : tells the mailbox where every rank's mailbox is mapped (peer_mailboxes[rank] =
+ *            this rank's own pointer); world <= 32;
+ *   send   : enqueue after pp_chamfer_fwd -- stores `sums` (2 floats, device) into every
+ *            peer's mailbox;
+ *   wait   : enqueue where the total is needed (after the backward, so the link latency is
+ *            hidden) -- polls the own mailbox for this step's contributions and writes their
+ *            sum, added in rank order, to sums_out (2 floats, device).  Bounded: after ~1 s
+ *            without a peer the result is NaN and *status (device int, may be NULL) is set to 1.
+ * Every rank must issue the same sequence of send/wait pairs.  Both launches are graph-capturable.
+ */
+size_t pp_loss_exchange_handle_bytes(void);
+int pp_loss_exchange_create(void **mailbox, unsigned char *handle, int device);
+int pp_loss_exchange_open(const unsigned char *handle, void **peer_mailbox, int device);
+int pp_loss_exchange_bind(void *mailbox, void *const *peer_mailboxes, int world, int device);
+int pp_loss_exchange_close(void *mailbox, void *const *peer_mailboxes, int rank, int world, int device);
+int pp_loss_exchange_send(const float *sums, void *mailbox, int rank, int world, int device, void *stream);
+int pp_loss_exchange_wait(void *mailbox, int world, float *sums_out, int32_t *status, int device,
+                          void *stream);
+
 /* ------------------------------------------------------------- diagnostics */
 
 /*

@@ -36,6 +36,13 @@ SIGNATURES = {
     "pp_knn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "pp_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "pp_knn_stats": (_i, [_vp, _vp]),
+    "pp_loss_exchange_handle_bytes": (_sz, []),
+    "pp_loss_exchange_create": (_i, [_vp, _vp, _i]),
+    "pp_loss_exchange_open": (_i, [_vp, _vp, _i]),
+    "pp_loss_exchange_bind": (_i, [_vp, _vp, _i, _i]),
+    "pp_loss_exchange_close": (_i, [_vp, _vp, _i, _i, _i]),
+    "pp_loss_exchange_send": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "pp_loss_exchange_wait": (_i, [_vp, _i, _vp, _vp, _i, _vp]),
     "pp_three_nn": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_three_interpolate_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_three_interpolate_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),

@@ -1,0 +1,177 @@
+// loss_exchange.cu -- the ONE collective of the batch-sharded Chamfer step, over NVLink peer
+// memory instead of a library call.
+//
+// The reference has no multi-GPU path; ours shards the batch and needs the global
+// [sum(dist1), sum(dist2)] for the loss value.  That is 8 bytes per rank: an
+// NCCL all-reduce of it is pure latency (~20 us per step on 8 GPUs, 20 % of the 0.1 ms step).
+// Here every rank owns a small MAILBOX in its own HBM, mapped into all peers through CUDA IPC:
+//   send:  one warp, lane p stores this rank's two partial sums straight into peer p's mailbox
+//          (two 64-bit stores over NVLink; each word carries its sequence number, so no flag,
+//          no fence and no ordering between the words is needed);
+//   wait:  one warp, lane p polls slot p of the OWN mailbox until the expected sequence number
+//          shows up, then the sums are added in rank order (bit-identical on every rank).
+// send is enqueued right after the finalize kernel, wait after the backward kernels, so the
+// NVLink latency hides behind the backward.  Both are ordinary kernels: they capture into CUDA
+// graphs (the sequence number lives in device memory) and use no host synchronisation.
+// The poll is bounded (about one second): a missing peer yields NaN sums and a status flag, never
+// a hung GPU.
+#include "pp_common.cuh"
+
+namespace pp {
+namespace {
+
+constexpr int LX_MAX_WORLD = 32;  // one lane per peer
+
+struct LxSlot {
+    unsigned long long w0, w1;  // (float bits << 32) | sequence number
+};
+
+struct LxMailbox {
+    LxSlot slot[2][LX_MAX_WORLD];  // [sequence parity][source rank]
+    unsigned seq;                  // steps sent so far (device resident: graph replays advance it)
+    unsigned pad[15];
+    LxSlot *peer[LX_MAX_WORLD];    // every rank's mailbox as mapped into THIS process
+};
+
+__device__ __forceinline__ void st_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(32)
+lx_send_kernel(const float *__restrict__ sums, LxMailbox *box, int rank, int world) {
+    pdl_wait();  // the finalize kernel's sums are complete and visible
+    pdl_launch_dependents();
+    const int lane = threadIdx.x;
+    const unsigned seq = box->seq + 1u;
+    if (lane < world) {
+        LxSlot *dst = box->peer[lane] + (size_t)(seq & 1u) * LX_MAX_WORLD + rank;
+        st_sys_u64(&dst->w0, ((unsigned long long)__float_as_uint(sums[0]) << 32) | seq);
+        st_sys_u64(&dst->w1, ((unsigned long long)__float_as_uint(sums[1]) << 32) | seq);
+    }
+    __syncwarp();
+    if (lane == 0) box->seq = seq;
+}
+
+__global__ void __launch_bounds__(32)
+lx_wait_kernel(LxMailbox *box, int world, float *__restrict__ out, int *__restrict__ status) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int lane = threadIdx.x;
+    const unsigned seq = box->seq;  // written by the send kernel earlier in this stream
+    float s1 = 0.f, s2 = 0.f;
+    bool ok = true;
+    if (lane < world) {
+        const LxSlot *src = &box->slot[seq & 1u][lane];
+        const long long t0 = clock64();
+        unsigned long long a, b;
+        for (;;) {
+            a = ld_sys_u64(&src->w0);
+            b = ld_sys_u64(&src->w1);
+            if ((unsigned)a == seq && (unsigned)b == seq) break;
+            if (clock64() - t0 > 2000000000ll) {  // ~1 s at 1.9 GHz: give up, never hang the GPU
+                ok = false;
+                break;
+            }
+            __nanosleep(64);
+        }
+        s1 = __uint_as_float((unsigned)(a >> 32));
+        s2 = __uint_as_float((unsigned)(b >> 32));
+    }
+    const bool all_ok = __all_sync(FULL_MASK, ok);
+    float t1 = 0.f, t2 = 0.f;
+    for (int p = 0; p < world; p++) {  // rank order: the same bits on every rank
+        t1 += __shfl_sync(FULL_MASK, s1, p);
+        t2 += __shfl_sync(FULL_MASK, s2, p);
+    }
+    if (lane == 0) {
+        const float nan = __int_as_float(0x7fc00000);
+        out[0] = all_ok ? t1 : nan;
+        out[1] = all_ok ? t2 : nan;
+        if (!all_ok && status != nullptr) *status = 1;
+    }
+}
+
+}  // namespace
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" size_t pp_loss_exchange_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int pp_loss_exchange_create(void **mailbox, unsigned char *handle, int device) {
+    PP_REQUIRE(mailbox && handle, "loss_exchange_create: null argument");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    void *p = nullptr;
+    PP_CUDA(cudaMalloc(&p, sizeof(LxMailbox)));
+    PP_CUDA(cudaMemset(p, 0, sizeof(LxMailbox)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("loss_exchange_create: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    memcpy(handle, &h, sizeof(h));
+    *mailbox = p;
+    return PP_OK;
+}
+
+extern "C" int pp_loss_exchange_open(const unsigned char *handle, void **peer_mailbox, int device) {
+    PP_REQUIRE(handle && peer_mailbox, "loss_exchange_open: null argument");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    PP_CUDA(cudaIpcOpenMemHandle(peer_mailbox, h, cudaIpcMemLazyEnablePeerAccess));
+    return PP_OK;
+}
+
+extern "C" int pp_loss_exchange_bind(void *mailbox, void *const *peer_mailboxes, int world, int device) {
+    PP_REQUIRE(mailbox && peer_mailboxes, "loss_exchange_bind: null argument");
+    PP_REQUIRE(world >= 1 && world <= LX_MAX_WORLD, "loss_exchange_bind: world=%d outside [1,%d]", world, LX_MAX_WORLD);
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    LxMailbox *box = (LxMailbox *)mailbox;
+    PP_CUDA(cudaMemcpy(&box->peer[0], peer_mailboxes, sizeof(void *) * world, cudaMemcpyHostToDevice));
+    return PP_OK;
+}
+
+extern "C" int pp_loss_exchange_close(void *mailbox, void *const *peer_mailboxes, int rank, int world, int device) {
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    PP_CUDA(cudaDeviceSynchronize());
+    if (peer_mailboxes)
+        for (int p = 0; p < world; p++)
+            if (p != rank && peer_mailboxes[p]) cudaIpcCloseMemHandle(peer_mailboxes[p]);
+    if (mailbox) PP_CUDA(cudaFree(mailbox));
+    return PP_OK;
+}
+
+extern "C" int pp_loss_exchange_send(const float *sums, void *mailbox, int rank, int world, int device,
+                                     void *stream) {
+    PP_REQUIRE(sums && mailbox, "loss_exchange_send: null pointer");
+    PP_REQUIRE(world >= 1 && world <= LX_MAX_WORLD && rank >= 0 && rank < world, "loss_exchange_send: bad rank/world %d/%d", rank, world);
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    PP_CUDA(launch_pdl(lx_send_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, sums, (LxMailbox *)mailbox, rank, world));
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_loss_exchange_wait(void *mailbox, int world, float *sums_out, int32_t *status, int device,
+                                     void *stream) {
+    PP_REQUIRE(sums_out && mailbox, "loss_exchange_wait: null pointer");
+    PP_REQUIRE(world >= 1 && world <= LX_MAX_WORLD, "loss_exchange_wait: bad world %d", world);
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    PP_CUDA(launch_pdl(lx_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (LxMailbox *)mailbox, world, sums_out,
+                       (int *)status));
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}

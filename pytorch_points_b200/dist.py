@@ -90,3 +90,78 @@ def allreduce_chamfer_sums(sums, group=None):
     if _world(group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     return sums
+
+
+class LossExchange:
+    """All-reduce (SUM) of the 2-float Chamfer partial sums over NVLink peer memory
+    (csrc/loss_exchange.cu): every rank stores its sums straight into every peer's mailbox and
+    polls its own.  Two tiny graph-capturable kernels per step, no collective-library call.
+
+        lx = LossExchange(device)            # collective: every rank of `group` must call it
+        ... pp_chamfer_fwd(..., sums) ...
+        lx.send(sums)                        # right after the forward
+        ... backward kernels ...
+        lx.wait(total)                       # total (2 floats, device) = sum over ranks
+
+    Raises at construction when peer mapping is impossible (no CUDA IPC / no P2P); callers then
+    keep using `torch.distributed.all_reduce`."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        from . import _C
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("LossExchange needs an initialised torch.distributed process group")
+        self._C = _C
+        self.device = torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = _C.lib.pp_loss_exchange_handle_bytes()
+        handle = (ctypes.c_ubyte * nbytes)()
+        box = ctypes.c_void_p()
+        err = None
+        try:
+            _C.check(_C.lib.pp_loss_exchange_create(ctypes.byref(box), handle, self.device.index), "pp_loss_exchange_create")
+        except RuntimeError as e:  # still take part in the collectives below
+            err = repr(e)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (bytes(handle), err), group=group)
+        self.mailbox = box
+        self.peers = (ctypes.c_void_p * self.world)()
+        if not any(g[1] for g in gathered):
+            for p, (hb, _) in enumerate(gathered):
+                if p == self.rank:
+                    self.peers[p] = box.value
+                    continue
+                ptr = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * nbytes).from_buffer_copy(hb)
+                try:
+                    _C.check(_C.lib.pp_loss_exchange_open(buf, ctypes.byref(ptr), self.device.index), "pp_loss_exchange_open")
+                    self.peers[p] = ptr.value
+                except RuntimeError as e:
+                    err = repr(e)
+                    break
+        else:
+            err = err or "a peer could not create its mailbox"
+        # agree on the outcome so that either every rank uses the exchange or none does
+        flags = [None] * self.world
+        dist.all_gather_object(flags, err, group=group)
+        bad = [f for f in flags if f]
+        if bad:
+            raise RuntimeError("LossExchange unavailable: " + bad[0])
+        _C.check(_C.lib.pp_loss_exchange_bind(self.mailbox, self.peers, self.world, self.device.index), "pp_loss_exchange_bind")
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dist.barrier(group=group)  # every mailbox is bound before anyone sends
+
+    def send(self, sums):
+        C = self._C
+        C.check(C.lib.pp_loss_exchange_send(C.ptr(sums), self.mailbox, self.rank, self.world, self.device.index,
+                                            C.stream_of(self.device)), "pp_loss_exchange_send")
+
+    def wait(self, out):
+        C = self._C
+        C.check(C.lib.pp_loss_exchange_wait(self.mailbox, self.world, C.ptr(out), C.ptr(self.status), self.device.index,
+                                            C.stream_of(self.device)), "pp_loss_exchange_wait")
+        return out
+
+    def timed_out(self):
+        """True if any wait() so far gave up on a peer (synchronises)."""
+        return bool(self.status.item())

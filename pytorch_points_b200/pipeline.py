@@ -76,13 +76,15 @@ class GraphedChamferStep:
     i's loss while i+1 runs (each step still copies its inputs in and its loss out).
     """
 
-    def __init__(self, host_pairs, total_batch=None, device=None, group=None, world_size=1):
-        """With `world_size` > 1 every rank builds its own step over its shard of the batch.  The
-        8-byte NCCL all-reduce of the loss sums is NOT captured: the step is split into a forward
-        graph and a backward graph and the all-reduce is issued eagerly between the two replays
-        (asynchronously, so it overlaps the backward, whose weights are constants)."""
+    def __init__(self, host_pairs, total_batch=None, device=None, group=None, world_size=1, exchange=None):
+        """With `world_size` > 1 every rank builds its own step over its shard of the batch.  With an
+        `exchange` (dist.LossExchange) the global loss sums travel through peer memory and the whole
+        step -- forward, send, backward, wait, D2H -- is ONE graph.  Without it the 8-byte NCCL
+        all-reduce is NOT captured: the step is split into a forward graph and a backward graph
+        and the all-reduce is issued eagerly between the two replays (asynchronously, so it
+        overlaps the backward, whose weights are constants)."""
         from ._ext import losses
-        self.world_size, self.group = world_size, group
+        self.world_size, self.group, self.exchange = world_size, group, exchange
         dev = torch.device(device if device is not None else torch.cuda.current_device())
         if dev.type != "cuda":
             raise RuntimeError("GraphedChamferStep needs a CUDA device")
@@ -113,7 +115,8 @@ class GraphedChamferStep:
         self.sums_host = [torch.zeros(2).pin_memory() for _ in range(2)]  # per buffer set
         self.compute_stream = torch.cuda.Stream(dev)
         self.copy_stream = torch.cuda.Stream(dev)
-        self.launches = 4  # chamfer_fwd, chamfer_finalize, chamfer_bwd<0>, chamfer_bwd<1>
+        # chamfer_fwd, chamfer_finalize, chamfer_bwd<0>, chamfer_bwd<1> (+ lx_send, lx_wait)
+        self.launches = 4 + (2 if exchange is not None else 0)
 
         def copy_body(s):
             self.xyz1[s].copy_(self.host_pairs[s][0], non_blocking=True)
@@ -127,10 +130,16 @@ class GraphedChamferStep:
             losses.nmdistance_backward_uniform(self.xyz1[s], self.xyz2[s], self.grad1, self.grad2, self.gw,
                                                self.idx1, self.idx2)
 
+        self.total = torch.zeros(2, device=dev) if exchange is not None else self.sums
+
         def compute_body(s):
             fwd_body(s)
+            if exchange is not None:
+                exchange.send(self.sums)
             bwd_body(s)
-            self.sums_host[s].copy_(self.sums, non_blocking=True)
+            if exchange is not None:
+                exchange.wait(self.total)
+            self.sums_host[s].copy_(self.total, non_blocking=True)
 
         cur = torch.cuda.current_stream(dev)
         self.copy_stream.wait_stream(cur)
@@ -149,7 +158,7 @@ class GraphedChamferStep:
             with torch.cuda.graph(g, stream=self.copy_stream):
                 copy_body(s)
             self.copy_graph.append(g)
-            if world_size == 1:
+            if world_size == 1 or exchange is not None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self.compute_stream):
                     compute_body(s)
@@ -182,7 +191,7 @@ class GraphedChamferStep:
             self._primed = True
         with torch.cuda.stream(self.compute_stream):
             self.compute_stream.wait_event(self.copied[s])
-            if self.world_size == 1:
+            if self.world_size == 1 or self.exchange is not None:
                 self.compute_graph[s].replay()
             else:
                 import torch.distributed as dist
