@@ -239,6 +239,49 @@ def test_graphed_chamfer_step_pipelined(pp):
         assert abs(g - w) <= 1e-6 * abs(w), (got, want)
 
 
+def test_loss_exchange_single_rank(pp, tmp_path):
+    """dist.LossExchange (peer-memory exchange of the loss sums) on a 1-rank group: mailbox creation,
+    send/wait kernels, sequence numbering across eager launches and CUDA-graph replays, and the
+    graphed Chamfer step built on it.  (W > 1 is exercised by tools/lx_test.py on a multi-GPU box.)"""
+    import torch.distributed as dist
+    from pytorch_points_b200.dist import LossExchange
+    from pytorch_points_b200.pipeline import GraphedChamferStep
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("nccl", init_method="file://" + str(tmp_path / "pg"), rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        lx = LossExchange(torch.device("cuda", 0))
+        sums, total = torch.zeros(2, device="cuda"), torch.zeros(2, device="cuda")
+        for step in range(5):
+            sums.copy_(torch.tensor([1.5 + step, -2.0 * step], device="cuda"))
+            lx.send(sums)
+            lx.wait(total)
+            assert torch.equal(total, sums)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                lx.send(sums)
+                lx.wait(total)
+        for step in range(4):
+            sums.copy_(torch.tensor([9.0 * step, 0.125], device="cuda"))
+            torch.cuda.synchronize()
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(total, sums)
+        assert not lx.timed_out()
+        pairs = [(uniform_cloud(3, 500, 701).pin_memory(), uniform_cloud(3, 400, 702).pin_memory())]
+        step_obj = GraphedChamferStep(pairs, world_size=1, exchange=lx)
+        d1, d2, _, _ = pp.nndistance(dev(pairs[0][0]), dev(pairs[0][1]))
+        want = (d1.mean() + d2.mean()).item()
+        for _ in range(3):
+            assert abs(step_obj.run() - want) <= 1e-6 * abs(want)
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+
+
 def test_labeled_chamfer(pp, oracle_mod):
     a, b = uniform_cloud(2, 700, 27), uniform_cloud(2, 900, 28)
     g = torch.Generator().manual_seed(29)
