@@ -73,3 +73,53 @@ def furthest_point_sample(xyz, npoint, NCHW=True, seedIdx=0):
     if NCHW:
         sampled_pc = sampled_pc.transpose(2, 1).contiguous()
     return idx, sampled_pc
+
+
+# ---------------------------------------------------------------------------
+# k-NN based geometry helpers: the reference's versions call
+# pytorch3d.ops.knn_points (network/geo_operations.py:88-152); these run on this repo's KNN.
+# ---------------------------------------------------------------------------
+def _gather_neighbours(points, idx):
+    """points (B, N, C), idx (B, M, K) -> (B, M, K, C)."""
+    B, M, K = idx.shape
+    C = points.shape[-1]
+    flat = torch.gather(points, 1, idx.reshape(B, M * K, 1).long().expand(B, M * K, C))
+    return flat.view(B, M, K, C)
+
+
+def pointUniformLaplacian(points, knn_idx=None, nn_size=3):
+    """Uniform (umbrella) Laplacian of a point cloud: point minus the mean of its nn_size nearest
+    neighbours.  points (B, N, 3), knn_idx (B, N, K) optional -> (laplacian (B, N, 3), knn_idx)."""
+    from .operations import knn_points
+    if knn_idx is None:
+        _, knn_idx, group = knn_points(points, points, K=nn_size + 1, return_nn=True)
+        knn_idx, group = knn_idx[:, :, 1:], group[:, :, 1:, :]
+    else:
+        group = _gather_neighbours(points, knn_idx)
+    lap = points - torch.sum(group, dim=2) / knn_idx.shape[2]
+    return lap, knn_idx
+
+
+def batch_normals(points, base=None, nn_size=20, NCHW=True, idx=None):
+    """PCA normals: for every point the direction of least variance of its nn_size nearest
+    neighbours in `base` (default: the cloud itself).  points (B, C, M) if NCHW else (B, M, C)
+    -> (normals, same layout; idx (B, M, nn_size)).  Sign is arbitrary.  The reference uses its
+    cuSOLVER batch_svd extension (out of scope); torch.linalg.svd here."""
+    from .operations import knn_points
+    if base is None:
+        base = points
+    if NCHW:
+        points = points.transpose(2, 1).contiguous()
+        base = base.transpose(2, 1).contiguous()
+    assert nn_size < base.shape[1]
+    B, M, C = points.shape
+    if idx is None:
+        _, idx, group = knn_points(points, base, K=nn_size, return_nn=True)
+    else:
+        group = _gather_neighbours(base, idx)
+    centred = group - torch.mean(group, dim=2, keepdim=True)          # (B, M, k, C)
+    _, _, vh = torch.linalg.svd(centred.reshape(B * M, nn_size, C), full_matrices=False)
+    normals = vh[:, -1, :].reshape(B, M, C)                           # smallest singular direction
+    if NCHW:
+        normals = normals.transpose(1, 2)
+    return normals, idx

@@ -57,3 +57,49 @@ class SharedMLP(nn.Sequential):
         for i in range(len(args) - 1):
             self.add_module("layer{}".format(i),
                             Conv2d(args[i], args[i + 1], 1, normalization=normalization, activation=activation))
+
+
+class DenseEdgeConv(nn.Module):
+    """Densely connected edge convolution over a k-NN graph (reference network/layers.py:23-82),
+    with the neighbour search on `operations.knn_points` (this repo's KNN kernels) instead of
+    pytorch3d -- SURVEY.md next row N4."""
+
+    def __init__(self, in_channels, growth_rate, n, k, **kwargs):
+        super().__init__()
+        self.growth_rate, self.n, self.k = growth_rate, n, k
+        self.mlps = nn.ModuleList([nn.Conv2d(2 * in_channels, growth_rate, 1, bias=True)])
+        for _ in range(1, n):
+            in_channels += growth_rate
+            self.mlps.append(nn.Conv2d(in_channels, growth_rate, 1, bias=True))
+        self.out_channels = in_channels + growth_rate
+
+    def get_local_graph(self, x, k, idx=None):
+        """x (B, C, N) -> edge features [x_i, x_j - x_i] (B, 2C, N, k) over the k nearest
+        neighbours j of i (the point itself excluded), and their indices (B, N, k)."""
+        from .operations import knn_points
+        import torch
+        pts = x.transpose(1, 2).contiguous()  # (B, N, C)
+        if idx is None:
+            _, idx, nn_pts = knn_points(pts, pts, K=k + 1, return_nn=True)  # (B, N, k+1[, C])
+            idx, nn_pts = idx[:, :, 1:], nn_pts[:, :, 1:, :]
+        else:
+            B, N, C = pts.shape
+            nn_pts = torch.gather(pts.unsqueeze(1).expand(B, N, N, C), 2, idx.long().unsqueeze(-1).expand(B, N, idx.shape[2], C))
+        neighbours = nn_pts.permute(0, 3, 1, 2)              # (B, C, N, k)
+        centre = x.unsqueeze(-1).expand_as(neighbours)
+        return torch.cat([centre, neighbours - centre], dim=1), idx
+
+    def forward(self, x, idx=None):
+        """x (B, C, N) -> (features (B, C', N), knn idx (B, N, k))."""
+        import torch
+        for i, mlp in enumerate(self.mlps):
+            if i == 0:
+                y, idx = self.get_local_graph(x, k=self.k, idx=idx)
+                x = x.unsqueeze(-1).repeat(1, 1, 1, self.k)
+                y = torch.cat([nn.functional.relu_(mlp(y)), x], dim=1)
+            elif i == (self.n - 1):
+                y = torch.cat([mlp(y), y], dim=1)
+            else:
+                y = torch.cat([nn.functional.relu_(mlp(y)), y], dim=1)
+        y, _ = torch.max(y, dim=-1)
+        return y, idx

@@ -122,3 +122,133 @@ def chamfer_mean_loss(xyz1, xyz2):
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
     return s[0] / (B * n) + s[1] / (B * m)
+
+
+# ---------------------------------------------------------------------------
+# Point-cloud regularisers built on the k-NN graph (reference
+# network/model_loss.py:73-163,326-398, there on pytorch3d.ops.knn_points).
+# ---------------------------------------------------------------------------
+def _knn_graph(points, nn_size):
+    """Neighbour indices (B, N, nn_size) and neighbour coordinates, the point itself dropped."""
+    from .operations import knn_points
+    _, idx, group = knn_points(points, points, K=nn_size + 1, return_nn=True)
+    return idx[:, :, 1:], group[:, :, 1:, :]
+
+
+def _edge_lengths(points, idx, group=None):
+    from .geo_operations import _gather_neighbours
+    if group is None:
+        group = _gather_neighbours(points, idx)
+    return torch.norm(group - points.unsqueeze(2), dim=-1, p=2)
+
+
+class PointLaplacianLoss(torch.nn.Module):
+    """Compares the uniform Laplacians of two clouds in correspondence (same order, or idx12)."""
+
+    def __init__(self, nn_size, metric, use_norm=False):
+        super().__init__()
+        self.metric, self.nn_size, self.use_norm = metric, nn_size, use_norm
+
+    def forward(self, point1, point2, idx12=None, *args, **kwargs):
+        """point1 (B, N, D) reference (defines the graph), point2 (B, M, D), idx12 (B, N) optional."""
+        from .geo_operations import pointUniformLaplacian
+        lap1, knn_idx = pointUniformLaplacian(point1, nn_size=self.nn_size)
+        if idx12 is not None:
+            point2 = torch.gather(point2, 1, idx12.unsqueeze(-1).expand(-1, -1, point2.shape[-1]))
+            lap2, _ = pointUniformLaplacian(point2, nn_size=self.nn_size)
+        else:
+            assert point2.shape[1] == point1.shape[1]
+            lap2, _ = pointUniformLaplacian(point2, knn_idx=knn_idx)
+        if self.use_norm:
+            lap1, lap2 = torch.norm(lap1, dim=-1, p=2), torch.norm(lap2, dim=-1, p=2)
+        return self.metric(lap1, lap2)
+
+
+class PointEdgeLengthLoss(torch.nn.Module):
+    """Penalises changes of the k-NN edge lengths; the graph comes from the reference cloud."""
+
+    def __init__(self, nn_size, metric):
+        super().__init__()
+        self.metric, self.nn_size = metric, nn_size
+
+    def forward(self, points_ref, points):
+        idx, group_ref = _knn_graph(points_ref, self.nn_size)
+        return self.metric(_edge_lengths(points_ref, idx, group_ref), _edge_lengths(points, idx))
+
+
+class PointStretchLoss(torch.nn.Module):
+    """Penalises stretch only: max(d / d_ref - 1, 0) over the reference cloud's k-NN edges."""
+
+    def __init__(self, nn_size, reduction="mean"):
+        super().__init__()
+        self.nn_size, self.reduction = nn_size, reduction
+
+    def forward(self, points_ref, points):
+        idx, group_ref = _knn_graph(points_ref, self.nn_size)
+        d_ref, d = _edge_lengths(points_ref, idx, group_ref), _edge_lengths(points, idx)
+        stretch = torch.clamp(d / (d_ref + 1e-10) - 1, min=0)
+        if self.reduction == "mean":
+            return torch.mean(stretch)
+        if self.reduction == "sum":
+            return torch.mean(torch.sum(stretch, dim=-1))
+        if self.reduction == "none":
+            return stretch
+        if self.reduction == "max":
+            return torch.mean(torch.max(stretch, dim=-1)[0])
+        raise NotImplementedError
+
+
+class SimplePointRepulsionLoss(torch.nn.Module):
+    """Penalises neighbours closer than `radius`: 1/sqrt(d^2 + 1e-4) for d^2 < radius^2."""
+
+    def __init__(self, nn_size, radius, reduction="mean"):
+        super().__init__()
+        self.nn_size, self.reduction, self.radius2 = nn_size, reduction, radius * radius
+
+    def forward(self, points, knn_idx=None):
+        from .geo_operations import _gather_neighbours
+        if knn_idx is None:
+            knn_idx, group = _knn_graph(points, self.nn_size)
+            group = group.detach()  # as in the reference: neighbours are constants
+        else:
+            group = _gather_neighbours(points, knn_idx)
+        v = group - points.unsqueeze(2)
+        d2 = torch.sum(v * v, dim=-1)
+        loss = torch.where(d2 < self.radius2, 1 / torch.sqrt(d2 + 1e-4), torch.zeros_like(d2))
+        if self.reduction == "mean":
+            return loss.mean()
+        if self.reduction == "max":
+            return torch.mean(torch.max(loss, dim=-1)[0])
+        if self.reduction == "sum":  # the reference line (model_loss.py:393) cannot run; mean of per-point sums intended
+            return torch.sum(loss, dim=-1).mean()
+        if self.reduction == "none":
+            return loss
+        raise NotImplementedError
+
+
+class NormalLoss(torch.nn.Module):
+    """1 - cos between the PCA normals of two clouds in correspondence."""
+
+    def __init__(self, nn_size=10, reduction="mean"):
+        super().__init__()
+        self.nn_size, self.reduction = nn_size, reduction
+        self.cos = torch.nn.CosineSimilarity(dim=-1, eps=1e-08)
+
+    def forward(self, gt, pred, idx12=None):
+        from .geo_operations import batch_normals
+        gt_normals, idx = batch_normals(gt, nn_size=self.nn_size, NCHW=False)
+        if idx12 is not None:
+            pred = torch.gather(pred, 1, idx12.unsqueeze(-1).expand(-1, -1, pred.shape[-1]))
+            pred_normals, _ = batch_normals(pred, nn_size=self.nn_size, NCHW=False)
+        else:
+            pred_normals, _ = batch_normals(pred, nn_size=self.nn_size, NCHW=False, idx=idx)
+        loss = 1 - self.cos(pred_normals, gt_normals)
+        if self.reduction == "mean":  # the reference line (model_loss.py:352) cannot run; plain mean intended
+            return loss.mean()
+        if self.reduction == "max":
+            return (torch.max(loss, dim=-1)[0]).mean()
+        if self.reduction == "sum":
+            return torch.sum(loss, dim=-1).mean()
+        if self.reduction == "none":
+            return loss
+        raise NotImplementedError

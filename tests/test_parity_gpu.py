@@ -765,6 +765,59 @@ def test_pointnet_sa_group_all_and_fp_module(pp, oracle_mod):
     assert known_feats.grad is not None and torch.isfinite(known_feats.grad).all()
 
 
+# --------------------------------------------------------------------------- KNN callers (N4)
+def _brute_knn(points, k):
+    d = torch.cdist(points.double(), points.double())
+    return d.topk(k + 1, dim=-1, largest=False).indices[:, :, 1:]
+
+
+def test_knn_callers_laplacian_edgeconv_and_losses(pp):
+    """the snapshot's pytorch3d.knn_points callers on this repo's KNN --
+    DenseEdgeConv.get_local_graph (layers.py:41-62), pointUniformLaplacian / batch_normals
+    (geo_operations.py:88-152) and the point regularisers (model_loss.py:73-163,326-398) --
+    against brute-force torch restatements."""
+    torch.manual_seed(3)
+    B, N, k = 2, 3000, 8
+    pts = dev(uniform_cloud(B, N, 801))
+    want_idx = _brute_knn(pts, k)
+    # Laplacian
+    lap, idx = pp.pointUniformLaplacian(pts, nn_size=k)
+    assert torch.equal(idx, want_idx)
+    nb = torch.gather(pts.unsqueeze(1).expand(B, N, N, 3), 2, want_idx.unsqueeze(-1).expand(B, N, k, 3))
+    assert torch.allclose(lap, pts - nb.mean(2), rtol=1e-5, atol=1e-6)
+    lap2, _ = pp.pointUniformLaplacian(pts, knn_idx=idx)
+    assert torch.allclose(lap, lap2, rtol=1e-6, atol=1e-7)
+    # edge convolution graph + module forward/backward
+    x = pts.transpose(1, 2).contiguous().requires_grad_(True)
+    conv = pp.DenseEdgeConv(3, 12, n=3, k=k).cuda()
+    edge, eidx = conv.get_local_graph(x, k)
+    assert edge.shape == (B, 6, N, k) and torch.equal(eidx, want_idx)
+    assert torch.allclose(edge[:, 3:], nb.permute(0, 3, 1, 2) - x.unsqueeze(-1), rtol=1e-5, atol=1e-6)
+    y, _ = conv(x)
+    assert y.shape == (B, conv.out_channels, N)
+    y.square().mean().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all() and x.grad.abs().sum() > 0
+    # regularisers
+    l1 = torch.nn.L1Loss()
+    assert pp.PointEdgeLengthLoss(k, l1)(pts, pts).item() == 0.0
+    assert abs(pp.PointStretchLoss(k)(pts, 2 * pts).item() - 1.0) < 1e-5
+    assert pp.PointStretchLoss(k)(pts, 0.5 * pts).item() == 0.0
+    assert pp.PointLaplacianLoss(k, l1)(pts, pts).item() == 0.0
+    d2 = ((nb - pts.unsqueeze(2)) ** 2).sum(-1)
+    rep = torch.where(d2 < 0.03 ** 2, 1 / torch.sqrt(d2 + 1e-4), torch.zeros_like(d2)).mean()
+    assert abs(pp.SimplePointRepulsionLoss(k, 0.03)(pts).item() - rep.item()) <= 1e-5 * max(rep.item(), 1e-6)
+    moved = pts.clone().requires_grad_(True)
+    pp.SimplePointRepulsionLoss(k, 0.05)(moved).backward()
+    assert torch.isfinite(moved.grad).all()
+    # PCA normals: a noisy plane z ~ 0 has normals +-z; identical clouds give zero normal loss
+    plane = pts.clone()
+    plane[..., 2] *= 1e-3
+    normals, nidx = pp.batch_normals(plane, nn_size=12, NCHW=False)
+    assert normals.shape == (B, N, 3) and nidx.shape == (B, N, 12)
+    assert (normals[..., 2].abs() > 0.99).float().mean().item() > 0.99
+    assert pp.NormalLoss(nn_size=12, reduction="none")(plane, plane).abs().max().item() < 1e-4
+
+
 # --------------------------------------------------------------------------- full-size properties
 def test_chamfer_target_shape_properties(pp, oracle_mod):
     """B=32, N=M=8192 (north-star target) is too big for the CPU oracle inside a unit test:
