@@ -14,12 +14,12 @@ for (B,N,it) in [(32,8192,5),(4,131072,3),(2,4096,5)]:
     for maker in (uniform_cloud, sphere_cloud):
         p = maker(B,N,4).cuda()
         ref = None
-        for prune, q1 in ((0, 0), (1, 1)):
-            _C.set_option("knn_prune", prune); _C.set_option("knn_q1", q1)
+        for prune in (0, 1):
+            _C.set_option("knn_prune", prune)
             ms = t(lambda: sampling.knn(16,p,p), it)
             _C.set_option("timing", 1); sampling.knn(16,p,p); torch.cuda.synchronize(); kms, _ = _C.timing_collect("knn"); _C.set_option("timing", 0)
             _C.set_option("knn_stats", 1); out = sampling.knn(16,p,p); v, tot = _C.knn_stats(); _C.set_option("knn_stats", 0)
             if ref is None: ref = out
             else: assert torch.equal(ref[0], out[0]) and torch.equal(ref[1], out[1]), "pruned result differs"
-            print("knn k16 B%d N%d %s prune=%d q1=%d: %.3f ms (sweep kernel %.3f)  %.3g pairs/s  tiles visited %.0f/%.0f = %.1f%%" % (B,N,maker.__name__,prune,q1,ms,kms,B*N*N/ms*1e3,v,tot,100*v/max(tot,1)), flush=True)
-_C.set_option("knn_prune", 1); _C.set_option("knn_q1", 0)
+            print("knn k16 B%d N%d %s prune=%d: %.3f ms (sweep kernel %.3f)  %.3g pairs/s  tiles visited %.0f/%.0f = %.1f%%" % (B,N,maker.__name__,prune,ms,kms,B*N*N/ms*1e3,v,tot,100*v/max(tot,1)), flush=True)
+_C.set_option("knn_prune", 1)
