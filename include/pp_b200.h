@@ -219,7 +219,7 @@ int pp_three_interpolate_bwd(const float *grad_out, const int32_t *idx, const fl
  *            peer's mailbox;
  *   wait   : enqueue where the total is needed (after the backward, so the link latency is
  *            hidden) -- polls the own mailbox for this step's contributions and writes their
- *            sum, added in rank order, to sums_out (2 floats, device).  Bounded: after ~1 s
+ *            sum, added in rank order, to sums_out (2 floats, device).  Bounded: after ~10 s
  *            without a peer the result is NaN and *status (device int, may be NULL) is set to 1.
  * Every rank must issue the same sequence of send/wait pairs.  Both launches are graph-capturable.
  */

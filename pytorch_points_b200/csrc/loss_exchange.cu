@@ -13,8 +13,8 @@
 // send is enqueued right after the finalize kernel, wait after the backward kernels, so the
 // NVLink latency hides behind the backward.  Both are ordinary kernels: they capture into CUDA
 // graphs (the sequence number lives in device memory) and use no host synchronisation.
-// The poll is bounded (about one second): a missing peer yields NaN sums and a status flag, never
-// a hung GPU.
+// The poll is bounded (about ten seconds, far beyond any start-up skew between ranks): a missing
+// peer yields NaN sums and a status flag, never a hung GPU.
 #include "pp_common.cuh"
 
 namespace pp {
@@ -73,7 +73,7 @@ lx_wait_kernel(LxMailbox *box, int world, float *__restrict__ out, int *__restri
             a = ld_sys_u64(&src->w0);
             b = ld_sys_u64(&src->w1);
             if ((unsigned)a == seq && (unsigned)b == seq) break;
-            if (clock64() - t0 > 2000000000ll) {  // ~1 s at 1.9 GHz: give up, never hang the GPU
+            if (clock64() - t0 > 20000000000ll) {  // ~10 s at 1.9 GHz: give up, never hang the GPU
                 ok = false;
                 break;
             }

@@ -148,6 +148,9 @@ class GraphedChamferStep:
             copy_body(0)
             copy_body(1)
         self.copy_stream.synchronize()
+        if exchange is not None:
+            import torch.distributed as dist
+            dist.barrier(group=group)  # ranks enter the first exchange together (its poll is bounded)
         with torch.cuda.stream(self.compute_stream):
             for _ in range(2):  # warm-up on the capture stream (also creates its key workspace)
                 compute_body(0)
