@@ -5,7 +5,7 @@
 // (Z-order) curve.  A warp's 32 queries are then spatial neighbours and every 64 consecutive
 // points form a compact tile with a small bounding box, so a tile whose box is farther from the
 // warp's query box than the largest current k-th distance cannot contribute and is never
-// loaded.  On uniform clouds 2 % (N = 131072) to 25 % (N = 8192) of the tiles survive.
+// loaded.  On uniform clouds 1.6 % (N = 131072) to 18 % (N = 8192) of the tiles survive.
 // The result is bit-identical to the unordered brute-force sweep: distances are evaluated in the
 // same rounding order, selection and final order use the total order (distance, ORIGINAL
 // index), a tile is only skipped when that is provably safe in floating point, and the
@@ -598,7 +598,16 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
                 const int bit = __ffs(todo) - 1;
                 todo &= todo - 1u;
                 const int t = tile_of(s0 + bit);
-                if (prune && pass == 1 && km_can_skip(__shfl_sync(FULL_MASK, gap, bit), warp_taumax())) continue;
+                if (prune) {
+                    // Second, sharper test with the thresholds as they are NOW: every lane measures
+                    // the gap between ITS query and the tile's box against ITS k-th distance; the
+                    // tile is loaded only if some lane cannot rule it out.  (The lane-parallel test
+                    // above used the warp's whole query box and its largest threshold.)
+                    const float4 b0 = __ldg(boxes + t * 2), b1 = __ldg(boxes + t * 2 + 1);
+                    const float plo[3] = {qx, qy, qz};
+                    const bool need = active && !km_can_skip(km_box_gap2(plo, plo, b0, b1), tau);
+                    if (!__any_sync(FULL_MASK, need)) continue;
+                }
                 n_visited++;
                 __syncwarp();
                 load_tile(t, true);
