@@ -452,8 +452,8 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
                 unsorted &= unsorted - 1u;
             }
             const int src = half == 0 ? a : (bsrc < 0 ? a : bsrc);
-            const bool mine = sl < k && (half == 0 || bsrc >= 0);
-            unsigned long long my = sl < k ? sL[src][sl] : ~0ull;  // ~0 sorts behind every real key
+            const bool mine = sl < k && (half == 0 || bsrc >= 0);  // an idle half touches no list
+            unsigned long long my = mine ? sL[src][sl] : ~0ull;    // ~0 sorts behind every real key
 #pragma unroll
             for (int size = 2; size <= W; size <<= 1) {
 #pragma unroll
@@ -482,8 +482,8 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
             const int src = half == 0 ? a : (bsrc < 0 ? a : bsrc);
             const int n = half == 0 ? na : (bsrc < 0 ? 0 : nb);
             const int steps = max(na, bsrc < 0 ? 0 : nb);
-            const bool slot = sl < k;
-            unsigned long long my = slot ? sL[src][sl] : 0ull;  // 0 never compares greater: inert lanes
+            const bool slot = sl < k && (half == 0 || bsrc >= 0);  // an idle half touches no list
+            unsigned long long my = slot ? sL[src][sl] : 0ull;     // 0 never compares greater: inert lanes
             for (int e = 0; e < steps; e++) {
                 unsigned long long key = ~0ull;  // nothing to insert: greater than every entry
                 if (e < n)
