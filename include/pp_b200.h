@@ -246,7 +246,8 @@ int pp_microbench(int which, int iters, float *ms, double *work, int device);
  * With pp_set_option("timing", 1) every launch of a dominant kernel is bracketed by CUDA
  * events on the launching stream.  pp_timing_collect(name) waits for the recorded events and
  * returns their summed duration and count, then forgets them.  Names: "chamfer_fwd",
- * "chamfer_finalize", "chamfer_bwd", "fps", "ball_query", "knn", "gather_fwd".
+ * "chamfer_finalize", "chamfer_bwd", "fps", "ball_query", "query_group", "query_group_bwd", "knn" (the
+ * sweep kernel), "gather_fwd".
  */
 int pp_timing_collect(const char *name, double *total_ms, int *count);
 
@@ -257,7 +258,23 @@ int pp_timing_collect(const char *name, double *total_ms, int *count);
  */
 int pp_knn_stats(double *tiles_visited, double *tiles_total);
 
-/* Tuning knob for experiments: selects a kernel variant (0 = default). */
+/*
+ * Process-wide integer options (diagnostics and A/B switches; results never depend on them):
+ *   "timing" (0)                 per-kernel CUDA events, see pp_timing_collect
+ *   "pdl" (1)                    programmatic dependent launch of the short follow-up kernels
+ *   "chamfer_variant" (0)        0 = automatic; 1 / 2 = 256- / 128-point reference blocks;
+ *                                13 / 14 = the same without the per-warp sweep rotation
+ *   "chamfer_blocks_per_sm" (24) target CTA count per SM for the query split heuristic
+ *   "chamfer_generic" (0)        force the generic (any point dimension) kernel
+ *   "fps_cluster" (0)            0 = automatic, else the cluster width 1 / 2 / 4 / 8
+ *   "fps_stream" (0)             force the streaming fallback kernel
+ *   "knn_morton" (-1)            -1 = automatic, 0 / 1 = never / always use the ordered sweep
+ *   "knn_prune" (1), "knn_estimate" (1), "knn_fused_prep" (1)
+ *                                pieces of the ordered sweep: box pruning, threshold seed,
+ *                                one-launch preparation
+ *   "knn_smem_lists" (0), "knn_generic" (0)   force the k <= 64 / any-dimension kernels
+ *   "knn_stats" (0)              see pp_knn_stats
+ */
 int pp_set_option(const char *name, int value);
 
 #ifdef __cplusplus

@@ -21,6 +21,6 @@ def timeit(fn, iters=60):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     ts.sort(); return ts[len(ts) // 2]
 for v in (2, 1):
-    for bps in (8, 12, 16, 20, 24, 28, 32, 48):
+    for bps in ([int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else (8, 12, 16, 20, 24, 28, 32, 48)):
         _C.set_option("chamfer_variant", v); _C.set_option("chamfer_blocks_per_sm", bps)
         print("variant %d blocks_per_sm %d: step %.4f ms" % (v, bps, timeit(step)), flush=True)
