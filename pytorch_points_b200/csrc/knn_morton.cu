@@ -360,8 +360,7 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
     __shared__ __align__(16) float sY[KM_TILE];
     __shared__ __align__(16) float sZ[KM_TILE];
     __shared__ int sI[KM_TILE];
-    __shared__ float sBD[KM_CB][32];
-    __shared__ int sBI[KM_CB][32];
+    __shared__ unsigned long long sBK[KM_CB][32];  // per-lane candidate keys
     __shared__ unsigned long long sL[32][LP];
 
     const int b = blockIdx.y;
@@ -484,20 +483,18 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
             const int steps = max(na, bsrc < 0 ? 0 : nb);
             const bool slot = sl < k && (half == 0 || bsrc >= 0);  // an idle half touches no list
             unsigned long long my = slot ? sL[src][sl] : 0ull;     // 0 never compares greater: inert lanes
+            const unsigned long long *cand = &sBK[0][src];
             for (int e = 0; e < steps; e++) {
-                unsigned long long key = ~0ull;  // nothing to insert: greater than every entry
-                if (e < n)
-                    key = ((unsigned long long)__float_as_uint(sBD[e][src]) << 32) | (unsigned)sBI[e][src];
-                const unsigned m = __ballot_sync(FULL_MASK, key < my);
-                if (m == 0u) continue;  // warp-uniform: both candidates already beaten
-                const unsigned mh = W == 16 ? ((m >> (16 * half)) & 0xffffu) : m;
+                // nothing (left) to insert for this half: a key greater than every entry
+                const unsigned long long key = e < n ? cand[e * 32] : ~0ull;
+                const bool lt = key < my;  // true exactly for the slots from the insertion point on
+                if (!__any_sync(FULL_MASK, lt)) continue;  // warp-uniform: both candidates already beaten
                 const unsigned plo = __shfl_up_sync(FULL_MASK, (unsigned)my, 1, W);
                 const unsigned phi = __shfl_up_sync(FULL_MASK, (unsigned)(my >> 32), 1, W);
-                if (mh != 0u && slot) {
-                    const int pos = __ffs(mh) - 1;  // first slot that is larger: the candidate goes here
-                    if (sl == pos) my = key;
-                    else if (sl > pos) my = ((unsigned long long)phi << 32) | plo;
-                }
+                // every slot behind the insertion point takes its predecessor, the insertion point
+                // itself (predecessor <= key, or no predecessor) takes the candidate: max(key, prev)
+                const unsigned long long prev = sl == 0 ? 0ull : (((unsigned long long)phi << 32) | plo);
+                if (lt) my = key > prev ? key : prev;
             }
             if (slot && n > 0) sL[src][sl] = my;
         }
@@ -638,8 +635,8 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
                                                          (unsigned)sI[jj + 4 * h + r];
                                         fill++;
                                     } else {
-                                        sBD[cnt][lane] = dd[4 * h + r];
-                                        sBI[cnt][lane] = sI[jj + 4 * h + r];
+                                        sBK[cnt][lane] = ((unsigned long long)__float_as_uint(dd[4 * h + r]) << 32) |
+                                                         (unsigned)sI[jj + 4 * h + r];
                                         cnt++;
                                     }
                                 }
