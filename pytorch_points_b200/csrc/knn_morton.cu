@@ -423,6 +423,8 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
         }
     }
     for (int e = lane; e < 32 * LP; e += 32) (&sL[0][0])[e] = KM_EMPTY;
+#pragma unroll
+    for (int e = 0; e < KM_CB; e++) sBK[e][lane] = ~0ull;
     __syncwarp();
 
     float tau = PP_INF, tau0 = PP_INF;  // accept d <= tau; tau0 = seed (upper bound of the k-th distance)
@@ -485,8 +487,8 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
             unsigned long long my = slot ? sL[src][sl] : 0ull;     // 0 never compares greater: inert lanes
             const unsigned long long *cand = &sBK[0][src];
             for (int e = 0; e < steps; e++) {
-                // nothing (left) to insert for this half: a key greater than every entry
-                const unsigned long long key = e < n ? cand[e * 32] : ~0ull;
+                // slots past a lane's count hold ~0 (greater than every entry: nothing to insert)
+                const unsigned long long key = cand[e * 32];
                 const bool lt = key < my;  // true exactly for the slots from the insertion point on
                 if (!__any_sync(FULL_MASK, lt)) continue;  // warp-uniform: both candidates already beaten
                 const unsigned plo = __shfl_up_sync(FULL_MASK, (unsigned)my, 1, W);
@@ -499,6 +501,7 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
             if (slot && n > 0) sL[src][sl] = my;
         }
         __syncwarp();
+        for (int e = 0; e < cnt; e++) sBK[e][lane] = ~0ull;  // consumed: back to "nothing here"
         cnt = 0;
         if (sorted) tau = fminf(tau0, __uint_as_float((unsigned)(sL[lane][k - 1] >> 32)));
     };
@@ -565,8 +568,8 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
     };
     // outward along the curve: t0, t0+1, t0-1, t0+2, ... (wrapping)
     auto tile_of = [&](int s) -> int {
-        int t = (s & 1) ? t0 + (s + 1) / 2 : t0 - s / 2;
-        t %= ntiles;
+        int t = (s & 1) ? t0 + (s + 1) / 2 : t0 - s / 2;  // in (-ntiles, 2 * ntiles): no division needed
+        if (t >= ntiles) t -= ntiles;
         return t < 0 ? t + ntiles : t;
     };
 
