@@ -356,9 +356,9 @@ knn_sweep_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
                  float *__restrict__ dist, int *__restrict__ idx, unsigned long long *__restrict__ visited) {
     constexpr int W = K <= 16 ? 16 : 32;  // lanes per list
     constexpr int LP = K + 1;             // padded row length (keys)
-    __shared__ __align__(16) float sX[KM_TILE];
-    __shared__ __align__(16) float sY[KM_TILE];
-    __shared__ __align__(16) float sZ[KM_TILE];
+    // one array for the tile (x | y | z planes): the hot loop addresses all three from one base
+    __shared__ __align__(16) float sP[3 * KM_TILE];
+    float *const sX = sP, *const sY = sP + KM_TILE, *const sZ = sP + 2 * KM_TILE;
     __shared__ int sI[KM_TILE];
     __shared__ unsigned long long sBK[KM_CB][32];  // per-lane candidate keys
     __shared__ unsigned long long sL[32][LP];
