@@ -475,13 +475,22 @@ def test_knn_bit_exact(pp, oracle_mod, B, M, N, k, maker):
 
 
 @pytest.mark.parametrize("maker,M,N,k", [(uniform_cloud, 700, 5000, 16), (lattice_cloud, 600, 4500, 16),
-                                          (sphere_cloud, 300, 6000, 32), (uniform_cloud, 513, 4097, 5)])
+                                          (sphere_cloud, 300, 6000, 32), (uniform_cloud, 513, 4097, 5),
+                                          (lattice_cloud, 333, 2111, 12),   # k < list width 16, exact ties
+                                          (lattice_cloud, 100, 2500, 20),   # full-warp lists (17..32), k < 32
+                                          (uniform_cloud, 10, 3000, 1),     # one partial query warp, k = 1
+                                          (None, 400, 2600, 16),            # duplicated points: zero distances, index order
+                                          (uniform_cloud, 257, 16500, 8)])  # above the one-launch preparation limit
 def test_knn_morton_sweep_matches_oracle(pp, oracle_mod, maker, M, N, k):
     """Spatially ordered sweep (forced on): same (distance, original index) order, bit for bit,
     including exact ties (lattice) and query != points."""
     from pytorch_points_b200 import _C
-    p = maker(2, N, 70)
-    q = maker(2, M, 71)
+    if maker is None:
+        p = with_duplicates(uniform_cloud(2, N, 70), 0.3)
+        q = p[:, :M].clone()
+    else:
+        p = maker(2, N, 70)
+        q = maker(2, M, 71)
     ed, ei = oracle_mod.knn(k, np32(q), np32(p))
     _C.set_option("knn_morton", 1)
     try:
@@ -490,8 +499,9 @@ def test_knn_morton_sweep_matches_oracle(pp, oracle_mod, maker, M, N, k):
     finally:
         _C.set_option("knn_morton", -1)
     assert np.array_equal(np32(idx), ei) and np.array_equal(np32(dist), ed)
-    ed2, ei2 = oracle_mod.knn(k, np32(p[:1, :800]), np32(p[:1]))
-    assert np.array_equal(np32(idx_s[:1, :800]), ei2) and np.array_equal(np32(dist_s[:1, :800]), ed2)
+    ns = min(800, N)
+    ed2, ei2 = oracle_mod.knn(k, np32(p[:1, :ns]), np32(p[:1]))
+    assert np.array_equal(np32(idx_s[:1, :ns]), ei2) and np.array_equal(np32(dist_s[:1, :ns]), ed2)
 
 
 def test_knn_shared_list_kernel_matches(pp, oracle_mod):
