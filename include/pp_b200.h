@@ -65,10 +65,17 @@ int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M, in
  * (_ext/nmdistance.cpp:17-20,32 -> _ext/nmdistance_cuda.cu:56-115,142-166).
  *   label1 (B,N) label2 (B,M) fp32 (the reference casts labels to the point dtype,
  *   network/model_loss.py:452-453); unmatched points get idx -1, dist 0.
+ *   workspace / workspace_bytes / flags: as for pp_chamfer_fwd (same size, same 0xff protocol;
+ *   the two entry points may share one buffer).  With a workspace and c == 3 the one-pass
+ *   kernel runs with a label mask; it returns the reference's results whenever every
+ *   same-label distance is below the reference's own 1e10 sentinel (nmdistance_cuda.cu:70).
+ *   workspace == NULL (or c != 3) selects the literal chunk-by-chunk restatement of the
+ *   reference kernel, quirks included.
  */
 int pp_chamfer_labeled_fwd(const float *xyz1, const float *xyz2, const float *label1,
                            const float *label2, int B, int N, int M, int c, float *dist1,
-                           float *dist2, int32_t *idx1, int32_t *idx2, int device, void *stream);
+                           float *dist2, int32_t *idx1, int32_t *idx2, void *workspace,
+                           size_t workspace_bytes, int flags, int device, void *stream);
 
 /*
  * Chamfer backward.  Replaces losses.nmdistance_backward

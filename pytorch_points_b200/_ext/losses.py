@@ -67,9 +67,13 @@ def labeled_nmdistance_forward(xyz1, xyz2, label1, label2, dist1, dist2, idx1, i
     M = xyz2.shape[1]
     if label1.numel() != B * N or label2.numel() != B * M:
         raise RuntimeError("labeled_nmdistance_forward: labels must be (B,N[,1]) and (B,M[,1])")
+    nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
+    key, ws = _workspace(dev, nbytes)
     rc = _C.lib.pp_chamfer_labeled_fwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(label1), _C.ptr(label2), B, N, M, c,
                                        _C.ptr(dist1), _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2),
-                                       dev.index, _C.stream_of(dev))
+                                       _C.ptr(ws), ws.numel(), _C.PP_CHAMFER_WS_CLEAN, dev.index, _C.stream_of(dev))
+    if rc != 0:
+        _workspaces.pop(key, None)
     _C.check(rc, "pp_chamfer_labeled_fwd")
     return 1
 

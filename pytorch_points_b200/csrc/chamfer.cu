@@ -56,15 +56,21 @@ __device__ __forceinline__ void publish_column_min(int lane, int leader, unsigne
         : "memory");
 }
 
-template <int Q, int THREADS, int RB, int MINB, bool ROTATE>
+// LABELED (LabeledNmdistanceFunction, _ext/nmdistance_cuda.cu:56-115): only pairs with equal fp32
+// labels are candidates -- every other distance is replaced by +inf right after it is computed,
+// so both minima see same-label partners only; a point without a partner keeps +inf and the
+// finalize kernel turns that into the reference's (dist 0, idx -1).
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE, bool LABELED>
 __global__ void __launch_bounds__(THREADS, MINB)
 chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int N, int M,
                    unsigned long long *__restrict__ key1, unsigned long long *__restrict__ key2,
-                   int queries_per_split) {
+                   int queries_per_split, const float *__restrict__ label1,
+                   const float *__restrict__ label2) {
     __shared__ __align__(16) float sX[RB];
     __shared__ __align__(16) float sY[RB];
     __shared__ __align__(16) float sZ[RB];
     __shared__ __align__(16) unsigned sW[RB];  // filter: best column value seen (bits)
+    __shared__ __align__(16) float sLab[LABELED ? RB : 4];
 
     pdl_launch_dependents();  // the finalize kernel may take the SM slots this grid's tail frees
     constexpr int TQ = Q * THREADS;
@@ -94,6 +100,8 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
         sY[t] = y;
         sZ[t] = z;
         sW[t] = w;
+        // padding carries a NaN label: equal to nothing
+        if (LABELED) sLab[t] = j < M ? __ldg(label2 + (size_t)b * M + j) : __int_as_float(0x7fc00000);
     }
     __syncthreads();
 
@@ -106,15 +114,18 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
         const int group = q0 / Q;
 
         float nqx[Q], nqy[Q], nqz[Q], best[Q], prev[Q];
+        float ql[LABELED ? Q : 1];
         int granule[Q];
 #pragma unroll
         for (int q = 0; q < Q; q++) {
             const int i = q0 + q;
             float x = PP_INF, y = PP_INF, z = PP_INF;
+            if (LABELED) ql[q] = __int_as_float(0x7fc00000);
             if (i < q_end) {
                 x = __ldg(p1 + (size_t)i * 3 + 0);
                 y = __ldg(p1 + (size_t)i * 3 + 1);
                 z = __ldg(p1 + (size_t)i * 3 + 2);
+                if (LABELED) ql[q] = __ldg(label1 + (size_t)b * N + i);
             }
             nqx[q] = -x;  // negated: rn(r + (-q)) == rn(r - q)
             nqy[q] = -y;
@@ -131,7 +142,10 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
         // to index 0 the row minima found so far are published and tracking restarts -- the
         // packed (value, granule) RED.MIN resolves ties towards the lower granule.
         constexpr int WARPS = THREADS / 32;
-        const int rot = ROTATE ? __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5) * (RB / WARPS), 0) : 0;
+        // (offsets are whole granules: the row side attributes an improvement to the granule
+        //  whose last step it is checked at, so a sweep must start on a granule boundary)
+        static_assert(RB % CH_GR == 0, "reference blocks are whole granules");
+        const int rot = ROTATE ? __shfl_sync(FULL_MASK, ((int)(threadIdx.x >> 5) * (RB / WARPS)) & ~(CH_GR - 1), 0) : 0;
 #pragma unroll 1
         for (int step = 0; step < RB; step += 4) {
             int jj = step + rot;
@@ -157,12 +171,24 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
             const float2 y01 = make_float2(Y.x, Y.y), y23 = make_float2(Y.z, Y.w);
             const float2 z01 = make_float2(Z.x, Z.y), z23 = make_float2(Z.z, Z.w);
             float c0 = PP_INF, c1 = PP_INF, c2 = PP_INF, c3 = PP_INF;
+            float4 LB = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (LABELED) LB = *reinterpret_cast<const float4 *>(sLab + jj);
 #pragma unroll
             for (int q = 0; q < Q; q += 2) {
-                const float2 a01 = sqdist2_xyz(x01, y01, z01, nqx[q], nqy[q], nqz[q]);
-                const float2 a23 = sqdist2_xyz(x23, y23, z23, nqx[q], nqy[q], nqz[q]);
-                const float2 b01 = sqdist2_xyz(x01, y01, z01, nqx[q + 1], nqy[q + 1], nqz[q + 1]);
-                const float2 b23 = sqdist2_xyz(x23, y23, z23, nqx[q + 1], nqy[q + 1], nqz[q + 1]);
+                float2 a01 = sqdist2_xyz(x01, y01, z01, nqx[q], nqy[q], nqz[q]);
+                float2 a23 = sqdist2_xyz(x23, y23, z23, nqx[q], nqy[q], nqz[q]);
+                float2 b01 = sqdist2_xyz(x01, y01, z01, nqx[q + 1], nqy[q + 1], nqz[q + 1]);
+                float2 b23 = sqdist2_xyz(x23, y23, z23, nqx[q + 1], nqy[q + 1], nqz[q + 1]);
+                if (LABELED) {
+                    a01.x = LB.x == ql[q] ? a01.x : PP_INF;
+                    a01.y = LB.y == ql[q] ? a01.y : PP_INF;
+                    a23.x = LB.z == ql[q] ? a23.x : PP_INF;
+                    a23.y = LB.w == ql[q] ? a23.y : PP_INF;
+                    b01.x = LB.x == ql[q + 1] ? b01.x : PP_INF;
+                    b01.y = LB.y == ql[q + 1] ? b01.y : PP_INF;
+                    b23.x = LB.z == ql[q + 1] ? b23.x : PP_INF;
+                    b23.y = LB.w == ql[q + 1] ? b23.y : PP_INF;
+                }
                 best[q] = fmin3(fmin3(best[q], a01.x, a01.y), a23.x, a23.y);
                 best[q + 1] = fmin3(fmin3(best[q + 1], b01.x, b01.y), b23.x, b23.y);
                 c0 = fmin3(c0, a01.x, b01.x);
@@ -224,13 +250,15 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
 //   rows   : a warp takes 32 queries; for each, its 32 lanes test the 32 references of the
 //            recorded granule at once (coalesced 384-byte read, ballot, find-first-set);
 //   columns: a thread re-evaluates the Q queries of the recorded group, fully unrolled.
-template <int Q>
+template <int Q, bool LABELED>
 __global__ void __launch_bounds__(256)
 chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int B, int N,
                         int M, unsigned long long *__restrict__ key1,
                         unsigned long long *__restrict__ key2, float *__restrict__ dist1,
                         float *__restrict__ dist2, int *__restrict__ idx1, int *__restrict__ idx2,
-                        float *__restrict__ sums, int row_blocks) {
+                        float *__restrict__ sums, int row_blocks, const float *__restrict__ label1,
+                        const float *__restrict__ label2) {
+    constexpr unsigned INF_BITS = 0x7f800000u;  // LABELED: no same-label partner -> (dist 0, idx -1)
     const int lane = threadIdx.x & 31;
     float s1 = 0.f, s2 = 0.f;
     pdl_wait();                // keys are complete and visible
@@ -242,7 +270,7 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
         const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
         unsigned want = 0u;
         int g = 0, b = 0;
-        float qx = 0.f, qy = 0.f, qz = 0.f;
+        float qx = 0.f, qy = 0.f, qz = 0.f, ql = 0.f;
         const bool valid = t < total1;
         if (valid) {
             const unsigned long long key = key1[t];
@@ -252,6 +280,7 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
             b = (int)(t / N);
             const float *q = xyz1 + (size_t)t * 3;
             qx = q[0]; qy = q[1]; qz = q[2];
+            if (LABELED) ql = label1[t];
         }
         int found = g * CH_GR;
 #pragma unroll 4
@@ -262,17 +291,23 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
             const float x_s = __shfl_sync(FULL_MASK, qx, s);
             const float y_s = __shfl_sync(FULL_MASK, qy, s);
             const float z_s = __shfl_sync(FULL_MASK, qz, s);
+            const float l_s = LABELED ? __shfl_sync(FULL_MASK, ql, s) : 0.f;
             const int j = g_s * CH_GR + lane;
             bool match = false;
             if (j < M) {
                 const float *r = xyz2 + ((size_t)b_s * M + j) * 3;
                 const float d = sqdist_xyz(__ldg(r), __ldg(r + 1), __ldg(r + 2), x_s, y_s, z_s);
                 match = __float_as_uint(d) == w_s;
+                if (LABELED) match = match && __ldg(label2 + (size_t)b_s * M + j) == l_s;
             }
             const unsigned hit = __ballot_sync(FULL_MASK, match);
             if (lane == s && hit != 0u) found = g_s * CH_GR + __ffs(hit) - 1;
         }
         if (valid) {
+            if (LABELED && want == INF_BITS) {
+                want = 0u;
+                found = -1;
+            }
             dist1[t] = __uint_as_float(want);
             idx1[t] = found;
             s1 = __uint_as_float(want);
@@ -284,10 +319,11 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
             const int b = (int)(u / M);
             const unsigned long long key = key2[u];
             key2[u] = KEY_INIT;
-            const unsigned want = (unsigned)(key >> 32);
+            unsigned want = (unsigned)(key >> 32);
             const int g = (int)(unsigned)key;
             const float *r = xyz2 + (size_t)u * 3;
             const float rx = r[0], ry = r[1], rz = r[2];
+            const float rl = LABELED ? label2[u] : 0.f;
             const float *q = xyz1 + (size_t)b * N * 3;
             const int i0 = g * Q;
             int found = i0;
@@ -298,8 +334,14 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
                     // same operand roles as the hot loop: (cloud-2 point) - (cloud-1 point)
                     const float d = sqdist_xyz(rx, ry, rz, __ldg(q + (size_t)i * 3), __ldg(q + (size_t)i * 3 + 1),
                                                __ldg(q + (size_t)i * 3 + 2));
-                    if (__float_as_uint(d) == want) found = i;
+                    bool same = __float_as_uint(d) == want;
+                    if (LABELED) same = same && __ldg(label1 + (size_t)b * N + i) == rl;
+                    if (same) found = i;
                 }
+            }
+            if (LABELED && want == INF_BITS) {
+                want = 0u;
+                found = -1;
             }
             dist2[u] = __uint_as_float(want);
             idx2[u] = found;
@@ -465,10 +507,11 @@ extern "C" size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M) {
     return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M);
 }
 
-template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true>
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true, bool LABELED = false>
 static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                               unsigned long long *key1, unsigned long long *key2, float *dist1,
-                              float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st) {
+                              float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st,
+                              const float *label1 = nullptr, const float *label2 = nullptr) {
     constexpr int TQ = Q * THREADS;
     const int ref_blocks = ceil_div(M, RB);
     // Query splits: enough CTAs for several waves (tail effect), but as few as possible so
@@ -484,16 +527,16 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     dim3 grid(ref_blocks, B, splits);
     {
         KernelTimer timer("chamfer_fwd", st);
-        chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE><<<grid, THREADS, 0, st>>>(xyz1, xyz2, N, M, key1, key2,
-                                                                   queries_per_split);
+        chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, LABELED><<<grid, THREADS, 0, st>>>(
+            xyz1, xyz2, N, M, key1, key2, queries_per_split, label1, label2);
     }
     PP_LAUNCH_CHECK();
     const int row_blocks = (int)ceil_div_ll((long long)B * N, 256);
     const int col_blocks = (int)ceil_div_ll((long long)B * M, 256);
     {
         KernelTimer timer("chamfer_finalize", st);
-        PP_CUDA(launch_pdl(chamfer_finalize_kernel<Q>, dim3(row_blocks + col_blocks), dim3(256), 0, st, xyz1, xyz2, B,
-                           N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks));
+        PP_CUDA(launch_pdl(chamfer_finalize_kernel<Q, LABELED>, dim3(row_blocks + col_blocks), dim3(256), 0, st, xyz1,
+                           xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks, label1, label2));
     }
     PP_LAUNCH_CHECK();
     return PP_OK;
@@ -564,6 +607,10 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     switch (pick) {
         case 1: return launch_chamfer_fwd<8, 128, 256, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 2: return launch_chamfer_fwd<8, 128, 128, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 3: return launch_chamfer_fwd<8, 128, 96, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 4: return launch_chamfer_fwd<8, 128, 64, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 5: return launch_chamfer_fwd<8, 64, 128, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 6: return launch_chamfer_fwd<8, 128, 160, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 13: return launch_chamfer_fwd<8, 128, 256, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         case 14: return launch_chamfer_fwd<8, 128, 128, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
         default: break;
@@ -574,8 +621,8 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
 
 extern "C" int pp_chamfer_labeled_fwd(const float *xyz1, const float *xyz2, const float *label1,
                                       const float *label2, int B, int N, int M, int c, float *dist1,
-                                      float *dist2, int32_t *idx1, int32_t *idx2, int device,
-                                      void *stream) {
+                                      float *dist2, int32_t *idx1, int32_t *idx2, void *workspace,
+                                      size_t workspace_bytes, int flags, int device, void *stream) {
     PP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && c >= 1, "chamfer_labeled_fwd: bad sizes");
     if (B == 0 || (N == 0 && M == 0)) return PP_OK;
     PP_REQUIRE((N == 0 || (xyz1 && label1 && dist1 && idx1)) && (M == 0 || (xyz2 && label2 && dist2 && idx2)), "chamfer_labeled_fwd: null pointer");
@@ -587,7 +634,25 @@ extern "C" int pp_chamfer_labeled_fwd(const float *xyz1, const float *xyz2, cons
         if (M) { PP_CUDA(cudaMemsetAsync(dist2, 0, sizeof(float) * (size_t)B * M, st)); PP_CUDA(cudaMemsetAsync(idx2, 0, sizeof(int) * (size_t)B * M, st)); }
         return PP_OK;
     }
-    return launch_generic(true, xyz1, xyz2, label1, label2, B, N, M, c, dist1, dist2, idx1, idx2, st);
+    if (c != 3 || workspace == nullptr || get_option("chamfer_generic", 0))
+        return launch_generic(true, xyz1, xyz2, label1, label2, B, N, M, c, dist1, dist2, idx1, idx2, st);
+    // fast path: the one-pass kernel with the label mask (same key workspace protocol as pp_chamfer_fwd)
+    PP_REQUIRE((long long)B * N * c < (1ll << 31) && (long long)B * M * c < (1ll << 31),
+               "chamfer_labeled_fwd: B*N*c must fit int32 indexing like the reference");
+    const size_t need = pp_chamfer_fwd_workspace_bytes(B, N, M);
+    PP_REQUIRE(((uintptr_t)workspace & 7) == 0, "chamfer_labeled_fwd: workspace misaligned");
+    if (workspace_bytes < need) {
+        set_error("chamfer_labeled_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
+        return PP_ENOSPC;
+    }
+    unsigned long long *key1 = (unsigned long long *)workspace;
+    unsigned long long *key2 = key1 + (size_t)B * N;
+    if (!(flags & PP_CHAMFER_WS_CLEAN)) PP_CUDA(cudaMemsetAsync(workspace, 0xff, need, st));
+    if (M <= 4096)
+        return launch_chamfer_fwd<8, 128, 128, 4, true, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2,
+                                                              nullptr, st, label1, label2);
+    return launch_chamfer_fwd<8, 128, 256, 4, true, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2,
+                                                          nullptr, st, label1, label2);
 }
 
 static int chamfer_bwd_impl(const float *xyz1, const float *xyz2, const float *graddist1,

@@ -65,7 +65,7 @@ def test_chamfer_forward_bit_exact(pp, oracle_mod, B, N, M, maker, seed):
     assert np.array_equal(np32(d2).view(np.uint32), e2.view(np.uint32)), "dist2 bits"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 13, 14])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 13, 14])
 def test_chamfer_forward_all_variants(pp, oracle_mod, variant):
     from pytorch_points_b200 import _C
     a = with_duplicates(uniform_cloud(2, 1500, 11))
@@ -297,6 +297,45 @@ def test_labeled_chamfer(pp, oracle_mod):
     o1, o2 = oracle_mod.chamfer_bwd(np32(a), np32(b), np.ones((2, 700), np.float32), np.ones((2, 900), np.float32), j1, j2)
     assert_grad_close(np32(ga.grad), o1, "labeled gradxyz1")
     assert_grad_close(np32(gb.grad), o2, "labeled gradxyz2")
+
+
+@pytest.mark.parametrize("B,N,M,nl,dup", [(1, 1, 1, 1, False), (2, 33, 5000, 5, True), (3, 4500, 257, 2, False),
+                                           (1, 2500, 2500, 40, True), (2, 127, 129, 300, False)])
+def test_labeled_chamfer_fast_path_matches_oracle_and_generic(pp, oracle_mod, B, N, M, nl, dup):
+    """One-pass kernel with the label mask (pp_chamfer_labeled_fwd with a workspace) against the
+    oracle and against the chunk-by-chunk restatement (chamfer_generic=1): ragged sizes, both
+    reference-block widths (M <= 4096 / above), duplicated points (ties must resolve to the lowest
+    same-label index), labels without a partner on either side (-> idx -1, dist 0)."""
+    from pytorch_points_b200 import _C
+    a, b = uniform_cloud(B, N, 61), uniform_cloud(B, M, 62)
+    if dup:
+        a, b = with_duplicates(a), with_duplicates(b)
+    g = torch.Generator().manual_seed(63)
+    la = torch.randint(0, nl + 1, (B, N, 1), generator=g)  # label nl never appears in b
+    lb = torch.randint(-1, nl, (B, M, 1), generator=g)     # label -1 never appears in a
+    e1, e2, j1, j2 = oracle_mod.chamfer_labeled_fwd(np32(a), np32(b), np32(la.float()), np32(lb.float()))
+    for generic in (0, 1, 0):  # fast, generic, fast again (the key workspace must come back clean)
+        _C.set_option("chamfer_generic", generic)
+        try:
+            d1, d2, i1, i2 = pp.labeled_nndistance(dev(a), dev(b), dev(la), dev(lb))
+        finally:
+            _C.set_option("chamfer_generic", 0)
+        assert np.array_equal(np32(i1), j1) and np.array_equal(np32(i2), j2), "generic=%d" % generic
+        assert np.array_equal(np32(d1), e1) and np.array_equal(np32(d2), e2), "generic=%d" % generic
+    # the unlabeled path shares the workspace: it must still see it clean
+    d1, d2, i1, i2 = pp.nndistance(dev(a), dev(b))
+    f1, f2, k1, k2 = oracle_mod.chamfer_fwd(np32(a), np32(b))
+    assert np.array_equal(np32(i1), k1) and np.array_equal(np32(i2), k2)
+    assert np.array_equal(np32(d1), f1) and np.array_equal(np32(d2), f2)
+
+
+def test_labeled_chamfer_single_label_equals_unlabeled(pp):
+    a, b = dev(with_duplicates(uniform_cloud(2, 3000, 64))), dev(uniform_cloud(2, 5000, 65))
+    la, lb = torch.zeros(2, 3000, 1, device="cuda"), torch.zeros(2, 5000, 1, device="cuda")
+    got = pp.labeled_nndistance(a, b, la, lb)
+    want = pp.nndistance(a, b)
+    for x, y in zip(got, want):
+        assert torch.equal(x, y)
 
 
 def test_chamfer_fused_sums(pp):
