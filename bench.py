@@ -254,7 +254,31 @@ def main():
             except Exception as e:  # noqa: BLE001
                 exchange_note += " (peer exchange unavailable: %s)" % (repr(e)[:120],)
 
-    def step_device():
+    # Fused step (default): forward + uniform backward in two launches
+    # (pp_chamfer_fwd_bwd_uniform); PP_FUSED_BWD=0 = the four-launch sequence.  Checked against
+    # the four-launch sequence on this very input before anything is timed.
+    fused = os.environ.get("PP_FUSED_BWD", "1") != "0"
+    fused_note = "disabled (PP_FUSED_BWD=0)"
+    if fused:
+        c1, c2 = torch.empty_like(a), torch.empty_like(b)
+        losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
+        losses.nmdistance_backward_uniform(a, b, c1, c2, gw, i1, i2)
+        j1, j2 = i1.clone(), i2.clone()
+        losses.nmdistance_forward_backward_uniform(a, b, d1, d2, i1, i2, sums, gw, g1, g2)
+        err = max(float((g1 - c1).abs().max() / c1.abs().max()), float((g2 - c2).abs().max() / c2.abs().max()))
+        if torch.equal(i1, j1) and torch.equal(i2, j2) and err <= 1e-5:
+            fused_note = "on; gradients agree with the four-launch sequence to %.1e (rel. to max)" % err
+        else:
+            fused, fused_note = False, "CHECK FAILED (rel err %.3g): fell back to the four-launch sequence" % err
+            sys.stderr.write("[bench] fused forward+backward disagrees with the separate kernels; not used\n")
+        del c1, c2, j1, j2
+        if world > 1:  # every rank must take the same path
+            flag = torch.tensor([1 if fused else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if fused and int(flag.item()) == 0:
+                fused, fused_note = False, "CHECK FAILED on another rank: four-launch sequence"
+
+    def step_device_unfused():
         # forward (+ fused partial sums) -> exchange of the 2 sums -> backward with the two
         # constant upstream weights d(loss)/d(dist) = 1/(B_total*N), 1/(B_total*M)
         losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
@@ -270,6 +294,19 @@ def main():
             exchange.wait(total)
         elif work is not None:
             work.wait()
+
+    def step_device_fused():
+        # forward + finalize with the backward folded in (constant upstream weights), then the
+        # exchange of the 2 sums
+        losses.nmdistance_forward_backward_uniform(a, b, d1, d2, i1, i2, sums, gw, g1, g2)
+        if exchange is not None:
+            exchange.send(sums)
+            exchange.wait(total)
+        elif world > 1:
+            total.copy_(sums)
+            dist.all_reduce(total)
+
+    step_device = step_device_fused if fused else step_device_unfused
 
     from pytorch_points_b200.pipeline import HostPrefetcher
     prefetcher = HostPrefetcher(dev, depth=2)
@@ -305,7 +342,8 @@ def main():
     if world > 1:
         dist.all_reduce(sums)  # the communicator exists before the first replay
         torch.cuda.synchronize()
-    graphed = GraphedChamferStep([(a_host, b_host)], total_batch=total_B, device=dev, world_size=world, exchange=exchange)
+    graphed = GraphedChamferStep([(a_host, b_host)], total_batch=total_B, device=dev, world_size=world, exchange=exchange,
+                                 fused_backward=fused)
 
     def step_e2e_graph():
         """The whole step (H2D x2 from pinned host, forward, backward, D2H of the loss sums) as one
@@ -388,6 +426,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_step = timed(step_device, args.steps, args.warmup)
+    ms_step_unfused = timed(step_device_unfused, args.steps, args.warmup) if fused else ms_step
     ms_e2e_plugin = timed_e2e(step_e2e, args.steps, args.warmup)
     ms_e2e_autograd = timed_e2e(step_e2e_autograd, min(args.steps, 50), 3)
     if graphed is not None:
@@ -395,8 +434,10 @@ def main():
         losses_read[0] = 0
         ms_e2e = timed_e2e(step_e2e_pipelined, args.steps, args.warmup, finish=finish_pipelined)
         assert losses_read[0] == args.steps + args.warmup, "every step's loss must be read on the host"
-        e2e_api = ("pipeline.GraphedChamferStep.submit()/loss(): compute graph(s) (pp_chamfer_fwd + finalize with fused loss "
-                   "sums, [eager NCCL all-reduce of the sums when N>1,] pp_chamfer_bwd_uniform, D2H of the sums) on one "
+        e2e_api = ("pipeline.GraphedChamferStep.submit()/loss(): compute graph(s) (" +
+                   ("pp_chamfer_fwd_bwd_uniform: forward + finalize with fused loss sums and backward" if fused else
+                    "pp_chamfer_fwd + finalize with fused loss sums, pp_chamfer_bwd_uniform") +
+                   ", [exchange of the sums when N>1,] D2H of the sums) on one "
                    "stream, copy graph (H2D of the NEXT step's two clouds from pinned host) on a second stream; "
                    "software-pipelined two deep: the host reads step i's loss while step i+1 runs -- every step copies "
                    "its inputs in and has its loss read on the host inside the timed region")
@@ -448,8 +489,10 @@ def main():
         "note": "the reference rounding order needs 6 FP32 lane-ops per pair (3 sub, 1 mul, 2 fma = 8 FLOP in "
                 "12 FLOP slots), so 0.667 of the FFMA peak is the hard ceiling; op_mix_ceiling is that bound "
                 "measured live with the packed FADD2/FMUL2/FFMA2+FMNMX3 mix",
-        "other_kernels_ms": {"chamfer_finalize": kt["chamfer_finalize"][0] / max(kt["chamfer_finalize"][1], 1),
-                             "chamfer_bwd(2 launches)": kt["chamfer_bwd"][0] / max(kt["chamfer_bwd"][1], 1)},
+        "other_kernels_ms": ({"chamfer_finalize(+fused backward)": kt["chamfer_finalize"][0] / max(kt["chamfer_finalize"][1], 1)}
+                             if fused else
+                             {"chamfer_finalize": kt["chamfer_finalize"][0] / max(kt["chamfer_finalize"][1], 1),
+                              "chamfer_bwd(2 launches)": kt["chamfer_bwd"][0] / max(kt["chamfer_bwd"][1], 1)}),
     }
 
     line = {
@@ -473,8 +516,10 @@ def main():
                                       "nmdistance_backward_uniform (the reference-shaped plugin boundary) + D2H of the loss sums"},
                 "autograd_api": {"value": pairs_per_step / (ms_e2e_autograd * 1e-3), "ms_per_step": ms_e2e_autograd,
                                  "api": "host .to(device) + dist.sharded_chamfer_loss (torch.autograd) + loss.backward() + loss.item()"}, "timing": "one CUDA-event region over all K steps; every step copies its inputs from pinned host memory and ends with a host read of the loss"},
-        "gpu_launches": (4 + (2 if exchange is not None else 0)) * args.steps,
-        "gpu_launches_note": "per step: chamfer_fwd_kernel, chamfer_finalize_kernel, chamfer_bwd_kernel<0>, <1>"
+        "fused_step": {"state": fused_note, "ms_per_step_four_launch_sequence": ms_step_unfused},
+        "gpu_launches": ((2 if fused else 4) + (2 if exchange is not None else 0)) * args.steps,
+        "gpu_launches_note": ("per step: chamfer_fwd_kernel, chamfer_finalize_kernel<fused backward>" if fused else
+                              "per step: chamfer_fwd_kernel, chamfer_finalize_kernel, chamfer_bwd_kernel<0>, <1>")
                              + (", lx_send_kernel, lx_wait_kernel" if exchange is not None else ""),
         "clocks": clocks, "roofline": roofline,
         "loss": {"device_leg": loss_dev, "e2e_plugin_leg": loss_e2e, "e2e_graph_leg": loss_graph},

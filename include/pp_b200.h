@@ -97,6 +97,21 @@ int pp_chamfer_bwd_uniform(const float *xyz1, const float *xyz2, const float *gw
                            const int32_t *idx1, const int32_t *idx2, int B, int N, int M, int c,
                            float *gradxyz1, float *gradxyz2, int device, void *stream);
 
+/*
+ * Chamfer forward AND backward for sum/mean-type losses in two launches (extension, no reference
+ * counterpart): pp_chamfer_fwd followed by pp_chamfer_bwd_uniform, with the backward folded into
+ * the kernel that resolves the nearest-neighbour indices.  c == 3.  Outputs as for pp_chamfer_fwd
+ * (dist/idx/sums) plus gradxyz1 (B,N,3) / gradxyz2 (B,M,3), fully overwritten; gw = 2-float DEVICE
+ * vector d(loss)/d[sum(dist1), sum(dist2)], known before the forward for a mean-type loss.
+ * Gradients equal pp_chamfer_bwd_uniform's up to fp32 summation order (both use unordered
+ * RED.ADD.F32 like the reference's atomicAdd, _ext/nmdistance_cuda.cu:176-181).
+ * workspace / workspace_bytes / flags: as for pp_chamfer_fwd (the entry points may share it).
+ */
+int pp_chamfer_fwd_bwd_uniform(const float *xyz1, const float *xyz2, const float *gw, int B, int N,
+                               int M, float *dist1, float *dist2, int32_t *idx1, int32_t *idx2,
+                               float *sums, float *gradxyz1, float *gradxyz2, void *workspace,
+                               size_t workspace_bytes, int flags, int device, void *stream);
+
 /* ---------------------------------------------------------------- sampling */
 
 /*
@@ -270,7 +285,8 @@ int pp_knn_stats(double *tiles_visited, double *tiles_total);
  *   "timing" (0)                 per-kernel CUDA events, see pp_timing_collect
  *   "pdl" (1)                    programmatic dependent launch of the short follow-up kernels
  *   "chamfer_variant" (0)        0 = automatic; 1 / 2 = 256- / 128-point reference blocks;
- *                                13 / 14 = the same without the per-warp sweep rotation
+ *                                3 / 4 / 6 = 96- / 64- / 160-point blocks; 5 = 64-thread CTAs;
+ *                                13 / 14 = 1 / 2 without the per-warp sweep rotation
  *   "chamfer_blocks_per_sm" (24) target CTA count per SM for the query split heuristic
  *   "chamfer_generic" (0)        force the generic (any point dimension) kernel
  *   "fps_cluster" (0)            0 = automatic, else the cluster width 1 / 2 / 4 / 8

@@ -24,6 +24,7 @@ SIGNATURES = {
     "pp_chamfer_labeled_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "pp_chamfer_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_chamfer_bwd_uniform": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "pp_chamfer_fwd_bwd_uniform": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "pp_fps": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_fps_gather": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "pp_gather_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),

@@ -108,3 +108,31 @@ def nmdistance_backward_uniform(xyz1, xyz2, gradxyz1, gradxyz2, gw, idx1, idx2):
                                        _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_bwd_uniform")
     return 1
+
+
+def nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, sums, gw, gradxyz1, gradxyz2):
+    """Extension: `nmdistance_forward(..., sums=sums)` followed by `nmdistance_backward_uniform` in
+    two launches instead of four -- the backward rides in the kernel that resolves the indices.
+    For losses that depend on dist1/dist2 only through their sums with weights `gw` known up
+    front (mean / sum Chamfer).  `sums` may be None.  c == 3."""
+    dev = _C.require_cuda(xyz1, xyz2, dist1, dist2, idx1, idx2, gw, gradxyz1, gradxyz2)
+    _C.require_contiguous(xyz1, xyz2, dist1, dist2, idx1, idx2, gw, gradxyz1, gradxyz2)
+    _check_f32(xyz1, xyz2, dist1, dist2, gw, gradxyz1, gradxyz2)
+    B, N, c = xyz1.shape
+    M = xyz2.shape[1]
+    if c != 3 or xyz2.shape[0] != B or xyz2.shape[2] != 3:
+        raise RuntimeError("nmdistance_forward_backward_uniform: needs (B,N,3) and (B,M,3) clouds")
+    if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
+        raise RuntimeError("nmdistance_forward_backward_uniform: idx tensors must be int32")
+    if gw.numel() != 2 or gradxyz1.shape != xyz1.shape or gradxyz2.shape != xyz2.shape:
+        raise RuntimeError("nmdistance_forward_backward_uniform: gw must hold 2 floats, gradients match the clouds")
+    nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
+    key, ws = _workspace(dev, nbytes)
+    rc = _C.lib.pp_chamfer_fwd_bwd_uniform(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(gw), B, N, M, _C.ptr(dist1),
+                                           _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums),
+                                           _C.ptr(gradxyz1), _C.ptr(gradxyz2), _C.ptr(ws), ws.numel(),
+                                           _C.PP_CHAMFER_WS_CLEAN, dev.index, _C.stream_of(dev))
+    if rc != 0:
+        _workspaces.pop(key, None)
+    _C.check(rc, "pp_chamfer_fwd_bwd_uniform")
+    return 1

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
 chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int N, int M,
                    unsigned long long *__restrict__ key1, unsigned long long *__restrict__ key2,
                    int queries_per_split, const float *__restrict__ label1,
-                   const float *__restrict__ label2) {
+                   const float *__restrict__ label2, float *__restrict__ zero1,
+                   float *__restrict__ zero2) {
     __shared__ __align__(16) float sX[RB];
     __shared__ __align__(16) float sY[RB];
     __shared__ __align__(16) float sZ[RB];
@@ -102,6 +103,20 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
         sW[t] = w;
         // padding carries a NaN label: equal to nothing
         if (LABELED) sLab[t] = j < M ? __ldg(label2 + (size_t)b * M + j) : __int_as_float(0x7fc00000);
+    }
+    // Fused backward (pp_chamfer_fwd_bwd_uniform): the finalize kernel accumulates the gradients
+    // with RED.ADD, so they start from zero -- each (reference block, split 0) CTA clears its
+    // slice of gradxyz2, each (reference block 0, split) CTA its slice of gradxyz1.  The finalize
+    // kernel starts after this whole grid has completed (griddepcontrol.wait).
+    if (zero2 != nullptr && blockIdx.z == 0) {
+        const int lim = (min(M, ref_begin + RB) - ref_begin) * 3;
+        float *z = zero2 + ((size_t)b * M + ref_begin) * 3;
+        for (int t = threadIdx.x; t < lim; t += THREADS) z[t] = 0.f;
+    }
+    if (zero1 != nullptr && blockIdx.x == 0) {
+        const int lim = (q_end - q_begin) * 3;
+        float *z = zero1 + ((size_t)b * N + q_begin) * 3;
+        for (int t = threadIdx.x; t < lim; t += THREADS) z[t] = 0.f;
     }
     __syncthreads();
 
@@ -250,14 +265,20 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
 //   rows   : a warp takes 32 queries; for each, its 32 lanes test the 32 references of the
 //            recorded granule at once (coalesced 384-byte read, ballot, find-first-set);
 //   columns: a thread re-evaluates the Q queries of the recorded group, fully unrolled.
-template <int Q, bool LABELED>
+// FUSE_BWD (pp_chamfer_fwd_bwd_uniform): the backward for a loss that sees dist1/dist2 only through
+// their sums runs right here -- the thread that resolves a point's neighbour also forms
+// v = 2*gw[side]*(point - neighbour) (_ext/nmdistance_cuda.cu:176-181, same rounding steps as
+// chamfer_bwd_kernel) and adds +v to its own gradient and -v to the neighbour's with RED.ADD.F32
+// on arrays the forward kernel cleared.  No idx round trip, no extra launches.
+template <int Q, bool LABELED, bool FUSE_BWD>
 __global__ void __launch_bounds__(256)
 chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int B, int N,
                         int M, unsigned long long *__restrict__ key1,
                         unsigned long long *__restrict__ key2, float *__restrict__ dist1,
                         float *__restrict__ dist2, int *__restrict__ idx1, int *__restrict__ idx2,
                         float *__restrict__ sums, int row_blocks, const float *__restrict__ label1,
-                        const float *__restrict__ label2) {
+                        const float *__restrict__ label2, const float *__restrict__ gw,
+                        float *__restrict__ g1, float *__restrict__ g2) {
     constexpr unsigned INF_BITS = 0x7f800000u;  // LABELED: no same-label partner -> (dist 0, idx -1)
     const int lane = threadIdx.x & 31;
     float s1 = 0.f, s2 = 0.f;
@@ -311,6 +332,16 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
             dist1[t] = __uint_as_float(want);
             idx1[t] = found;
             s1 = __uint_as_float(want);
+            if (FUSE_BWD && found >= 0) {
+                const float g = __fmul_rn(__ldg(gw + 0), 2.f);
+                const size_t nb = ((size_t)b * M + found) * 3;
+                const float vx = __fmul_rn(g, __fsub_rn(qx, __ldg(xyz2 + nb + 0)));
+                const float vy = __fmul_rn(g, __fsub_rn(qy, __ldg(xyz2 + nb + 1)));
+                const float vz = __fmul_rn(g, __fsub_rn(qz, __ldg(xyz2 + nb + 2)));
+                float *own = g1 + (size_t)t * 3, *other = g2 + nb;
+                atomicAdd(own + 0, vx); atomicAdd(own + 1, vy); atomicAdd(own + 2, vz);
+                atomicAdd(other + 0, -vx); atomicAdd(other + 1, -vy); atomicAdd(other + 2, -vz);
+            }
         }
     } else {
         const long long total2 = (long long)B * M;
@@ -346,6 +377,16 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
             dist2[u] = __uint_as_float(want);
             idx2[u] = found;
             s2 = __uint_as_float(want);
+            if (FUSE_BWD && found >= 0) {
+                const float g = __fmul_rn(__ldg(gw + 1), 2.f);
+                const size_t nb = ((size_t)b * N + found) * 3;
+                const float vx = __fmul_rn(g, __fsub_rn(rx, __ldg(xyz1 + nb + 0)));
+                const float vy = __fmul_rn(g, __fsub_rn(ry, __ldg(xyz1 + nb + 1)));
+                const float vz = __fmul_rn(g, __fsub_rn(rz, __ldg(xyz1 + nb + 2)));
+                float *own = g2 + (size_t)u * 3, *other = g1 + nb;
+                atomicAdd(own + 0, vx); atomicAdd(own + 1, vy); atomicAdd(own + 2, vz);
+                atomicAdd(other + 0, -vx); atomicAdd(other + 1, -vy); atomicAdd(other + 2, -vz);
+            }
         }
     }
     if (sums != nullptr) {
@@ -511,7 +552,8 @@ template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true, bool LABELED
 static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                               unsigned long long *key1, unsigned long long *key2, float *dist1,
                               float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st,
-                              const float *label1 = nullptr, const float *label2 = nullptr) {
+                              const float *label1 = nullptr, const float *label2 = nullptr,
+                              const float *gw = nullptr, float *g1 = nullptr, float *g2 = nullptr) {
     constexpr int TQ = Q * THREADS;
     const int ref_blocks = ceil_div(M, RB);
     // Query splits: enough CTAs for several waves (tail effect), but as few as possible so
@@ -528,15 +570,21 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     {
         KernelTimer timer("chamfer_fwd", st);
         chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, LABELED><<<grid, THREADS, 0, st>>>(
-            xyz1, xyz2, N, M, key1, key2, queries_per_split, label1, label2);
+            xyz1, xyz2, N, M, key1, key2, queries_per_split, label1, label2, g1, g2);
     }
     PP_LAUNCH_CHECK();
     const int row_blocks = (int)ceil_div_ll((long long)B * N, 256);
     const int col_blocks = (int)ceil_div_ll((long long)B * M, 256);
     {
         KernelTimer timer("chamfer_finalize", st);
-        PP_CUDA(launch_pdl(chamfer_finalize_kernel<Q, LABELED>, dim3(row_blocks + col_blocks), dim3(256), 0, st, xyz1,
-                           xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks, label1, label2));
+        if (!LABELED && gw != nullptr)
+            PP_CUDA(launch_pdl(chamfer_finalize_kernel<Q, false, true>, dim3(row_blocks + col_blocks), dim3(256), 0,
+                               st, xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks,
+                               label1, label2, gw, g1, g2));
+        else
+            PP_CUDA(launch_pdl(chamfer_finalize_kernel<Q, LABELED, false>, dim3(row_blocks + col_blocks), dim3(256),
+                               0, st, xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, row_blocks,
+                               label1, label2, gw, g1, g2));
     }
     PP_LAUNCH_CHECK();
     return PP_OK;
@@ -567,10 +615,11 @@ static int launch_generic(bool labeled, const float *xyz1, const float *xyz2, co
     return PP_OK;
 }
 
-extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
-                              float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,
-                              void *workspace, size_t workspace_bytes, int flags, int device,
-                              void *stream) {
+// gw/g1/g2 != nullptr: the fused forward + uniform backward (c == 3 only).
+static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
+                            float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,
+                            void *workspace, size_t workspace_bytes, int flags, int device,
+                            void *stream, const float *gw, float *g1, float *g2) {
     PP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && c >= 1, "chamfer_fwd: bad sizes B=%d N=%d M=%d c=%d", B, N, M, c);
     PP_REQUIRE((long long)B * N * c < (1ll << 31) && (long long)B * M * c < (1ll << 31),
                "chamfer_fwd: B*N*c must fit int32 indexing like the reference");
@@ -585,9 +634,13 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
         // the reference's loops never run and leave the Python-side zero fill in place
         if (N) { PP_CUDA(cudaMemsetAsync(dist1, 0, sizeof(float) * (size_t)B * N, st)); PP_CUDA(cudaMemsetAsync(idx1, 0, sizeof(int) * (size_t)B * N, st)); }
         if (M) { PP_CUDA(cudaMemsetAsync(dist2, 0, sizeof(float) * (size_t)B * M, st)); PP_CUDA(cudaMemsetAsync(idx2, 0, sizeof(int) * (size_t)B * M, st)); }
+        // nothing to match against: gradients are zero (as in chamfer_bwd_impl)
+        if (gw && N) PP_CUDA(cudaMemsetAsync(g1, 0, sizeof(float) * (size_t)B * N * c, st));
+        if (gw && M) PP_CUDA(cudaMemsetAsync(g2, 0, sizeof(float) * (size_t)B * M * c, st));
         return PP_OK;
     }
     if (c != 3 || get_option("chamfer_generic", 0)) {
+        PP_REQUIRE(gw == nullptr, "chamfer_fwd_bwd_uniform: only available for c == 3");
         PP_REQUIRE(sums == nullptr, "chamfer_fwd: fused sums are only available for c == 3");
         return launch_generic(false, xyz1, xyz2, nullptr, nullptr, B, N, M, c, dist1, dist2, idx1, idx2, st);
     }
@@ -605,18 +658,37 @@ extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     int pick = get_option("chamfer_variant", 0);
     if (pick == 0) pick = (M <= 4096) ? 2 : 1;  // smaller reference blocks keep small clouds spread over all SMs
     switch (pick) {
-        case 1: return launch_chamfer_fwd<8, 128, 256, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 2: return launch_chamfer_fwd<8, 128, 128, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 3: return launch_chamfer_fwd<8, 128, 96, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 4: return launch_chamfer_fwd<8, 128, 64, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 5: return launch_chamfer_fwd<8, 64, 128, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 6: return launch_chamfer_fwd<8, 128, 160, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 13: return launch_chamfer_fwd<8, 128, 256, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
-        case 14: return launch_chamfer_fwd<8, 128, 128, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st);
+        case 1: return launch_chamfer_fwd<8, 128, 256, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 2: return launch_chamfer_fwd<8, 128, 128, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 3: return launch_chamfer_fwd<8, 128, 96, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 4: return launch_chamfer_fwd<8, 128, 64, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 5: return launch_chamfer_fwd<8, 64, 128, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 6: return launch_chamfer_fwd<8, 128, 160, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 13: return launch_chamfer_fwd<8, 128, 256, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 14: return launch_chamfer_fwd<8, 128, 128, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         default: break;
     }
     set_error("chamfer_fwd: unknown variant %d", pick);
     return PP_EINVAL;
+}
+
+extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
+                              float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,
+                              void *workspace, size_t workspace_bytes, int flags, int device,
+                              void *stream) {
+    return chamfer_fwd_impl(xyz1, xyz2, B, N, M, c, dist1, dist2, idx1, idx2, sums, workspace,
+                            workspace_bytes, flags, device, stream, nullptr, nullptr, nullptr);
+}
+
+extern "C" int pp_chamfer_fwd_bwd_uniform(const float *xyz1, const float *xyz2, const float *gw, int B,
+                                          int N, int M, float *dist1, float *dist2, int32_t *idx1,
+                                          int32_t *idx2, float *sums, float *gradxyz1, float *gradxyz2,
+                                          void *workspace, size_t workspace_bytes, int flags,
+                                          int device, void *stream) {
+    PP_REQUIRE(gw != nullptr || B == 0, "chamfer_fwd_bwd_uniform: null weight vector");
+    PP_REQUIRE(B == 0 || ((N == 0 || gradxyz1) && (M == 0 || gradxyz2)), "chamfer_fwd_bwd_uniform: null gradient pointer");
+    return chamfer_fwd_impl(xyz1, xyz2, B, N, M, 3, dist1, dist2, idx1, idx2, sums, workspace,
+                            workspace_bytes, flags, device, stream, gw, gradxyz1, gradxyz2);
 }
 
 extern "C" int pp_chamfer_labeled_fwd(const float *xyz1, const float *xyz2, const float *label1,

@@ -76,13 +76,17 @@ class GraphedChamferStep:
     i's loss while i+1 runs (each step still copies its inputs in and its loss out).
     """
 
-    def __init__(self, host_pairs, total_batch=None, device=None, group=None, world_size=1, exchange=None):
+    def __init__(self, host_pairs, total_batch=None, device=None, group=None, world_size=1, exchange=None,
+                 fused_backward=True):
         """With `world_size` > 1 every rank builds its own step over its shard of the batch.  With an
         `exchange` (dist.LossExchange) the global loss sums travel through peer memory and the whole
         step -- forward, send, backward, wait, D2H -- is ONE graph.  Without it the 8-byte NCCL
         all-reduce is NOT captured: the step is split into a forward graph and a backward graph
         and the all-reduce is issued eagerly between the two replays (asynchronously, so it
-        overlaps the backward, whose weights are constants)."""
+        overlaps the backward, whose weights are constants).
+        `fused_backward` (default): the forward and the uniform backward are the two launches of
+        `nmdistance_forward_backward_uniform`; False = the four-launch sequence forward, finalize,
+        backward x2."""
         from ._ext import losses
         self.world_size, self.group, self.exchange = world_size, group, exchange
         dev = torch.device(device if device is not None else torch.cuda.current_device())
@@ -115,20 +119,27 @@ class GraphedChamferStep:
         self.sums_host = [torch.zeros(2).pin_memory() for _ in range(2)]  # per buffer set
         self.compute_stream = torch.cuda.Stream(dev)
         self.copy_stream = torch.cuda.Stream(dev)
-        # chamfer_fwd, chamfer_finalize, chamfer_bwd<0>, chamfer_bwd<1> (+ lx_send, lx_wait)
-        self.launches = 4 + (2 if exchange is not None else 0)
+        # chamfer_fwd, chamfer_finalize[, chamfer_bwd<0>, chamfer_bwd<1>] (+ lx_send, lx_wait)
+        self.fused_backward = bool(fused_backward)
+        self.launches = (2 if self.fused_backward else 4) + (2 if exchange is not None else 0)
 
         def copy_body(s):
             self.xyz1[s].copy_(self.host_pairs[s][0], non_blocking=True)
             self.xyz2[s].copy_(self.host_pairs[s][1], non_blocking=True)
 
         def fwd_body(s):
-            losses.nmdistance_forward(self.xyz1[s], self.xyz2[s], self.dist1, self.dist2, self.idx1, self.idx2,
-                                      sums=self.sums)
+            if self.fused_backward:
+                losses.nmdistance_forward_backward_uniform(self.xyz1[s], self.xyz2[s], self.dist1, self.dist2,
+                                                           self.idx1, self.idx2, self.sums, self.gw, self.grad1,
+                                                           self.grad2)
+            else:
+                losses.nmdistance_forward(self.xyz1[s], self.xyz2[s], self.dist1, self.dist2, self.idx1, self.idx2,
+                                          sums=self.sums)
 
         def bwd_body(s):
-            losses.nmdistance_backward_uniform(self.xyz1[s], self.xyz2[s], self.grad1, self.grad2, self.gw,
-                                               self.idx1, self.idx2)
+            if not self.fused_backward:
+                losses.nmdistance_backward_uniform(self.xyz1[s], self.xyz2[s], self.grad1, self.grad2, self.gw,
+                                                   self.idx1, self.idx2)
 
         self.total = torch.zeros(2, device=dev) if exchange is not None else self.sums
 
@@ -167,11 +178,14 @@ class GraphedChamferStep:
                     compute_body(s)
                 self.compute_graph.append(g)
             else:
-                gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                gf = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gf, stream=self.compute_stream):
                     fwd_body(s)
-                with torch.cuda.graph(gb, stream=self.compute_stream):
-                    bwd_body(s)
+                gb = None  # fused: the backward already ran inside the forward graph
+                if not self.fused_backward:
+                    gb = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gb, stream=self.compute_stream):
+                        bwd_body(s)
                 self.compute_graph.append((gf, gb))
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
@@ -201,7 +215,8 @@ class GraphedChamferStep:
                 gf, gb = self.compute_graph[s]
                 gf.replay()
                 work = dist.all_reduce(self.sums, group=self.group, async_op=True)
-                gb.replay()
+                if gb is not None:
+                    gb.replay()
                 work.wait()
                 self.sums_host[s].copy_(self.sums, non_blocking=True)
             self.done[s].record(self.compute_stream)

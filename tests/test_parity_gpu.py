@@ -338,6 +338,51 @@ def test_labeled_chamfer_single_label_equals_unlabeled(pp):
         assert torch.equal(x, y)
 
 
+@pytest.mark.parametrize("B,N,M", [(2, 31, 1001), (3, 1001, 250), (1, 4097, 4099), (2, 2500, 2500)])
+def test_chamfer_entry_points_agree(pp, oracle_mod, B, N, M):
+    """Plain, labeled and fused-backward entry points on the same clouds: odd cloud strides,
+    partial last granules / query groups, duplicated points."""
+    from pytorch_points_b200._ext import losses
+    a, b = with_duplicates(uniform_cloud(B, N, 81)), with_duplicates(uniform_cloud(B, M, 82))
+    g = torch.Generator().manual_seed(83)
+    la, lb = torch.randint(0, 3, (B, N, 1), generator=g), torch.randint(1, 4, (B, M, 1), generator=g)
+    e = oracle_mod.chamfer_fwd(np32(a), np32(b))
+    el = oracle_mod.chamfer_labeled_fwd(np32(a), np32(b), np32(la.float()), np32(lb.float()))
+    got = pp.nndistance(dev(a), dev(b))
+    gotl = pp.labeled_nndistance(dev(a), dev(b), dev(la), dev(lb))
+    d1 = torch.empty(B, N, device="cuda"); d2 = torch.empty(B, M, device="cuda")
+    i1 = torch.empty(B, N, dtype=torch.int32, device="cuda"); i2 = torch.empty(B, M, dtype=torch.int32, device="cuda")
+    g1, g2 = torch.empty(B, N, 3, device="cuda"), torch.empty(B, M, 3, device="cuda")
+    gw = torch.tensor([0.5, 2.0], device="cuda")
+    losses.nmdistance_forward_backward_uniform(dev(a), dev(b), d1, d2, i1, i2, None, gw, g1, g2)
+    for x, y in zip(got, e):
+        assert np.array_equal(np32(x), y)
+    for x, y in zip(gotl, el):
+        assert np.array_equal(np32(x), y)
+    for x, y in zip((d1, d2, i1, i2), e):
+        assert np.array_equal(np32(x), y)
+    o1, o2 = oracle_mod.chamfer_bwd(np32(a), np32(b), np.full((B, N), 0.5, np.float32), np.full((B, M), 2.0, np.float32), e[2], e[3])
+    assert_grad_close(np32(g1), o1, "gradxyz1")
+    assert_grad_close(np32(g2), o2, "gradxyz2")
+
+
+def test_chamfer_unaligned_views(pp, oracle_mod):
+    """Clouds that start 4 bytes into an allocation: no kernel may assume 16-byte alignment of
+    the base pointers."""
+    from pytorch_points_b200._ext import losses
+    a, b = uniform_cloud(2, 640, 84), uniform_cloud(2, 512, 85)
+    e = oracle_mod.chamfer_fwd(np32(a), np32(b))
+    abuf = torch.empty(a.numel() + 1, device="cuda"); bbuf = torch.empty(b.numel() + 1, device="cuda")
+    av, bv = abuf[1:].view(2, 640, 3), bbuf[1:].view(2, 512, 3)
+    av.copy_(a); bv.copy_(b)
+    assert av.data_ptr() % 16 == 4 and av.is_contiguous()
+    d1 = torch.empty(2, 640, device="cuda"); d2 = torch.empty(2, 512, device="cuda")
+    i1 = torch.empty(2, 640, dtype=torch.int32, device="cuda"); i2 = torch.empty(2, 512, dtype=torch.int32, device="cuda")
+    losses.nmdistance_forward(av, bv, d1, d2, i1, i2)
+    for x, y in zip((d1, d2, i1, i2), e):
+        assert np.array_equal(np32(x), y)
+
+
 def test_chamfer_fused_sums(pp):
     from pytorch_points_b200._ext import losses
     a, b = dev(uniform_cloud(3, 999, 30)), dev(uniform_cloud(3, 1001, 31))
@@ -346,6 +391,66 @@ def test_chamfer_fused_sums(pp):
     sums = torch.full((2,), 123.0, device="cuda")
     losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
     assert torch.allclose(sums[0], d1.sum(), rtol=1e-5) and torch.allclose(sums[1], d2.sum(), rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,N,M,dup", [(1, 1, 1, False), (3, 999, 1001, True), (2, 5000, 300, False),
+                                        (2, 257, 4500, True), (4, 2500, 2500, False)])
+def test_chamfer_fused_forward_backward(pp, oracle_mod, B, N, M, dup):
+    """pp_chamfer_fwd_bwd_uniform (backward folded into the index-resolving kernel) against the
+    oracle: dist/idx bit-exact, gradients within 1e-5; twice in a row on dirty gradient buffers (the
+    forward kernel clears them) and followed by a plain forward on the shared key workspace."""
+    from pytorch_points_b200._ext import losses
+    a, b = uniform_cloud(B, N, 71), uniform_cloud(B, M, 72)
+    if dup:
+        a, b = with_duplicates(a), with_duplicates(b)
+    e1, e2, j1, j2 = oracle_mod.chamfer_fwd(np32(a), np32(b))
+    w = (0.25 / (B * N), 3.0 / (B * M))
+    o1, o2 = oracle_mod.chamfer_bwd(np32(a), np32(b), np.full((B, N), w[0], np.float32), np.full((B, M), w[1], np.float32), j1, j2)
+    ad, bd = dev(a), dev(b)
+    d1 = torch.empty(B, N, device="cuda"); d2 = torch.empty(B, M, device="cuda")
+    i1 = torch.empty(B, N, dtype=torch.int32, device="cuda"); i2 = torch.empty(B, M, dtype=torch.int32, device="cuda")
+    sums = torch.full((2,), 55.0, device="cuda")
+    gw = torch.tensor(w, device="cuda")
+    g1, g2 = torch.full_like(ad, 7.0), torch.full_like(bd, -7.0)
+    for _ in range(2):
+        losses.nmdistance_forward_backward_uniform(ad, bd, d1, d2, i1, i2, sums, gw, g1, g2)
+        assert np.array_equal(np32(i1), j1) and np.array_equal(np32(i2), j2)
+        assert np.array_equal(np32(d1), e1) and np.array_equal(np32(d2), e2)
+        assert torch.allclose(sums[0], d1.sum(), rtol=1e-5) and torch.allclose(sums[1], d2.sum(), rtol=1e-5)
+        assert_grad_close(np32(g1), o1, "fused gradxyz1")
+        assert_grad_close(np32(g2), o2, "fused gradxyz2")
+    # same numbers as the separate backward
+    h1, h2 = torch.empty_like(ad), torch.empty_like(bd)
+    losses.nmdistance_backward_uniform(ad, bd, h1, h2, gw, i1, i2)
+    assert_grad_close(np32(g1), np32(h1), "fused vs separate gradxyz1")
+    assert_grad_close(np32(g2), np32(h2), "fused vs separate gradxyz2")
+    losses.nmdistance_forward(ad, bd, d1, d2, i1, i2)
+    assert np.array_equal(np32(i1), j1) and np.array_equal(np32(i2), j2)
+
+
+def test_chamfer_fused_forward_backward_empty_side(pp):
+    from pytorch_points_b200._ext import losses
+    a, b = dev(uniform_cloud(2, 10, 73)), torch.empty(2, 0, 3, device="cuda")
+    d1 = torch.full((2, 10), 5.0, device="cuda"); d2 = torch.empty(2, 0, device="cuda")
+    i1 = torch.full((2, 10), 5, dtype=torch.int32, device="cuda"); i2 = torch.empty(2, 0, dtype=torch.int32, device="cuda")
+    g1, g2 = torch.full_like(a, 7.0), torch.empty_like(b)
+    losses.nmdistance_forward_backward_uniform(a, b, d1, d2, i1, i2, None, torch.ones(2, device="cuda"), g1, g2)
+    assert not d1.any() and not i1.any() and not g1.any()
+
+
+def test_graphed_step_fused_and_separate_agree(pp):
+    from pytorch_points_b200.pipeline import GraphedChamferStep
+    a, b = uniform_cloud(4, 700, 74).pin_memory(), uniform_cloud(4, 900, 75).pin_memory()
+    fused = GraphedChamferStep([(a, b)], fused_backward=True)
+    plain = GraphedChamferStep([(a, b)], fused_backward=False)
+    assert fused.launches == 2 and plain.launches == 4
+    for _ in range(3):
+        lf, lp = fused.run(), plain.run()
+        assert abs(lf - lp) <= 1e-6 * abs(lp)
+    torch.cuda.synchronize()
+    assert_grad_close(np32(fused.grad1), np32(plain.grad1), "graphed fused grad1")
+    assert_grad_close(np32(fused.grad2), np32(plain.grad2), "graphed fused grad2")
+    assert torch.equal(fused.idx1, plain.idx1) and torch.equal(fused.idx2, plain.idx2)
 
 
 # --------------------------------------------------------------------------- FPS
