@@ -573,8 +573,11 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
     sums = torch.zeros(2, device=dev)
 
     def chamfer_step():
-        losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
-        losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
+        if os.environ.get("PP_FUSED_BWD", "1") != "0":
+            losses.nmdistance_forward_backward_uniform(a, b, d1, d2, i1, i2, sums, gw, g1, g2)
+        else:
+            losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
+            losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
     _C.set_option("timing", 1)
     _C.timing_collect("chamfer_fwd")
     ms = timeit(chamfer_step)

@@ -60,7 +60,12 @@ __device__ __forceinline__ void publish_column_min(int lane, int leader, unsigne
 // labels are candidates -- every other distance is replaced by +inf right after it is computed,
 // so both minima see same-label partners only; a point without a partner keeps +inf and the
 // finalize kernel turns that into the reference's (dist 0, idx -1).
-template <int Q, int THREADS, int RB, int MINB, bool ROTATE, bool LABELED>
+// STAGEQ: a thread's Q query points are 12*Q contiguous bytes, so loading them straight from
+// global memory makes every LDG of a warp touch 24 different 128-byte lines (24 such loads per
+// tile: ~1200 cycles of the SM's single L1 wavefront queue, which the other warps' LDS.128 of the
+// hot loop wait behind).  Staged, the CTA reads its tile as whole lines into shared memory (one
+// pad word per 24 so that the per-thread readback at stride 25 words is conflict free).
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE, bool LABELED, bool STAGEQ = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int N, int M,
                    unsigned long long *__restrict__ key1, unsigned long long *__restrict__ key2,
@@ -72,6 +77,7 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
     __shared__ __align__(16) float sZ[RB];
     __shared__ __align__(16) unsigned sW[RB];  // filter: best column value seen (bits)
     __shared__ __align__(16) float sLab[LABELED ? RB : 4];
+    __shared__ float sQ[STAGEQ ? Q * THREADS * 3 + THREADS : 1];
 
     pdl_launch_dependents();  // the finalize kernel may take the SM slots this grid's tail frees
     constexpr int TQ = Q * THREADS;
@@ -121,6 +127,15 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
     __syncthreads();
 
     for (int qt = q_begin; qt < q_end; qt += TQ) {
+        if (STAGEQ) {
+            if (qt != q_begin) __syncthreads();  // the previous tile has been read by everybody
+            const int nfl = (min(q_end, qt + TQ) - qt) * 3;
+            const float *src = p1 + (size_t)qt * 3;
+#pragma unroll 8
+            for (int f = threadIdx.x; f < TQ * 3; f += THREADS)
+                sQ[f + f / (3 * Q)] = f < nfl ? __ldg(src + f) : PP_INF;  // padding: +inf like below
+            __syncthreads();
+        }
         // thread owns Q consecutive queries; a warp whose queries are all padding sits out
         const int q0 = qt + threadIdx.x * Q;
         // (the shuffle tells the compiler the test is warp-uniform, so the sweep below keeps
@@ -136,7 +151,11 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
             const int i = q0 + q;
             float x = PP_INF, y = PP_INF, z = PP_INF;
             if (LABELED) ql[q] = __int_as_float(0x7fc00000);
-            if (i < q_end) {
+            if (STAGEQ) {
+                const float *mine = sQ + threadIdx.x * (3 * Q + 1) + 3 * q;
+                x = mine[0]; y = mine[1]; z = mine[2];
+                if (LABELED && i < q_end) ql[q] = __ldg(label1 + (size_t)b * N + i);
+            } else if (i < q_end) {
                 x = __ldg(p1 + (size_t)i * 3 + 0);
                 y = __ldg(p1 + (size_t)i * 3 + 1);
                 z = __ldg(p1 + (size_t)i * 3 + 2);
@@ -548,7 +567,7 @@ extern "C" size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M) {
     return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M);
 }
 
-template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true, bool LABELED = false>
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true, bool LABELED = false, bool STAGEQ = false>
 static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                               unsigned long long *key1, unsigned long long *key2, float *dist1,
                               float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st,
@@ -569,7 +588,7 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     dim3 grid(ref_blocks, B, splits);
     {
         KernelTimer timer("chamfer_fwd", st);
-        chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, LABELED><<<grid, THREADS, 0, st>>>(
+        chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, LABELED, STAGEQ><<<grid, THREADS, 0, st>>>(
             xyz1, xyz2, N, M, key1, key2, queries_per_split, label1, label2, g1, g2);
     }
     PP_LAUNCH_CHECK();
@@ -656,7 +675,14 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     // workspace say so with PP_CHAMFER_WS_CLEAN and save the fill.
     if (!(flags & PP_CHAMFER_WS_CLEAN)) PP_CUDA(cudaMemsetAsync(workspace, 0xff, need, st));
     int pick = get_option("chamfer_variant", 0);
-    if (pick == 0) pick = (M <= 4096) ? 2 : 1;  // smaller reference blocks keep small clouds spread over all SMs
+    if (pick == 0) {
+        // Smaller reference blocks keep small clouds spread over all SMs.  A warp takes 32*Q = 256
+        // queries: when 4-warp CTAs would leave two or more warp slots of the last query split
+        // without work (N = 2500: 10 warps in 3 CTAs), 2-warp CTAs waste none.
+        const int warps = ceil_div(N, 256);
+        const bool narrow = ceil_div(warps, 2) * 2 < ceil_div(warps, 4) * 4;
+        pick = (M <= 4096) ? (narrow ? 25 : 22) : 21;
+    }
     switch (pick) {
         case 1: return launch_chamfer_fwd<8, 128, 256, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 2: return launch_chamfer_fwd<8, 128, 128, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
@@ -664,6 +690,9 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
         case 4: return launch_chamfer_fwd<8, 128, 64, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 5: return launch_chamfer_fwd<8, 64, 128, 10>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 6: return launch_chamfer_fwd<8, 128, 160, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 21: return launch_chamfer_fwd<8, 128, 256, 5, true, false, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 22: return launch_chamfer_fwd<8, 128, 128, 5, true, false, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 25: return launch_chamfer_fwd<8, 64, 128, 10, true, false, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 13: return launch_chamfer_fwd<8, 128, 256, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 14: return launch_chamfer_fwd<8, 128, 128, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         default: break;

@@ -1,19 +1,23 @@
 #!/bin/bash
-# Round-end check on the GPU box: KNN captures, full GPU test-suite, smoke, default bench.
+# Round-end check on the GPU box: Chamfer captures (default variants, fused finalize), launch list
+# of the default bench, full GPU test-suite, smoke, default bench.
 mkdir -p gpurun_out
 NCU="ncu --set full --import-source on --clock-control none -f"
-timeout 300 $NCU -k regex:knn_sweep -c 1 -s 1 -o gpurun_out/prof_knn8k python tools/prof_all.py knn 32 8192 > gpurun_out/cap.log 2>&1
-timeout 300 $NCU -k regex:knn_sweep -c 1 -s 1 -o gpurun_out/prof_knn131k python tools/prof_all.py knn 4 131072 >> gpurun_out/cap.log 2>&1
-timeout 300 $NCU -k regex:km_prepare_small -c 1 -s 1 -o gpurun_out/prof_knnprep8k python tools/prof_all.py knn 32 8192 >> gpurun_out/cap.log 2>&1
+timeout 200 $NCU -k regex:chamfer_fwd_kernel -c 1 -s 2 -o gpurun_out/prof_ch2500 python tools/prof_chamfer.py 32 2500 0 24 fused > gpurun_out/cap.log 2>&1
+timeout 200 $NCU -k regex:chamfer_finalize -c 1 -s 2 -o gpurun_out/prof_finfused2500 python tools/prof_chamfer.py 32 2500 0 24 fused >> gpurun_out/cap.log 2>&1
+timeout 200 $NCU -k regex:chamfer_fwd_kernel -c 1 -s 2 -o gpurun_out/prof_ch8192 python tools/prof_chamfer.py 32 8192 0 24 fused >> gpurun_out/cap.log 2>&1
 grep -c "==PROF== Report" gpurun_out/cap.log
-timeout 400 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_default.csv \
+    python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+timeout 400 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
 timeout 100 python __graft_entry__.py smoke 2>&1 | tail -1
 timeout 400 python bench.py > gpurun_out/bench_r01_n1.json 2> gpurun_out/bench_err.log
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/bench_r01_n1.json").read().strip().splitlines()[-1])
-print("value", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "roofline", d["roofline"]["frac"])
+print("value", d["value"], d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "roofline", d["roofline"]["frac"], d["roofline"]["kernel_ms"])
+print("fused", d["fused_step"])
 x = d["extras"]
-for k in ("knn_k16_B32_N8192", "knn_k16_B4_N131072", "fps_B16_N16384_m1024"):
+for k in ("chamfer_fwd_bwd_B32_N8192", "knn_k16_B32_N8192", "knn_k16_B4_N131072", "fps_B16_N16384_m1024"):
     print(k, x[k]["ms_per_step"])
 PY
