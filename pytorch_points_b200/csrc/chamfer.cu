@@ -56,6 +56,25 @@ __device__ __forceinline__ void publish_column_min(int lane, int leader, unsigne
         : "memory");
 }
 
+// Election-free form: EVERY lane whose column minimum equals the warp minimum publishes its own
+// (value, group) key.  Exact for the same reason the election was: RED.MIN on the packed key
+// keeps the lowest group among equal values.  Saves the ballot / find-first / lane compare of
+// the elected form; ties (more than one publishing lane) are rare.
+__device__ __forceinline__ void publish_column_min_all(unsigned mine, unsigned mn, unsigned long long *gkey,
+                                                       unsigned long long key, unsigned *filt) {
+    const unsigned faddr = (unsigned)__cvta_generic_to_shared(filt);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.eq.u32 p, %0, %1;\n\t"
+        "@p red.global.min.u64 [%2], %3;\n\t"
+        "@p st.shared.u32 [%4], %1;\n\t"
+        "}"
+        :
+        : "r"(mine), "r"(mn), "l"(gkey), "l"(key), "r"(faddr)
+        : "memory");
+}
+
 // LABELED (LabeledNmdistanceFunction, _ext/nmdistance_cuda.cu:56-115): only pairs with equal fp32
 // labels are candidates -- every other distance is replaced by +inf right after it is computed,
 // so both minima see same-label partners only; a point without a partner keeps +inf and the
@@ -65,7 +84,7 @@ __device__ __forceinline__ void publish_column_min(int lane, int leader, unsigne
 // tile: ~1200 cycles of the SM's single L1 wavefront queue, which the other warps' LDS.128 of the
 // hot loop wait behind).  Staged, the CTA reads its tile as whole lines into shared memory (one
 // pad word per 24 so that the per-thread readback at stride 25 words is conflict free).
-template <int Q, int THREADS, int RB, int MINB, bool ROTATE, bool LABELED, bool STAGEQ = false>
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE, bool LABELED, bool STAGEQ = false, bool ELECT = true>
 __global__ void __launch_bounds__(THREADS, MINB)
 chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int N, int M,
                    unsigned long long *__restrict__ key1, unsigned long long *__restrict__ key2,
@@ -131,7 +150,7 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
             if (qt != q_begin) __syncthreads();  // the previous tile has been read by everybody
             const int nfl = (min(q_end, qt + TQ) - qt) * 3;
             const float *src = p1 + (size_t)qt * 3;
-#pragma unroll 8
+#pragma unroll  // 3*Q = 24 independent loads in flight: one memory round trip per tile
             for (int f = threadIdx.x; f < TQ * 3; f += THREADS)
                 sQ[f + f / (3 * Q)] = f < nfl ? __ldg(src + f) : PP_INF;  // padding: +inf like below
             __syncthreads();
@@ -247,11 +266,17 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
                     if (__any_sync(FULL_MASK, pp_[r])) {
                         const unsigned mine = __float_as_uint(cc[r]);
                         const unsigned mn = __reduce_min_sync(FULL_MASK, mine);
-                        // lowest lane holding the minimum == lowest query group in this warp
-                        const unsigned hit = __ballot_sync(FULL_MASK, mine == mn);
-                        publish_column_min(lane, __ffs(hit) - 1, k2 + ref_begin + jj + r,
-                                           ((unsigned long long)mn << 32) | (unsigned)group,
-                                           sW + jj + r, mn);
+                        if (ELECT) {
+                            // lowest lane holding the minimum == lowest query group in this warp
+                            const unsigned hit = __ballot_sync(FULL_MASK, mine == mn);
+                            publish_column_min(lane, __ffs(hit) - 1, k2 + ref_begin + jj + r,
+                                               ((unsigned long long)mn << 32) | (unsigned)group,
+                                               sW + jj + r, mn);
+                        } else {
+                            publish_column_min_all(mine, mn, k2 + ref_begin + jj + r,
+                                                   ((unsigned long long)mn << 32) | (unsigned)group,
+                                                   sW + jj + r);
+                        }
                     }
                 }
             }
@@ -567,7 +592,8 @@ extern "C" size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M) {
     return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M);
 }
 
-template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true, bool LABELED = false, bool STAGEQ = false>
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true, bool LABELED = false, bool STAGEQ = false,
+          bool ELECT = true>
 static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                               unsigned long long *key1, unsigned long long *key2, float *dist1,
                               float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st,
@@ -588,7 +614,7 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     dim3 grid(ref_blocks, B, splits);
     {
         KernelTimer timer("chamfer_fwd", st);
-        chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, LABELED, STAGEQ><<<grid, THREADS, 0, st>>>(
+        chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, LABELED, STAGEQ, ELECT><<<grid, THREADS, 0, st>>>(
             xyz1, xyz2, N, M, key1, key2, queries_per_split, label1, label2, g1, g2);
     }
     PP_LAUNCH_CHECK();
@@ -682,6 +708,7 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
         const int warps = ceil_div(N, 256);
         const bool narrow = ceil_div(warps, 2) * 2 < ceil_div(warps, 4) * 4;
         pick = (M <= 4096) ? (narrow ? 25 : 22) : 21;
+        if (get_option("chamfer_noelect", 1)) pick += 10;  // election-free column publish
     }
     switch (pick) {
         case 1: return launch_chamfer_fwd<8, 128, 256, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
@@ -693,6 +720,9 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
         case 21: return launch_chamfer_fwd<8, 128, 256, 5, true, false, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 22: return launch_chamfer_fwd<8, 128, 128, 5, true, false, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 25: return launch_chamfer_fwd<8, 64, 128, 10, true, false, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 31: return launch_chamfer_fwd<8, 128, 256, 5, true, false, true, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 32: return launch_chamfer_fwd<8, 128, 128, 5, true, false, true, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
+        case 35: return launch_chamfer_fwd<8, 64, 128, 10, true, false, true, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 13: return launch_chamfer_fwd<8, 128, 256, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 14: return launch_chamfer_fwd<8, 128, 128, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         default: break;
