@@ -285,8 +285,8 @@ int pp_knn_stats(double *tiles_visited, double *tiles_total);
  *   "timing" (0)                 per-kernel CUDA events, see pp_timing_collect
  *   "pdl" (1)                    programmatic dependent launch of the short follow-up kernels
  *   "chamfer_variant" (0)        0 = automatic (31 / 32 / 35 by cloud size); 1 / 2 = 256- /
- *                                128-point reference blocks; 3 / 4 / 6 = 96- / 64- / 160-point
- *                                blocks; 5 = 64-thread CTAs; 21 / 22 / 25 = 1 / 2 / 5 with the
+ *                                128-point reference blocks, 128-thread CTAs; 5 = 128-point
+ *                                blocks, 64-thread CTAs; 21 / 22 / 25 = 1 / 2 / 5 with the
  *                                query tile staged through shared memory; 31 / 32 / 35 = those
  *                                with the election-free column publish; 13 / 14 = 1 / 2
  *                                without the per-warp sweep rotation

@@ -65,7 +65,7 @@ def test_chamfer_forward_bit_exact(pp, oracle_mod, B, N, M, maker, seed):
     assert np.array_equal(np32(d2).view(np.uint32), e2.view(np.uint32)), "dist2 bits"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 13, 14, 21, 22, 25, 31, 32, 35])
+@pytest.mark.parametrize("variant", [1, 2, 5, 13, 14, 21, 22, 25, 31, 32, 35])
 def test_chamfer_forward_all_variants(pp, oracle_mod, variant):
     from pytorch_points_b200 import _C
     a = with_duplicates(uniform_cloud(2, 1500, 11))
