@@ -43,6 +43,15 @@ def test_argument_errors_without_gpu():
     rc = _C.lib.pp_fps(None, 1, 0, 4, 0, None, None, 0, None)
     assert rc == -22
     assert _C.lib.pp_chamfer_fwd_workspace_bytes(2, 10, 20) == 8 * (2 * 10 + 2 * 20)
+    # fused forward + backward: weight vector and gradient pointers are checked up front
+    rc = _C.lib.pp_chamfer_fwd_bwd_uniform(None, None, None, 1, 4, 4, None, None, None, None, None, None, None,
+                                           None, 0, 0, 0, None)
+    assert rc == -22 and b"weight" in _C.lib.pp_last_error_string()
+    rc = _C.lib.pp_chamfer_fwd_bwd_uniform(None, None, None, 0, 4, 4, None, None, None, None, None, None, None,
+                                           None, 0, 0, 0, None)
+    assert rc == 0  # empty batch: nothing to do
+    rc = _C.lib.pp_chamfer_labeled_fwd(None, None, None, None, 1, 4, 4, 0, None, None, None, None, None, 0, 0, 0, None)
+    assert rc == -22
 
 
 def test_ops_refuse_cpu_tensors():
@@ -55,3 +64,11 @@ def test_ops_refuse_cpu_tensors():
         network.ball_query(0.1, 4, torch.rand(1, 8, 3), torch.rand(1, 2, 3))
     with pytest.raises(RuntimeError):
         network.furthest_point_sample(torch.rand(1, 8, 3), 2, NCHW=False)
+    with pytest.raises(RuntimeError):
+        network.labeled_nndistance(torch.rand(1, 4, 3), torch.rand(1, 4, 3), torch.zeros(1, 4, 1), torch.zeros(1, 4, 1))
+    from pytorch_points_b200._ext import losses
+    a = torch.rand(1, 4, 3)
+    with pytest.raises(RuntimeError):
+        losses.nmdistance_forward_backward_uniform(a, a, torch.empty(1, 4), torch.empty(1, 4),
+                                                   torch.empty(1, 4, dtype=torch.int32), torch.empty(1, 4, dtype=torch.int32),
+                                                   None, torch.ones(2), torch.empty_like(a), torch.empty_like(a))
