@@ -9,5 +9,5 @@ from .operations import (GatherFunction, gather_points, BallQuery, ball_query, G
                          grouping_operation, QueryAndGroup, QueryAndGroupFunction, query_and_group, group_knn,
                          knn_points)
 from .pointnet2_utils import ThreeNN, three_nn, ThreeInterpolate, three_interpolate, GroupAll  # noqa: F401
-from .layers import Conv2d, SharedMLP, DenseEdgeConv  # noqa: F401
+from .layers import Conv2d, SharedMLP, DenseEdgeConv, SampledDenseEdgeConv  # noqa: F401
 from .pointnet2_modules import PointnetSAModule, PointnetSAModuleMSG, PointnetFPModule  # noqa: F401

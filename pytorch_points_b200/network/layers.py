@@ -1,4 +1,5 @@
-"""The two layer wrappers the set-abstraction / feature-propagation modules need.
+"""The layer wrappers the set-abstraction / feature-propagation modules need, and the two
+edge-convolution layers that call the KNN / FPS / gather operators.
 
 `Conv2d` and `SharedMLP` mirror `pytorch_points.network.layers.Conv2d` / `SharedMLP`
 (network/layers.py:9-21,136-183): same constructor arguments, same sub-module names
@@ -103,3 +104,62 @@ class DenseEdgeConv(nn.Module):
                 y = torch.cat([nn.functional.relu_(mlp(y)), y], dim=1)
         y, _ = torch.max(y, dim=-1)
         return y, idx
+
+
+class SampledDenseEdgeConv(DenseEdgeConv):
+    """`DenseEdgeConv` evaluated at `nsample` farthest-point-sampled centres only (reference
+    network/layers.py:85-133): FPS on the coordinates -> gather the centres' features -> k nearest
+    FEATURE neighbours of each centre among all N points -> the dense edge MLP -> max over k.
+    A caller of three hot-path operators (`furthest_point_sample`, `gather_points`, KNN).
+
+    The snapshot's `get_local_graph` unpacks `knn_points(..., return_nn=True)` into two names
+    (layers.py:99), which raises for the three-tuple the call returns; this mirror implements what
+    the surrounding code evidently intends (idx and neighbours, the nearest entry -- the centre
+    itself -- dropped)."""
+
+    def get_local_graph(self, query, x, k, idx=None):
+        """query (B, C, S) centres, x (B, C, N) all points -> edge features [q_i, x_j - q_i]
+        (B, 2C, S, k) over the k nearest neighbours j of centre i in feature space (the nearest
+        one, i itself, excluded) and their indices (B, S, k)."""
+        import torch
+        from . import operations as ops
+        pts = x.transpose(1, 2).contiguous()  # (B, N, C)
+        if idx is None:
+            _, idx, nn_pts = ops.knn_points(query.transpose(1, 2).contiguous(), pts, K=k + 1, return_nn=True)
+            idx, nn_pts = idx[:, :, 1:], nn_pts[:, :, 1:, :]
+        else:
+            B, N, C = pts.shape
+            S = query.shape[2]
+            nn_pts = torch.gather(pts.unsqueeze(1).expand(B, S, N, C), 2,
+                                  idx.long().unsqueeze(-1).expand(B, S, idx.shape[2], C))
+        neighbours = nn_pts.permute(0, 3, 1, 2)  # (B, C, S, k)
+        centre = query.unsqueeze(-1).expand_as(neighbours)
+        return torch.cat([centre, neighbours - centre], dim=1), idx
+
+    def forward(self, x, nsample, xyz):
+        """x (B, C, N) features, xyz (B, 3, N) coordinates ->
+        (features (B, C', nsample), sampled_xyz (B, 3, nsample), sampled_idx (B, nsample))."""
+        import torch
+        from . import geo_operations as geo
+        from . import operations as ops
+        if nsample == 1:
+            # one centre: the point nearest to the centroid
+            centroid = torch.mean(xyz, dim=-1, keepdim=True)  # (B, 3, 1)
+            _, sampled_idx, sampled_xyz = ops.knn_points(centroid.transpose(1, 2).contiguous(),
+                                                         xyz.transpose(1, 2).contiguous(), K=1, return_nn=True)
+            sampled_xyz = sampled_xyz.squeeze(2).transpose(1, 2).contiguous()  # (B, 1, 1, 3) -> (B, 3, 1)
+            sampled_idx = sampled_idx.squeeze(2).int()                          # (B, 1, 1) -> (B, 1)
+        else:
+            sampled_idx, sampled_xyz = geo.furthest_point_sample(xyz, nsample, NCHW=True)
+        sampled_x = ops.gather_points(x.contiguous(), sampled_idx)  # (B, C, nsample)
+        for i, mlp in enumerate(self.mlps):
+            if i == 0:
+                y, _ = self.get_local_graph(sampled_x, x, k=self.k)
+                centre = sampled_x.unsqueeze(-1).expand(-1, -1, -1, self.k)
+                y = torch.cat([nn.functional.relu_(mlp(y)), centre], dim=1)
+            elif i == (self.n - 1):
+                y = torch.cat([mlp(y), y], dim=1)
+            else:
+                y = torch.cat([nn.functional.relu_(mlp(y)), y], dim=1)
+        y, _ = torch.max(y, dim=-1)
+        return y, sampled_xyz, sampled_idx
