@@ -59,7 +59,7 @@ PP_CHAMFER_WS_CLEAN = 1
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "pytorch_points_b200: %s is missing. Build it with `python -m pytorch_points_b200._build` "
+            "pytorch_points_b200: %s is missing. Build it with `python pytorch_points_b200/_build.py` "
             "(or __graft_entry__.build()); there is no CPU or PyTorch fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
