@@ -6,7 +6,11 @@
 Default workload = BASELINE.json configs[1]: Chamfer distance fwd+bwd, B=32 clouds per GPU,
 N=M=2500 points (AtlasNet training shape), metric = unique point-pairs/s (B*N*M per step,
 whole job).  One "step" = nndistance forward (both directions + fused loss partial sums),
-the NCCL all-reduce of the two partial sums when N>1, and the backward scatter.
+the backward scatter for loss = mean(dist1) + mean(dist2), and, when N>1, the exchange of the
+two partial sums (peer-memory mailboxes; NCCL all-reduce with PP_LOSS_EXCHANGE=nccl).  Default:
+the two-launch form pp_chamfer_fwd_bwd_uniform (backward folded into the index-resolving
+kernel), checked against the four-launch sequence on the timed input first and timed next to
+it (`fused_step` in the line); PP_FUSED_BWD=0 times the four-launch sequence only.
 
 Legs printed in ONE JSON line by rank 0:
   value     device-resident: inputs already in HBM, C-ABI calls on the current stream;
