@@ -471,7 +471,6 @@ chamfer_finalize_kernel(const float *__restrict__ xyz1, const float *__restrict_
 // Secondary path: simple thread-per-query tiling, not the roofline kernel.
 // ---------------------------------------------------------------------------
 constexpr int GEN_CHUNK = 512;
-constexpr int GEN_MAXC = 8;  // chunk staged in shared memory for c <= 8
 
 template <bool LABELED>
 __global__ void __launch_bounds__(256)
