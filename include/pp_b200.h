@@ -284,13 +284,13 @@ int pp_knn_stats(double *tiles_visited, double *tiles_total);
  * Process-wide integer options (diagnostics and A/B switches; results never depend on them):
  *   "timing" (0)                 per-kernel CUDA events, see pp_timing_collect
  *   "pdl" (1)                    programmatic dependent launch of the short follow-up kernels
- *   "chamfer_variant" (0)        0 = automatic (31 / 32 / 35 by cloud size); 1 / 2 = 256- /
+ *   "chamfer_variant" (0)        0 = automatic (1 above 4096 points, else 32 / 35); 1 / 2 = 256- /
  *                                128-point reference blocks, 128-thread CTAs; 5 = 128-point
  *                                blocks, 64-thread CTAs; 21 / 22 / 25 = 1 / 2 / 5 with the
  *                                query tile staged through shared memory; 31 / 32 / 35 = those
  *                                with the election-free column publish; 13 / 14 = 1 / 2
  *                                without the per-warp sweep rotation
- *   "chamfer_noelect" (1)        automatic choice uses 31 / 32 / 35 (1) or 21 / 22 / 25 (0)
+ *   "chamfer_noelect" (1)        automatic choice below 4097 points uses 32 / 35 (1) or 22 / 25 (0)
  *   "chamfer_blocks_per_sm" (24) target CTA count per SM for the query split heuristic
  *   "chamfer_generic" (0)        force the generic (any point dimension) kernel
  *   "fps_cluster" (0)            0 = automatic, else the cluster width 1 / 2 / 4 / 8

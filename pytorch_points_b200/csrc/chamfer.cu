@@ -706,8 +706,10 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
         // without work (N = 2500: 10 warps in 3 CTAs), 2-warp CTAs waste none.
         const int warps = ceil_div(N, 256);
         const bool narrow = ceil_div(warps, 2) * 2 < ceil_div(warps, 4) * 4;
-        pick = (M <= 4096) ? (narrow ? 25 : 22) : 21;
-        if (get_option("chamfer_noelect", 1)) pick += 10;  // election-free column publish
+        // Large clouds keep the direct query loads: staging gains 0.5 % there with a warm L2 and
+        // loses 2-6 % when the clouds come from DRAM (a CTA-wide barrier behind the loads).
+        pick = (M <= 4096) ? (narrow ? 25 : 22) : 1;
+        if (pick != 1 && get_option("chamfer_noelect", 1)) pick += 10;  // election-free column publish
     }
     switch (pick) {
         case 1: return launch_chamfer_fwd<8, 128, 256, 5>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
