@@ -40,7 +40,8 @@ const char *pp_last_error_string(void);
 
 /* ------------------------------------------------------------------ losses */
 
-/* Scratch bytes pp_chamfer_fwd needs for (B,N,M). */
+/* Scratch bytes pp_chamfer_fwd needs for (B,N,M): 8 per point of either cloud (packed keys) plus
+ * 4 per (cloud, 256-query tile) and (cloud, 128-point reference block) of completion counters. */
 size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M);
 
 /*
@@ -289,7 +290,9 @@ int pp_knn_stats(double *tiles_visited, double *tiles_total);
  *                                blocks, 64-thread CTAs; 21 / 22 / 25 = 1 / 2 / 5 with the
  *                                query tile staged through shared memory; 31 / 32 / 35 = those
  *                                with the election-free column publish; 13 / 14 = 1 / 2
- *                                without the per-warp sweep rotation
+ *                                without the per-warp sweep rotation; 41 / 42 / 45 =
+ *                                EXPERIMENTAL (not yet validated on a GPU): 1 / 32 / 35 with the
+ *                                index resolution folded into the forward kernel
  *   "chamfer_noelect" (1)        automatic choice below 4097 points uses 32 / 35 (1) or 22 / 25 (0)
  *   "chamfer_blocks_per_sm" (24) target CTA count per SM for the query split heuristic
  *   "chamfer_generic" (0)        force the generic (any point dimension) kernel

@@ -3,6 +3,8 @@ through the C ABI) against the CPU oracle on identical seeded inputs.
 
 Bar (BASELINE.json north_star): indices bit-exact, distances bit-exact (same rounding order),
 gradients within 1e-5 relative error (atomic summation order differs, as in the reference)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -65,7 +67,12 @@ def test_chamfer_forward_bit_exact(pp, oracle_mod, B, N, M, maker, seed):
     assert np.array_equal(np32(d2).view(np.uint32), e2.view(np.uint32)), "dist2 bits"
 
 
-@pytest.mark.parametrize("variant", [1, 2, 5, 13, 14, 21, 22, 25, 31, 32, 35])
+# 41 / 42 / 45 (finalize folded into the forward kernel) are experimental and not yet run on a GPU:
+# PP_EXPERIMENTAL=1 adds them
+_VARIANTS = [1, 2, 5, 13, 14, 21, 22, 25, 31, 32, 35] + ([41, 42, 45] if os.environ.get("PP_EXPERIMENTAL") else [])
+
+
+@pytest.mark.parametrize("variant", _VARIANTS)
 def test_chamfer_forward_all_variants(pp, oracle_mod, variant):
     from pytorch_points_b200 import _C
     a = with_duplicates(uniform_cloud(2, 1500, 11))
