@@ -126,7 +126,9 @@ __device__ void fold_rows(const float *__restrict__ xyz1, const float *__restric
         }
         int found = g * CH_GR;
         const int nrow = min(32, row_end - base);
-#pragma unroll 4
+        // the resolving warp holds its CTA slot: keep many candidate loads in flight (the hot
+        // loop's registers are dead here)
+#pragma unroll 8
         for (int s = 0; s < nrow; s++) {
             const unsigned w_s = __shfl_sync(FULL_MASK, want, s);
             const int g_s = __shfl_sync(FULL_MASK, g, s);
