@@ -932,6 +932,35 @@ def _brute_knn(points, k):
     return d.topk(k + 1, dim=-1, largest=False).indices[:, :, 1:]
 
 
+@pytest.mark.skipif(not os.environ.get("PP_EXPERIMENTAL"), reason="written without GPU time left; PP_EXPERIMENTAL=1 runs it")
+@pytest.mark.parametrize("nsample", [64, 1])
+def test_sampled_dense_edge_conv_on_device(pp, oracle_mod, nsample):
+    """SampledDenseEdgeConv (network/layers.py:85-133) on the real operators: centres = FPS order of
+    the oracle (or the point nearest the centroid), their features gathered, neighbours = brute-force
+    k nearest in feature space with the centre itself dropped."""
+    torch.manual_seed(4)
+    B, C, N, k = 2, 3, 1500, 6
+    xyz_c = uniform_cloud(B, N, 811)
+    xyz = dev(xyz_c).transpose(1, 2).contiguous()
+    x = xyz.clone().requires_grad_(True)  # features = coordinates: distinct points, no feature ties
+    conv = pp.SampledDenseEdgeConv(C, 10, n=3, k=k).cuda()
+    y, sxyz, sidx = conv(x, nsample, xyz)
+    assert y.shape == (B, conv.out_channels, nsample) and sxyz.shape == (B, 3, nsample) and sidx.shape == (B, nsample)
+    if nsample == 1:
+        want = ((xyz - xyz.mean(-1, keepdim=True)) ** 2).sum(1).argmin(-1, keepdim=True)
+    else:
+        want = dev(torch.from_numpy(oracle_mod.fps(np32(xyz_c), nsample).astype(np.int64)))
+    assert torch.equal(sidx.long(), want)
+    assert torch.equal(sxyz, torch.gather(xyz, 2, want.unsqueeze(1).expand(B, 3, nsample)))
+    centres = torch.gather(x.detach(), 2, want.unsqueeze(1).expand(B, C, nsample))
+    edge, eidx = conv.get_local_graph(centres, x.detach(), k)
+    d = torch.cdist(centres.transpose(1, 2).double(), x.detach().transpose(1, 2).double())
+    assert torch.equal(eidx, d.topk(k + 1, dim=-1, largest=False).indices[:, :, 1:])
+    assert edge.shape == (B, 2 * C, nsample, k)
+    y.square().mean().backward()
+    assert torch.isfinite(x.grad).all() and x.grad.abs().sum() > 0
+
+
 def test_knn_callers_laplacian_edgeconv_and_losses(pp):
     """the snapshot's pytorch3d.knn_points callers on this repo's KNN --
     DenseEdgeConv.get_local_graph (layers.py:41-62), pointUniformLaplacian / batch_normals
