@@ -9,21 +9,29 @@ import torch
 
 from .. import _C
 
-_workspaces = {}
+_workspaces = {}   # (device index, stream handle) -> current scratch tensor
+_retired = []      # outgrown scratch tensors: kept alive, a CUDA graph may have baked their address in
 
 
 def _workspace(device, nbytes):
-    """Persistent per-(device, stream) scratch for the packed (distance, granule) keys of the
-    one-pass Chamfer kernel.  It is filled with 0xff once; every successful forward call leaves
-    it in that state again (the finalize kernel resets the keys it consumed), so steady-state
-    calls pass PP_CHAMFER_WS_CLEAN and skip the fill.  Stream-ordered reuse: calls on one stream
-    never overlap."""
+    """Scratch for the Chamfer forward (prepared clouds, packed keys, candidate lists).  The library
+    initialises what it reads, so the buffer carries no state between calls (flags = 0).
+    One buffer per (device, stream): calls on one stream never overlap.  A buffer that has been
+    handed out is never freed -- when a larger shape arrives the old tensor moves to `_retired`, so a
+    CUDA graph captured around an earlier call keeps a valid address.  While the current stream is
+    being captured the call gets a fresh tensor of its own from the graph's private pool: replays of
+    different graphs (or a replay racing an eager call) then never share scratch."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=device)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.full((max(nbytes, 1 << 20),), 0xFF, dtype=torch.uint8, device=device)
+        if buf is not None:
+            _retired.append(buf)
+        grow = nbytes if buf is None else max(nbytes, buf.numel() * 3 // 2)
+        buf = torch.empty((max(grow, 1 << 20),), dtype=torch.uint8, device=device)
         _workspaces[key] = buf
-    return key, buf
+    return buf
 
 
 def _check_f32(*ts):
@@ -45,13 +53,17 @@ def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None):
         raise RuntimeError("nmdistance_forward: xyz1 %s and xyz2 %s disagree" % (tuple(xyz1.shape), tuple(xyz2.shape)))
     if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
         raise RuntimeError("nmdistance_forward: idx tensors must be int32")
+    if dist1.numel() != B * N or idx1.numel() != B * N or dist2.numel() != B * M or idx2.numel() != B * M:
+        raise RuntimeError("nmdistance_forward: outputs must be (B,N) / (B,M)")
+    if sums is not None:
+        _C.require_cuda(xyz1, sums)
+        if sums.dtype != torch.float32 or sums.numel() != 2 or not sums.is_contiguous():
+            raise RuntimeError("nmdistance_forward: sums must be 2 contiguous float32 values")
     nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
-    key, ws = _workspace(dev, nbytes)
+    ws = _workspace(dev, nbytes)
     rc = _C.lib.pp_chamfer_fwd(_C.ptr(xyz1), _C.ptr(xyz2), B, N, M, c, _C.ptr(dist1), _C.ptr(dist2),
                                _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums), _C.ptr(ws), ws.numel(),
-                               _C.PP_CHAMFER_WS_CLEAN, dev.index, _C.stream_of(dev))
-    if rc != 0:
-        _workspaces.pop(key, None)  # state unknown after a failure: start from a fresh fill
+                               0, dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_fwd")
     return 1
 
@@ -67,13 +79,15 @@ def labeled_nmdistance_forward(xyz1, xyz2, label1, label2, dist1, dist2, idx1, i
     M = xyz2.shape[1]
     if label1.numel() != B * N or label2.numel() != B * M:
         raise RuntimeError("labeled_nmdistance_forward: labels must be (B,N[,1]) and (B,M[,1])")
+    if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
+        raise RuntimeError("labeled_nmdistance_forward: idx tensors must be int32")
+    if dist1.numel() != B * N or idx1.numel() != B * N or dist2.numel() != B * M or idx2.numel() != B * M:
+        raise RuntimeError("labeled_nmdistance_forward: outputs must be (B,N) / (B,M)")
     nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
-    key, ws = _workspace(dev, nbytes)
+    ws = _workspace(dev, nbytes)
     rc = _C.lib.pp_chamfer_labeled_fwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(label1), _C.ptr(label2), B, N, M, c,
                                        _C.ptr(dist1), _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2),
-                                       _C.ptr(ws), ws.numel(), _C.PP_CHAMFER_WS_CLEAN, dev.index, _C.stream_of(dev))
-    if rc != 0:
-        _workspaces.pop(key, None)
+                                       _C.ptr(ws), ws.numel(), 0, dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_labeled_fwd")
     return 1
 
@@ -85,6 +99,11 @@ def nmdistance_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, id
     _check_f32(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2)
     B, N, c = xyz1.shape
     M = xyz2.shape[1]
+    if idx1.dtype != torch.int32 or idx2.dtype != torch.int32:
+        raise RuntimeError("nmdistance_backward: idx tensors must be int32")
+    if gradxyz1.shape != xyz1.shape or gradxyz2.shape != xyz2.shape or graddist1.numel() != B * N \
+            or graddist2.numel() != B * M or idx1.numel() != B * N or idx2.numel() != B * M:
+        raise RuntimeError("nmdistance_backward: shapes disagree")
     rc = _C.lib.pp_chamfer_bwd(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(graddist1), _C.ptr(graddist2),
                                _C.ptr(idx1), _C.ptr(idx2), B, N, M, c, _C.ptr(gradxyz1), _C.ptr(gradxyz2),
                                dev.index, _C.stream_of(dev))
@@ -127,12 +146,10 @@ def nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, su
     if gw.numel() != 2 or gradxyz1.shape != xyz1.shape or gradxyz2.shape != xyz2.shape:
         raise RuntimeError("nmdistance_forward_backward_uniform: gw must hold 2 floats, gradients match the clouds")
     nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
-    key, ws = _workspace(dev, nbytes)
+    ws = _workspace(dev, nbytes)
     rc = _C.lib.pp_chamfer_fwd_bwd_uniform(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(gw), B, N, M, _C.ptr(dist1),
                                            _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums),
                                            _C.ptr(gradxyz1), _C.ptr(gradxyz2), _C.ptr(ws), ws.numel(),
-                                           _C.PP_CHAMFER_WS_CLEAN, dev.index, _C.stream_of(dev))
-    if rc != 0:
-        _workspaces.pop(key, None)
+                                           0, dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_fwd_bwd_uniform")
     return 1

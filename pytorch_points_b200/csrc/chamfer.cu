@@ -79,140 +79,18 @@ __device__ __forceinline__ void publish_column_min_all(unsigned mine, unsigned m
 // labels are candidates -- every other distance is replaced by +inf right after it is computed,
 // so both minima see same-label partners only; a point without a partner keeps +inf and the
 // finalize kernel turns that into the reference's (dist 0, idx -1).
-// ---------------------------------------------------------------------------------------------
-// FOLD (experimental, chamfer_variant 41 / 42 / 45): no finalize kernel.  The forward kernel
-// resolves the keys itself as soon as they are complete:
-//   rows    -- the 256 queries of a warp tile have met every reference block of their cloud when
-//              the gridDim.x warps (one per reference-block CTA) that own that tile have published;
-//              the last of them (fence + counter) resolves the 256 rows;
-//   columns -- the RB references of a block are complete when the gridDim.z query-split CTAs of
-//              that block are done; the last of them resolves the RB columns.
-// The work is spread over the grid and overlaps the sweeps of the other CTAs instead of waiting
-// for the grid to drain.  Counters live behind the keys in the workspace, start at 0xffffffff
-// (the workspace's clean state) and are put back by the resolving warp / CTA.
-template <bool FUSE_BWD>
-__device__ __forceinline__ void fold_bwd_term(float gg, float px, float py, float pz, const float *__restrict__ nbr,
-                                              float *own, float *oth) {
-    if (!FUSE_BWD) return;
-    const float vx = __fmul_rn(gg, __fsub_rn(px, __ldg(nbr + 0)));
-    const float vy = __fmul_rn(gg, __fsub_rn(py, __ldg(nbr + 1)));
-    const float vz = __fmul_rn(gg, __fsub_rn(pz, __ldg(nbr + 2)));
-    atomicAdd(own + 0, vx); atomicAdd(own + 1, vy); atomicAdd(own + 2, vz);
-    atomicAdd(oth + 0, -vx); atomicAdd(oth + 1, -vy); atomicAdd(oth + 2, -vz);
-}
-
-// one warp resolves rows [row0, row_end) (at most 256) of cloud b; same candidate test as
-// chamfer_finalize_kernel's row side
-template <bool FUSE_BWD>
-__device__ void fold_rows(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int b, int N, int M,
-                          unsigned long long *key1, int row0, int row_end, float *__restrict__ dist1,
-                          int *__restrict__ idx1, float *sums, const float *__restrict__ gw, float *g1,
-                          float *g2, int lane) {
-    float s1 = 0.f;
-    const float gg = FUSE_BWD ? __fmul_rn(__ldg(gw + 0), 2.f) : 0.f;
-    for (int base = row0; base < row_end; base += 32) {
-        const int i = base + lane;
-        const bool valid = i < row_end;
-        const size_t t = (size_t)b * N + (valid ? i : row0);
-        unsigned want = 0u;
-        int g = 0;
-        float qx = 0.f, qy = 0.f, qz = 0.f;
-        if (valid) {
-            const unsigned long long key = __ldcg(key1 + t);
-            key1[t] = KEY_INIT;
-            want = (unsigned)(key >> 32);
-            g = (int)(unsigned)key;
-            qx = __ldg(xyz1 + t * 3 + 0); qy = __ldg(xyz1 + t * 3 + 1); qz = __ldg(xyz1 + t * 3 + 2);
-        }
-        int found = g * CH_GR;
-        const int nrow = min(32, row_end - base);
-        // the resolving warp holds its CTA slot: keep many candidate loads in flight (the hot
-        // loop's registers are dead here)
-#pragma unroll 8
-        for (int s = 0; s < nrow; s++) {
-            const unsigned w_s = __shfl_sync(FULL_MASK, want, s);
-            const int g_s = __shfl_sync(FULL_MASK, g, s);
-            const float x_s = __shfl_sync(FULL_MASK, qx, s);
-            const float y_s = __shfl_sync(FULL_MASK, qy, s);
-            const float z_s = __shfl_sync(FULL_MASK, qz, s);
-            const int j = g_s * CH_GR + lane;
-            bool match = false;
-            if (j < M) {
-                const float *r = xyz2 + ((size_t)b * M + j) * 3;
-                match = __float_as_uint(sqdist_xyz(__ldg(r), __ldg(r + 1), __ldg(r + 2), x_s, y_s, z_s)) == w_s;
-            }
-            const unsigned hit = __ballot_sync(FULL_MASK, match);
-            if (lane == s && hit != 0u) found = g_s * CH_GR + __ffs(hit) - 1;
-        }
-        if (valid) {
-            dist1[t] = __uint_as_float(want);
-            idx1[t] = found;
-            s1 += __uint_as_float(want);
-            const size_t nbr = ((size_t)b * M + found) * 3;
-            fold_bwd_term<FUSE_BWD>(gg, qx, qy, qz, xyz2 + nbr, g1 + t * 3, g2 + nbr);
-        }
-    }
-    if (sums != nullptr) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(FULL_MASK, s1, o);
-        if (lane == 0) atomicAdd(sums + 0, s1);
-    }
-}
-
-// one thread resolves one column (reference j of cloud b): the Q queries of the recorded group
-template <int Q, bool FUSE_BWD>
-__device__ float fold_col(const float *__restrict__ xyz1, int b, int N, int M, unsigned long long *key2, int j,
-                          float rx, float ry, float rz, float *__restrict__ dist2, int *__restrict__ idx2,
-                          const float *__restrict__ gw, float *g1, float *g2) {
-    const size_t u = (size_t)b * M + j;
-    const unsigned long long key = __ldcg(key2 + u);
-    key2[u] = KEY_INIT;
-    const unsigned want = (unsigned)(key >> 32);
-    const int i0 = (int)(unsigned)key * Q;
-    const float *q = xyz1 + (size_t)b * N * 3;
-    int found = i0;
-#pragma unroll
-    for (int e = Q - 1; e >= 0; e--) {  // descending so the lowest match wins
-        const int i = i0 + e;
-        if (i < N) {
-            const float d = sqdist_xyz(rx, ry, rz, __ldg(q + (size_t)i * 3), __ldg(q + (size_t)i * 3 + 1),
-                                       __ldg(q + (size_t)i * 3 + 2));
-            if (__float_as_uint(d) == want) found = i;
-        }
-    }
-    dist2[u] = __uint_as_float(want);
-    idx2[u] = found;
-    if (FUSE_BWD) {
-        const float gg = __fmul_rn(__ldg(gw + 1), 2.f);
-        const size_t nbr = ((size_t)b * N + found) * 3;
-        fold_bwd_term<true>(gg, rx, ry, rz, xyz1 + nbr, g2 + u * 3, g1 + nbr);
-    }
-    return __uint_as_float(want);
-}
-
-struct FoldArgs {  // only read by FOLD instantiations
-    float *dist1, *dist2;
-    int *idx1, *idx2;
-    float *sums;
-    const float *gw;
-    float *g1, *g2;
-    unsigned *wdone, *cdone;  // per (cloud, 256-query warp tile) / per (cloud, reference block)
-};
-
 // STAGEQ: a thread's Q query points are 12*Q contiguous bytes, so loading them straight from
 // global memory makes every LDG of a warp touch 24 different 128-byte lines (24 such loads per
 // tile: ~1200 cycles of the SM's single L1 wavefront queue, which the other warps' LDS.128 of the
 // hot loop wait behind).  Staged, the CTA reads its tile as whole lines into shared memory (one
 // pad word per 24 so that the per-thread readback at stride 25 words is conflict free).
-template <int Q, int THREADS, int RB, int MINB, bool ROTATE, bool LABELED, bool STAGEQ = false, bool ELECT = true,
-          int FOLD = 0>  // FOLD: 0 = separate finalize kernel, 1 = folded, 2 = folded with the uniform backward
+template <int Q, int THREADS, int RB, int MINB, bool ROTATE, bool LABELED, bool STAGEQ = false, bool ELECT = true>
 __global__ void __launch_bounds__(THREADS, MINB)
 chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, int N, int M,
                    unsigned long long *__restrict__ key1, unsigned long long *__restrict__ key2,
                    int queries_per_split, const float *__restrict__ label1,
                    const float *__restrict__ label2, float *__restrict__ zero1,
-                   float *__restrict__ zero2, FoldArgs fold) {
-    static_assert(FOLD == 0 || (!LABELED && Q * 32 == 256), "folded finalize: unlabeled, 256-query warp tiles");
+                   float *__restrict__ zero2) {
     __shared__ __align__(16) float sX[RB];
     __shared__ __align__(16) float sY[RB];
     __shared__ __align__(16) float sZ[RB];
@@ -420,51 +298,6 @@ chamfer_fwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
             if (i < q_end)
                 atomicMin(k1 + i, ((unsigned long long)__float_as_uint(best[q]) << 32) |
                                       (unsigned)granule[q]);
-        }
-        if (FOLD) {
-            // this warp's 256 rows have now met reference block blockIdx.x; the last of the
-            // gridDim.x warps that own the tile resolves it
-            const int row0 = qt + (int)(threadIdx.x & ~31u) * Q;
-            __threadfence();
-            __syncwarp();
-            unsigned *cnt = fold.wdone + (size_t)b * ((N + 255) / 256) + row0 / 256;
-            unsigned old = 0u;
-            if (lane == 0) old = atomicAdd(cnt, 1u);
-            old = __shfl_sync(FULL_MASK, old, 0);
-            if (old == gridDim.x - 2u) {  // counters start at 0xffffffff
-                if (lane == 0) *cnt = 0xffffffffu;
-                __threadfence();
-                fold_rows<FOLD == 2>(xyz1, xyz2, b, N, M, key1, row0, min(q_end, row0 + 256), fold.dist1, fold.idx1,
-                                     fold.sums, fold.gw, fold.g1, fold.g2, lane);
-            }
-        }
-    }
-    if (FOLD) {
-        // columns of this reference block: complete once all gridDim.z query splits are through
-        __shared__ unsigned s_last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned *cnt = fold.cdone + (size_t)b * gridDim.x + blockIdx.x;
-            const unsigned old = atomicAdd(cnt, 1u);
-            s_last = old == gridDim.z - 2u;
-            if (s_last) *cnt = 0xffffffffu;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            float s2 = 0.f;
-            for (int t = threadIdx.x; t < RB; t += THREADS) {
-                const int j = ref_begin + t;
-                if (j < M)
-                    s2 += fold_col<Q, FOLD == 2>(xyz1, b, N, M, key2, j, sX[t], sY[t], sZ[t], fold.dist2, fold.idx2,
-                                                 fold.gw, fold.g1, fold.g2);
-            }
-            if (fold.sums != nullptr) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(FULL_MASK, s2, o);
-                if (lane == 0) atomicAdd(fold.sums + 1, s2);
-            }
         }
     }
 }
@@ -752,16 +585,19 @@ chamfer_bwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
 
 using namespace pp;
 
+static size_t chamfer_keys_bytes(int B, int N, int M) {
+    return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M);
+}
+
 extern "C" size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M) {
     if (B <= 0 || N < 0 || M < 0) return 0;
-    // packed keys, then the completion counters of the folded-finalize variants (one per cloud and
-    // 256-query warp tile, one per cloud and reference block of >= 128 points), rounded to 8 bytes
-    const size_t counters = (size_t)B * ((size_t)ceil_div(N, 256) + (size_t)ceil_div(M, 128));
-    return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M) + ((counters * 4 + 7) & ~(size_t)7);
+    // the sweep path's layout (chamfer_sweep.cu) contains more than the packed keys of the exact one-pass kernel
+    const size_t a = chamfer_keys_bytes(B, N, M), b = chamfer_sweep_workspace_bytes(B, N, M);
+    return a > b ? a : b;
 }
 
 template <int Q, int THREADS, int RB, int MINB, bool ROTATE = true, bool LABELED = false, bool STAGEQ = false,
-          bool ELECT = true, bool FOLD = false>
+          bool ELECT = true>
 static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M,
                               unsigned long long *key1, unsigned long long *key2, float *dist1,
                               float *dist2, int *idx1, int *idx2, float *sums, cudaStream_t st,
@@ -780,32 +616,10 @@ static int launch_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N
     splits = ceil_div(N, queries_per_split);
     PP_REQUIRE(B <= 65535 && splits <= 65535, "chamfer: grid too large (B=%d)", B);
     dim3 grid(ref_blocks, B, splits);
-    if (FOLD) {
-        // experimental: the forward kernel resolves the keys itself (no finalize launch).  The
-        // counters sit behind the keys (see pp_chamfer_fwd_workspace_bytes); gradients are
-        // accumulated while other CTAs still run, so they are cleared up front.
-        FoldArgs fa;
-        fa.dist1 = dist1; fa.dist2 = dist2; fa.idx1 = idx1; fa.idx2 = idx2; fa.sums = sums;
-        fa.gw = gw; fa.g1 = g1; fa.g2 = g2;
-        fa.wdone = reinterpret_cast<unsigned *>(key2 + (size_t)B * M);
-        fa.cdone = fa.wdone + (size_t)B * ceil_div(N, 256);
-        KernelTimer timer("chamfer_fwd", st);
-        if (gw != nullptr) {
-            PP_CUDA(cudaMemsetAsync(g1, 0, sizeof(float) * (size_t)B * N * 3, st));
-            PP_CUDA(cudaMemsetAsync(g2, 0, sizeof(float) * (size_t)B * M * 3, st));
-            chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, false, STAGEQ, ELECT, FOLD ? 2 : 0><<<grid, THREADS, 0, st>>>(
-                xyz1, xyz2, N, M, key1, key2, queries_per_split, nullptr, nullptr, nullptr, nullptr, fa);
-        } else {
-            chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, false, STAGEQ, ELECT, FOLD ? 1 : 0><<<grid, THREADS, 0, st>>>(
-                xyz1, xyz2, N, M, key1, key2, queries_per_split, nullptr, nullptr, nullptr, nullptr, fa);
-        }
-        PP_LAUNCH_CHECK();
-        return PP_OK;
-    }
     {
         KernelTimer timer("chamfer_fwd", st);
         chamfer_fwd_kernel<Q, THREADS, RB, MINB, ROTATE, LABELED, STAGEQ, ELECT><<<grid, THREADS, 0, st>>>(
-            xyz1, xyz2, N, M, key1, key2, queries_per_split, label1, label2, g1, g2, FoldArgs());
+            xyz1, xyz2, N, M, key1, key2, queries_per_split, label1, label2, g1, g2);
     }
     PP_LAUNCH_CHECK();
     const int row_blocks = (int)ceil_div_ll((long long)B * N, 256);
@@ -879,8 +693,14 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
         PP_REQUIRE(sums == nullptr, "chamfer_fwd: fused sums are only available for c == 3");
         return launch_generic(false, xyz1, xyz2, nullptr, nullptr, B, N, M, c, dist1, dist2, idx1, idx2, st);
     }
-    const size_t need = pp_chamfer_fwd_workspace_bytes(B, N, M);
-    PP_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 7) == 0, "chamfer_fwd: workspace null or misaligned");
+    PP_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0, "chamfer_fwd: workspace null or misaligned");
+    int pick = get_option("chamfer_variant", 0);
+    // Default: approximate sweep + exact resolution (chamfer_sweep.cu); 1..35 select the exact
+    // one-pass kernel below (A/B switch and the labeled path's kernel).
+    if (pick == 0 || pick == 50)
+        return chamfer_sweep_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, sums, workspace, workspace_bytes, gw,
+                                    g1, g2, st);
+    const size_t need = chamfer_keys_bytes(B, N, M);
     if (workspace_bytes < need) {
         set_error("chamfer_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
         return PP_ENOSPC;
@@ -890,8 +710,7 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     // The finalize kernel leaves the keys all-ones again; callers that own a persistent
     // workspace say so with PP_CHAMFER_WS_CLEAN and save the fill.
     if (!(flags & PP_CHAMFER_WS_CLEAN)) PP_CUDA(cudaMemsetAsync(workspace, 0xff, need, st));
-    int pick = get_option("chamfer_variant", 0);
-    if (pick == 0) {
+    if (pick == 60) {  // the exact kernel's own automatic choice
         // Smaller reference blocks keep small clouds spread over all SMs.  A warp takes 32*Q = 256
         // queries: when 4-warp CTAs would leave two or more warp slots of the last query split
         // without work (N = 2500: 10 warps in 3 CTAs), 2-warp CTAs waste none.
@@ -912,10 +731,6 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
         case 31: return launch_chamfer_fwd<8, 128, 256, 5, true, false, true, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 32: return launch_chamfer_fwd<8, 128, 128, 5, true, false, true, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 35: return launch_chamfer_fwd<8, 64, 128, 10, true, false, true, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
-        // experimental (not the default, see FOLD above): 1 / 32 / 35 with the finalize folded in
-        case 41: return launch_chamfer_fwd<8, 128, 256, 5, true, false, false, true, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
-        case 42: return launch_chamfer_fwd<8, 128, 128, 5, true, false, true, false, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
-        case 45: return launch_chamfer_fwd<8, 64, 128, 10, true, false, true, false, true>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 13: return launch_chamfer_fwd<8, 128, 256, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         case 14: return launch_chamfer_fwd<8, 128, 128, 5, false>(xyz1, xyz2, B, N, M, key1, key2, dist1, dist2, idx1, idx2, sums, st, nullptr, nullptr, gw, g1, g2);
         default: break;
@@ -963,7 +778,7 @@ extern "C" int pp_chamfer_labeled_fwd(const float *xyz1, const float *xyz2, cons
     // fast path: the one-pass kernel with the label mask (same key workspace protocol as pp_chamfer_fwd)
     PP_REQUIRE((long long)B * N * c < (1ll << 31) && (long long)B * M * c < (1ll << 31),
                "chamfer_labeled_fwd: B*N*c must fit int32 indexing like the reference");
-    const size_t need = pp_chamfer_fwd_workspace_bytes(B, N, M);
+    const size_t need = chamfer_keys_bytes(B, N, M);
     PP_REQUIRE(((uintptr_t)workspace & 7) == 0, "chamfer_labeled_fwd: workspace misaligned");
     if (workspace_bytes < need) {
         set_error("chamfer_labeled_fwd: workspace %zu < %zu bytes", workspace_bytes, need);

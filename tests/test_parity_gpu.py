@@ -67,9 +67,7 @@ def test_chamfer_forward_bit_exact(pp, oracle_mod, B, N, M, maker, seed):
     assert np.array_equal(np32(d2).view(np.uint32), e2.view(np.uint32)), "dist2 bits"
 
 
-# 41 / 42 / 45 (finalize folded into the forward kernel) are experimental and not yet run on a GPU:
-# PP_EXPERIMENTAL=1 adds them
-_VARIANTS = [1, 2, 5, 13, 14, 21, 22, 25, 31, 32, 35] + ([41, 42, 45] if os.environ.get("PP_EXPERIMENTAL") else [])
+_VARIANTS = [1, 2, 5, 13, 14, 21, 22, 25, 31, 32, 35]
 
 
 @pytest.mark.parametrize("variant", _VARIANTS)
@@ -932,7 +930,6 @@ def _brute_knn(points, k):
     return d.topk(k + 1, dim=-1, largest=False).indices[:, :, 1:]
 
 
-@pytest.mark.skipif(not os.environ.get("PP_EXPERIMENTAL"), reason="written without GPU time left; PP_EXPERIMENTAL=1 runs it")
 @pytest.mark.parametrize("nsample", [64, 1])
 def test_sampled_dense_edge_conv_on_device(pp, oracle_mod, nsample):
     """SampledDenseEdgeConv (network/layers.py:85-133) on the real operators: centres = FPS order of
