@@ -695,9 +695,10 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     }
     PP_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0, "chamfer_fwd: workspace null or misaligned");
     int pick = get_option("chamfer_variant", 0);
-    // Default: approximate sweep + exact resolution (chamfer_sweep.cu); 1..35 select the exact
-    // one-pass kernel below (A/B switch and the labeled path's kernel).
-    if (pick == 0 || pick == 50)
+    // 50 = approximate sweep (GEMM-expansion distances on the FFMA pipe) + exact resolution,
+    // chamfer_sweep.cu: bit-identical results, measured SLOWER than the exact one-pass kernel below on
+    // B200 (profiles/r02_*), so it is an option, not the default.
+    if (pick == 50)
         return chamfer_sweep_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, sums, workspace, workspace_bytes, gw,
                                     g1, g2, st);
     const size_t need = chamfer_keys_bytes(B, N, M);
@@ -710,7 +711,7 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     // The finalize kernel leaves the keys all-ones again; callers that own a persistent
     // workspace say so with PP_CHAMFER_WS_CLEAN and save the fill.
     if (!(flags & PP_CHAMFER_WS_CLEAN)) PP_CUDA(cudaMemsetAsync(workspace, 0xff, need, st));
-    if (pick == 60) {  // the exact kernel's own automatic choice
+    if (pick == 0) {
         // Smaller reference blocks keep small clouds spread over all SMs.  A warp takes 32*Q = 256
         // queries: when 4-warp CTAs would leave two or more warp slots of the last query split
         // without work (N = 2500: 10 warps in 3 CTAs), 2-warp CTAs waste none.
