@@ -3,9 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Default workload = BASELINE.json configs[1]: Chamfer distance fwd+bwd, B=32 clouds per GPU,
-N=M=2500 points (AtlasNet training shape), metric = unique point-pairs/s (B*N*M per step,
-whole job).  One "step" = nndistance forward (both directions + fused loss partial sums),
+Default workload = BASELINE.json configs[4] (`chamfer_b256_n8192`): Chamfer distance fwd+bwd, a
+batch of 256 clouds of N=M=8192 points sharded over the GPUs (256/W clouds per rank: STRONG
+scaling; at one GPU it is the largest single-GPU Chamfer configuration), metric = unique
+point-pairs/s (B*N*M per step, whole job).  `--workload chamfer_b32_n2500` (configs[1], weak
+scaling) and `chamfer_b32_n8192` (target shape) remain selectable and are reported, with their
+end-to-end legs, under `extras`.  One "step" = nndistance forward (both directions + fused loss partial sums),
 the backward scatter for loss = mean(dist1) + mean(dist2), and, when N>1, the exchange of the
 two partial sums (peer-memory mailboxes; NCCL all-reduce with PP_LOSS_EXCHANGE=nccl).  Default:
 the two-launch form pp_chamfer_fwd_bwd_uniform (backward folded into the index-resolving
@@ -14,8 +17,11 @@ it (`fused_step` in the line); PP_FUSED_BWD=0 times the four-launch sequence onl
 
 Legs printed in ONE JSON line by rank 0:
   value     device-resident: inputs already in HBM, C-ABI calls on the current stream;
-  e2e       through the public API (autograd Function `nndistance` + sharded mean loss) with
-            pinned HOST buffers copied in every step and the loss read back every step;
+  e2e       the reference-signature path a drop-in user runs: pinned HOST clouds copied in every
+            step (double-buffered copy stream), the autograd Function behind `nndistance` /
+            `sharded_chamfer_loss`, `loss.backward()`, and every step's loss read on the host
+            (one step behind, like a logging training loop); the CUDA-graph pipeline
+            (`pipeline.GraphedChamferStep`) and the plugin-level calls are reported next to it;
   roofline  dominant kernel (chamfer_fwd_kernel), duration from CUDA events on the launching
             stream (library timing hooks), against the FP32 pipe peak measured live;
   cpu_baseline  the CPU oracle port (oracle/pp_oracle.c, OpenMP) on the box's host cores;
@@ -107,6 +113,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+def cpu_threads_setup():
+    """All host threads for the OpenMP port, even under torch.distributed.run (which exports
+    OMP_NUM_THREADS=1); must run before the oracle library is loaded."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_WAIT_POLICY", "active")
+    return n
+
+
 def cpu_chamfer_step(a, b, total_batch):
     """One fwd+bwd pass of the oracle port over numpy clouds; returns the loss."""
     import numpy as np
@@ -124,6 +140,7 @@ def run_cpu_baseline(N, M, budget_s=12.0):
     """Oracle port on the host cores over a bounded sample of the workload."""
     import numpy as np
     from helpers import np32, uniform_cloud
+    cpu_threads_setup()
     import oracle
     oracle.lib()
     a1, b1 = np32(uniform_cloud(1, N, 1001)), np32(uniform_cloud(1, M, 2001))
@@ -149,38 +166,47 @@ def run_cpu_baseline(N, M, budget_s=12.0):
 
 
 def reference_arm(args, world, rank):
-    """--impl reference: the reference's CPU-side equivalent of the path on the host cores."""
+    """--impl reference: the reference's CPU-side equivalent of the path on the host cores.  Rank 0
+    alone runs it, with every host thread (the other ranks exit at once), on a bounded sample of the
+    job's clouds; throughput in pairs/s does not depend on how many clouds the sample holds."""
     kind, B, N, M = WORKLOADS[args.workload]
     if rank != 0:
         return
-    import numpy as np  # noqa: F401
     from helpers import np32, uniform_cloud
+    cores = cpu_threads_setup()
     import oracle
     oracle.lib()
     a1, b1 = np32(uniform_cloud(1, N, 1001)), np32(uniform_cloud(1, M, 2001))
-    cpu_chamfer_step(a1, b1, 1)
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < 2.0:  # thread pool up, clocks settled
+        cpu_chamfer_step(a1, b1, 1)
     t0 = time.perf_counter()
     cpu_chamfer_step(a1, b1, 1)
     t1 = max(time.perf_counter() - t0, 1e-4)
-    budget = 150.0
+    budget = 120.0
     bs = int(max(1, min(B, budget / max(args.steps + args.warmup, 1) / t1)))
     a, b = np32(uniform_cloud(bs, N, 1001)), np32(uniform_cloud(bs, M, 2001))
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):
         cpu_chamfer_step(a, b, bs)
-    t0 = time.perf_counter()
+    per_step = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         cpu_chamfer_step(a, b, bs)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+        per_step.append(time.perf_counter() - t0)
+    dt = sum(per_step) / max(len(per_step), 1)
     value = bs * N * M / dt
-    sample = ("each step = oracle port (C + OpenMP) Chamfer fwd+bwd over %d of the %d clouds per GPU, "
-              "N=M=%d; the reference has no CPU implementation of this path (SURVEY.md D2)" % (bs, B, N))
+    scaling = "strong" if args.workload == "chamfer_b256_n8192" else "weak"
+    sample = ("each step = oracle port (C + OpenMP, %d threads) Chamfer fwd+bwd over %d of the job's clouds, "
+              "N=M=%d; the reference has no CPU implementation of this path (SURVEY.md D2)" % (cores, bs, N))
     line = {
         "impl": "reference", "metric": "chamfer_fwd_bwd_point_pairs_per_s", "value": value,
         "unit": "point-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": dt * 1e3, "best_ms_per_step": min(per_step) * 1e3 if per_step else None,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: Chamfer fwd+bwd B=%d N=M=%d (CPU sample of %d clouds)" % (args.workload, B, N, bs)},
-        "cpu_baseline": {"value": value, "unit": "point-pairs/s", "cores": os.cpu_count(), "kind": "port",
+        "config": {"workload": workload_name(args.workload, B // world if scaling == "strong" else B, N, world),
+                   "cpu_sample_clouds": bs},
+        "cpu_baseline": {"value": value, "unit": "point-pairs/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "point-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -188,13 +214,19 @@ def reference_arm(args, world, rank):
     print(json.dumps(line), flush=True)
 
 
+def workload_name(name, per_gpu_batch, N, world):
+    """The `config.workload` string shared by both arms (the driver compares them)."""
+    return "%s: Chamfer (nndistance) fwd+bwd, %d clouds in the job (%d per GPU), N=M=%d, uniform [0,1)^3, " \
+           "loss = mean(dist1)+mean(dist2)" % (name, per_gpu_batch * world, per_gpu_batch, N)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="chamfer_b32_n2500", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="chamfer_b256_n8192", choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -370,13 +402,41 @@ def main():
             graphed.loss(in_flight.pop(0))
             losses_read[0] += 1
 
-    def step_e2e_autograd():
-        """Same step through the autograd API a PyTorch user calls."""
+    def step_e2e_autograd_blocking():
+        """The reference-signature step with nothing overlapped: host .to(device), autograd loss,
+        backward, loss.item()."""
         x = a_host.to(dev, non_blocking=True).requires_grad_(True)
         y = b_host.to(dev, non_blocking=True).requires_grad_(True)
         loss = sharded_chamfer_loss(x, y, total_batch=total_B)
         loss.backward()
         return loss.item()
+
+    ag_prefetcher = HostPrefetcher(dev, depth=2)
+    ag_prefetcher.prefetch((a_host, b_host))
+    ag_pending = []
+    ag_read = [0]
+
+    def step_e2e_autograd():
+        """The reference-signature step as a training loop runs it: this step's clouds were copied from
+        pinned host memory on the copy stream during the previous step (torch DataLoader-style
+        prefetch), the autograd Function behind nndistance / sharded_chamfer_loss, loss.backward(),
+        the next step's copies enqueued, then the PREVIOUS step's loss read on the host while this
+        step runs (every step's loss is read inside the timed region)."""
+        xd, yd = ag_prefetcher.get()
+        x, y = xd.detach().requires_grad_(True), yd.detach().requires_grad_(True)
+        loss = sharded_chamfer_loss(x, y, total_batch=total_B)
+        loss.backward()
+        ag_prefetcher.release()
+        ag_prefetcher.prefetch((a_host, b_host))
+        ag_pending.append(loss.detach())
+        if len(ag_pending) > 1:
+            ag_pending.pop(0).item()
+            ag_read[0] += 1
+
+    def finish_autograd():
+        while ag_pending:
+            ag_pending.pop(0).item()
+            ag_read[0] += 1
 
     def barrier():
         if world > 1:
@@ -432,11 +492,14 @@ def main():
     ms_step = timed(step_device, args.steps, args.warmup)
     ms_step_unfused = timed(step_device_unfused, args.steps, args.warmup) if fused else ms_step
     ms_e2e_plugin = timed_e2e(step_e2e, args.steps, args.warmup)
-    ms_e2e_autograd = timed_e2e(step_e2e_autograd, min(args.steps, 50), 3)
+    ms_e2e_autograd_blocking = timed_e2e(step_e2e_autograd_blocking, min(args.steps, 50), 3)
+    ag_read[0] = 0
+    ms_e2e_autograd = timed_e2e(step_e2e_autograd, args.steps, args.warmup, finish=finish_autograd)
+    assert ag_read[0] == args.steps + args.warmup, "every step's loss must be read on the host"
     if graphed is not None:
         ms_e2e_blocking = timed_e2e(step_e2e_graph, args.steps, args.warmup)
         losses_read[0] = 0
-        ms_e2e = timed_e2e(step_e2e_pipelined, args.steps, args.warmup, finish=finish_pipelined)
+        ms_e2e_graph = timed_e2e(step_e2e_pipelined, args.steps, args.warmup, finish=finish_pipelined)
         assert losses_read[0] == args.steps + args.warmup, "every step's loss must be read on the host"
         e2e_api = ("pipeline.GraphedChamferStep.submit()/loss(): compute graph(s) (" +
                    ("pp_chamfer_fwd_bwd_uniform: forward + finalize with fused loss sums and backward" if fused else
@@ -447,7 +510,7 @@ def main():
                    "its inputs in and has its loss read on the host inside the timed region")
         loss_graph = step_e2e_graph()
     else:
-        ms_e2e, e2e_api, loss_graph = ms_e2e_plugin, "see plugin_api (CUDA-graph step is single-GPU only)", None
+        ms_e2e_graph, e2e_api, loss_graph = ms_e2e_plugin, "see plugin_api (CUDA-graph step is single-GPU only)", None
         ms_e2e_blocking = ms_e2e_plugin
     # separate short pass with the library's per-kernel CUDA events switched on, so the event
     # records do not perturb the two timed legs above
@@ -475,15 +538,24 @@ def main():
     peak_tflops = ffma_flop / (ffma_ms * 1e-3) / 1e12
     pipe_pairs = mix_pairs / (mix_ms * 1e-3)
     achieved = flops_per_launch / (fwd_ms * 1e-3) / 1e12
-    traffic = None
+    # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload -- used only
+    # if it was taken from the kernel source that is running now (hash of csrc/chamfer.cu)
+    traffic, traffic_note = None, "no ncu capture committed for this workload"
     try:
-        summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        traffic = summ.get(args.workload, {}).get("chamfer_fwd_dram_bytes_per_launch")
-    except Exception:  # noqa: BLE001
-        pass
+        import hashlib
+        sha = hashlib.sha256(open(os.path.join(ROOT, "pytorch_points_b200", "csrc", "chamfer.cu"), "rb").read()).hexdigest()[:16]
+        ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(args.workload)
+        if ent:
+            if ent.get("chamfer_cu_sha16") == sha:
+                traffic = ent.get("chamfer_fwd_dram_bytes_per_launch")
+                traffic_note = "dram__bytes_read+write of %s, %s" % (ent.get("kernel", "?"), ent.get("capture", "?"))
+            else:
+                traffic_note = "stale capture (kernel source changed since %s): not reported" % ent.get("capture", "?")
+    except Exception as e:  # noqa: BLE001
+        traffic_note = "unreadable profiles/ncu_summary.json: %r" % (e,)
     roofline = {
         "kernel": "chamfer_fwd_kernel", "bound": "fp32", "achieved": achieved, "peak": peak_tflops,
-        "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic,
+        "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": "FFMA peak measured live by pp_microbench (MEASURED_PEAKS.json holds no FP32 entry)",
         "kernel_ms": fwd_ms, "kernel_launches_timed": kt["chamfer_fwd"][1],
         "algorithmic_flop_per_launch": flops_per_launch,
@@ -504,22 +576,30 @@ def main():
         "unit": "point-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: Chamfer (nndistance) fwd+bwd, B=%d clouds per GPU, N=M=%d, uniform [0,1)^3, "
-                               "loss = mean(dist1)+mean(dist2)%s" % (
-                                   args.workload, B, N, (", " + exchange_note) if world > 1 else ""),
-                   "global_batch": total_B, "l2": "flushed between timed steps (256 MiB write); inputs 1.9 MB < L2",
+        "config": {"workload": workload_name(args.workload, B, N, world),
+                   "loss_exchange": exchange_note if world > 1 else "none (single GPU)",
+                   "global_batch": total_B,
+                   "l2": "flushed between timed steps (256 MiB write); inputs %.1f MB per GPU" % (
+                       (a_host.numel() + b_host.numel()) * 4 / 1e6),
                    "timing": "per-step CUDA events on the current stream, max over ranks"},
-        "e2e": {"value": pairs_per_step / (ms_e2e * 1e-3), "unit": "point-pairs/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": world * (a_host.numel() + b_host.numel()) * 4, "d2h_bytes_per_step": world * 8,
-                "api": e2e_api,
-                "blocking_api": {"value": pairs_per_step / (ms_e2e_blocking * 1e-3), "ms_per_step": ms_e2e_blocking,
-                                 "api": "pipeline.GraphedChamferStep.run(): same graphs, the host waits for each step's loss "
-                                        "before enqueueing the next step"},
+        "e2e": {"value": pairs_per_step / (ms_e2e_autograd * 1e-3), "unit": "point-pairs/s", "ms_per_step": ms_e2e_autograd,
+                "h2d_bytes_per_step": world * (a_host.numel() + b_host.numel()) * 4, "d2h_bytes_per_step": world * 4,
+                "api": "reference-signature path: pipeline.HostPrefetcher (pinned host -> device on a copy stream, double "
+                       "buffered) + dist.sharded_chamfer_loss (the torch.autograd Function behind nndistance, loss sums "
+                       "all-reduced with torch.distributed when N>1) + loss.backward(); the host reads step i's loss while "
+                       "step i+1 runs -- every step copies its inputs in and has its loss read inside the timed region",
+                "autograd_blocking_api": {"value": pairs_per_step / (ms_e2e_autograd_blocking * 1e-3), "ms_per_step": ms_e2e_autograd_blocking,
+                                          "api": "host .to(device) + dist.sharded_chamfer_loss + loss.backward() + loss.item(), nothing overlapped"},
+                "graph_api": {"value": pairs_per_step / (ms_e2e_graph * 1e-3), "ms_per_step": ms_e2e_graph,
+                              "h2d_bytes_per_step": world * (a_host.numel() + b_host.numel()) * 4, "d2h_bytes_per_step": world * 8,
+                              "api": e2e_api},
+                "graph_blocking_api": {"value": pairs_per_step / (ms_e2e_blocking * 1e-3), "ms_per_step": ms_e2e_blocking,
+                                       "api": "pipeline.GraphedChamferStep.run(): same graphs, the host waits for each step's loss "
+                                              "before enqueueing the next step"},
                 "plugin_api": {"value": pairs_per_step / (ms_e2e_plugin * 1e-3), "ms_per_step": ms_e2e_plugin,
                                "api": "pipeline.HostPrefetcher (pinned host -> device, double buffered) + _ext.losses.nmdistance_forward / "
                                       "nmdistance_backward_uniform (the reference-shaped plugin boundary) + D2H of the loss sums"},
-                "autograd_api": {"value": pairs_per_step / (ms_e2e_autograd * 1e-3), "ms_per_step": ms_e2e_autograd,
-                                 "api": "host .to(device) + dist.sharded_chamfer_loss (torch.autograd) + loss.backward() + loss.item()"}, "timing": "one CUDA-event region over all K steps; every step copies its inputs from pinned host memory and ends with a host read of the loss"},
+                "timing": "one CUDA-event region over all K steps; every step copies its inputs from pinned host memory and has its loss read on the host"},
         "fused_step": {"state": fused_note, "ms_per_step_four_launch_sequence": ms_step_unfused},
         "gpu_launches": ((2 if fused else 4) + (2 if exchange is not None else 0)) * args.steps,
         "gpu_launches_note": ("per step: chamfer_fwd_kernel, chamfer_finalize_kernel<fused backward>" if fused else
@@ -567,33 +647,88 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
         return ts[len(ts) // 2]
 
     out = {}
-    # Chamfer fwd+bwd at the north-star target shape
-    B, N = 32, 8192
-    a, b = uniform_cloud(B, N, 1).to(dev), uniform_cloud(B, N, 2).to(dev)
-    d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, N, device=dev)
-    i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, N, dtype=torch.int32, device=dev)
-    gw = torch.full((2,), 1.0 / (B * N), device=dev)
-    g1, g2 = torch.empty_like(a), torch.empty_like(b)
-    sums = torch.zeros(2, device=dev)
+    # Chamfer fwd+bwd at configs[1] (AtlasNet shape) and at the north-star target shape, device-resident
+    # and end to end (same two e2e paths as the headline workload)
+    from pytorch_points_b200.dist import sharded_chamfer_loss
+    from pytorch_points_b200.pipeline import GraphedChamferStep, HostPrefetcher
+    for (B, N) in [(32, 2500), (32, 8192)]:
+        a_host, b_host = uniform_cloud(B, N, 1).pin_memory(), uniform_cloud(B, N, 2).pin_memory()
+        a, b = a_host.to(dev), b_host.to(dev)
+        d1 = torch.empty(B, N, device=dev); d2 = torch.empty(B, N, device=dev)
+        i1 = torch.empty(B, N, dtype=torch.int32, device=dev); i2 = torch.empty(B, N, dtype=torch.int32, device=dev)
+        gw = torch.full((2,), 1.0 / (B * N), device=dev)
+        g1, g2 = torch.empty_like(a), torch.empty_like(b)
+        sums = torch.zeros(2, device=dev)
 
-    def chamfer_step():
-        if os.environ.get("PP_FUSED_BWD", "1") != "0":
-            losses.nmdistance_forward_backward_uniform(a, b, d1, d2, i1, i2, sums, gw, g1, g2)
-        else:
-            losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
-            losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
-    _C.set_option("timing", 1)
-    _C.timing_collect("chamfer_fwd")
-    ms = timeit(chamfer_step)
-    tot, cnt = _C.timing_collect("chamfer_fwd")
-    _C.set_option("timing", 0)
-    kms = tot / max(cnt, 1)
-    out["chamfer_fwd_bwd_B32_N8192"] = {
-        "ms_per_step": ms, "point_pairs_per_s": B * N * N / (ms * 1e-3), "fwd_kernel_ms": kms,
-        "fwd_kernel_tflops": 8.0 * B * N * N / (kms * 1e-3) / 1e12,
-        "fwd_kernel_frac_of_fp32_peak": 8.0 * B * N * N / (kms * 1e-3) / 1e12 / peak_tflops,
-        "fwd_kernel_frac_of_op_mix_ceiling": B * N * N / (kms * 1e-3) / pipe_pairs}
-    del a, b, d1, d2, i1, i2, g1, g2
+        def chamfer_step():
+            if os.environ.get("PP_FUSED_BWD", "1") != "0":
+                losses.nmdistance_forward_backward_uniform(a, b, d1, d2, i1, i2, sums, gw, g1, g2)
+            else:
+                losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
+                losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
+        _C.set_option("timing", 1)
+        _C.timing_collect("chamfer_fwd")
+        ms = timeit(chamfer_step)
+        tot, cnt = _C.timing_collect("chamfer_fwd")
+        _C.set_option("timing", 0)
+        kms = tot / max(cnt, 1)
+        # e2e, K steps in one region, every step's inputs from pinned host memory, every loss read on the host
+        K, pf, pending = 40, HostPrefetcher(dev, depth=2), []
+        pf.prefetch((a_host, b_host))
+
+        def ag_step():
+            xd, yd = pf.get()
+            x, y = xd.detach().requires_grad_(True), yd.detach().requires_grad_(True)
+            loss = sharded_chamfer_loss(x, y, total_batch=B)
+            loss.backward()
+            pf.release()
+            pf.prefetch((a_host, b_host))
+            pending.append(loss.detach())
+            if len(pending) > 1:
+                pending.pop(0).item()
+        graphed = GraphedChamferStep([(a_host, b_host)], total_batch=B, device=dev, world_size=1, exchange=None,
+                                     fused_backward=os.environ.get("PP_FUSED_BWD", "1") != "0")
+        inflight = []
+
+        def graph_step():
+            inflight.append(graphed.submit())
+            if len(inflight) > 1:
+                graphed.loss(inflight.pop(0))
+
+        def region(step, drain):
+            for _ in range(5):
+                step()
+            drain()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                step()
+            drain()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / K
+
+        def drain_ag():
+            while pending:
+                pending.pop(0).item()
+
+        def drain_graph():
+            while inflight:
+                graphed.loss(inflight.pop(0))
+        ms_ag, ms_gr = region(ag_step, drain_ag), region(graph_step, drain_graph)
+        out["chamfer_fwd_bwd_B%d_N%d" % (B, N)] = {
+            "ms_per_step": ms, "point_pairs_per_s": B * N * N / (ms * 1e-3), "fwd_kernel_ms": kms,
+            "fwd_kernel_tflops": 8.0 * B * N * N / (kms * 1e-3) / 1e12,
+            "fwd_kernel_frac_of_fp32_peak": 8.0 * B * N * N / (kms * 1e-3) / 1e12 / peak_tflops,
+            "fwd_kernel_frac_of_op_mix_ceiling": B * N * N / (kms * 1e-3) / pipe_pairs,
+            "e2e_autograd_ms_per_step": ms_ag, "e2e_autograd_point_pairs_per_s": B * N * N / (ms_ag * 1e-3),
+            "e2e_graph_ms_per_step": ms_gr, "e2e_graph_point_pairs_per_s": B * N * N / (ms_gr * 1e-3),
+            "h2d_bytes_per_step": (a_host.numel() + b_host.numel()) * 4,
+            "e2e_note": "autograd = HostPrefetcher + sharded_chamfer_loss + backward, loss read one step behind; "
+                        "graph = pipeline.GraphedChamferStep.submit()/loss(); both copy the clouds from pinned host "
+                        "memory every step and read every step's loss on the host"}
+        del a, b, d1, d2, i1, i2, g1, g2, graphed, pf
 
     # config 3: FPS 16384 -> 1024 (+gather) and ball_query r=0.2 nsample=32, B=16
     B, N, m = 16, 16384, 1024
@@ -613,12 +748,14 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
     alg_bytes = 20.0 * N * (m - 1) * B
     smem_ms, smem_bytes = _C.microbench(4, 2048, dev.index)  # shared-memory read bandwidth, all 148 SMs
     smem_per_sm = smem_bytes / (smem_ms * 1e-3) / 1e9 / 148.0
-    sms_used = B * 4  # the occupancy query picks 4-CTA clusters for 16 clouds: 64 SMs hold the job
+    cluster, per_thread = _C.fps_last_plan()  # what the library actually launched
+    sms_used = B * max(cluster, 1)
     out["fps_B16_N16384_m1024"] = {
         "ms_per_step": ms, "samples_per_s": B * m / (ms * 1e-3), "kernel_ms": kms,
         "us_per_round": kms * 1e3 / (m - 1),
         "algorithmic_GBps": alg_bytes / (kms * 1e-3) / 1e9,
         "smem_GBps_per_sm_measured": smem_per_sm, "sms_holding_the_clouds": sms_used,
+        "cluster_width": cluster, "points_per_thread": per_thread,
         "frac_of_smem_roofline": alg_bytes / (kms * 1e-3) / 1e9 / (smem_per_sm * sms_used),
         "note": "cloud and running minima are register-resident across a thread-block cluster: no per-round "
                 "memory traffic; algorithmic bytes = 20*N per selected sample (SURVEY.md 8d)"}
@@ -714,7 +851,7 @@ def run_reference_cuda(dev, timeit):
     import ref_sampling
     from helpers import uniform_cloud
     res = {}
-    for (B, N) in [(32, 2500), (32, 8192)]:
+    for (B, N) in [(32, 2500), (32, 8192), (256, 8192)]:
         a, b = uniform_cloud(B, N, 1).to(dev), uniform_cloud(B, N, 2).to(dev)
         d1 = torch.zeros(B, N, device=dev); d2 = torch.zeros(B, N, device=dev)
         i1 = torch.zeros(B, N, dtype=torch.int32, device=dev); i2 = torch.zeros(B, N, dtype=torch.int32, device=dev)

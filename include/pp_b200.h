@@ -40,8 +40,9 @@ const char *pp_last_error_string(void);
 
 /* ------------------------------------------------------------------ losses */
 
-/* Scratch bytes pp_chamfer_fwd needs for (B,N,M): 8 per point of either cloud (packed keys) plus
- * 4 per (cloud, 256-query tile) and (cloud, 128-point reference block) of completion counters. */
+/* Scratch bytes pp_chamfer_fwd needs for (B,N,M): the larger of the exact one-pass kernel's packed
+ * keys (8 per point of either cloud) and the sweep path's layout (chamfer_variant 50: prepared
+ * clouds in query and reference form, keys, runner-up words and rescan lists, about 52 per point). */
 size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M);
 
 /*
@@ -52,7 +53,7 @@ size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M);
  *   sums: optional (may be NULL) 2 floats receiving [sum(dist1), sum(dist2)]
  *   (fused reduction for the loss mean / NCCL all-reduce input).
  *   workspace: >= pp_chamfer_fwd_workspace_bytes(B,N,M) bytes, 8-byte aligned.
- *   flags: 0, or PP_CHAMFER_WS_CLEAN when the first workspace_bytes(B,N,M) bytes are all
+ *   flags: 0, or PP_CHAMFER_WS_CLEAN when the first 8*B*(N+M) bytes are all
  *   0xff -- true for a buffer filled once with 0xff and since then only ever used by
  *   successful pp_chamfer_fwd calls on the same stream (each call restores that state).
  */
@@ -134,6 +135,13 @@ int pp_fps(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t
  */
 int pp_fps_gather(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
                   float *new_xyz, int device, void *stream);
+
+/*
+ * Launch shape the last pp_fps / pp_fps_gather call on this thread chose (diagnostics; bench.py's
+ * FPS roofline uses it): thread-block cluster width (CTAs, hence SMs, per cloud; 0 = the streaming
+ * fallback kernel) and points held per thread.
+ */
+int pp_fps_last_plan(int *cluster_width, int *points_per_thread);
 
 /*
  * gather_points forward / backward.  Replace sampling.gather_forward / gather_backward
@@ -242,8 +250,8 @@ int pp_three_interpolate_bwd(const float *grad_out, const int32_t *idx, const fl
  *            peer's mailbox;
  *   wait   : enqueue where the total is needed (after the backward, so the link latency is
  *            hidden) -- polls the own mailbox for this step's contributions and writes their
- *            sum, added in rank order, to sums_out (2 floats, device).  Bounded: after ~10 s
- *            without a peer the result is NaN and *status (device int, may be NULL) is set to 1.
+ *            sum, added in rank order, to sums_out (2 floats, device).  Bounded (option lx_timeout_ms, default 10 min):
+ *            after that long without a peer the result is NaN and *status (device int, may be NULL) is 1.
  * Every rank must issue the same sequence of send/wait pairs.  Both launches are graph-capturable.
  */
 size_t pp_loss_exchange_handle_bytes(void);
@@ -290,12 +298,16 @@ int pp_knn_stats(double *tiles_visited, double *tiles_total);
  *                                blocks, 64-thread CTAs; 21 / 22 / 25 = 1 / 2 / 5 with the
  *                                query tile staged through shared memory; 31 / 32 / 35 = those
  *                                with the election-free column publish; 13 / 14 = 1 / 2
- *                                without the per-warp sweep rotation; 41 / 42 / 45 =
- *                                EXPERIMENTAL (not yet validated on a GPU): 1 / 32 / 35 with the
- *                                index resolution folded into the forward kernel
+ *                                without the per-warp sweep rotation; 50 = approximate
+ *                                sweep (GEMM-expansion distances on the FFMA pipe, TMA-fed
+ *                                reference ring) + exact resolution: identical results,
+ *                                measured slower on B200
+ *   "chamfer_sweep_warps" (0), "chamfer_sweep_ctas_per_sm" (10/20)   launch shape of variant 50
  *   "chamfer_noelect" (1)        automatic choice below 4097 points uses 32 / 35 (1) or 22 / 25 (0)
  *   "chamfer_blocks_per_sm" (24) target CTA count per SM for the query split heuristic
  *   "chamfer_generic" (0)        force the generic (any point dimension) kernel
+ *   "chamfer_ws_check" (0)       debug: verify (synchronously) that a workspace passed with
+ *                                PP_CHAMFER_WS_CLEAN really is all-ones; PP_EINVAL if not
  *   "fps_cluster" (0)            0 = automatic, else the cluster width 1 / 2 / 4 / 8
  *   "fps_stream" (0)             force the streaming fallback kernel
  *   "knn_morton" (-1)            -1 = automatic, 0 / 1 = never / always use the ordered sweep
@@ -304,6 +316,8 @@ int pp_knn_stats(double *tiles_visited, double *tiles_total);
  *                                one-launch preparation
  *   "knn_smem_lists" (0), "knn_generic" (0)   force the k <= 64 / any-dimension kernels
  *   "knn_stats" (0)              see pp_knn_stats
+ *   "lx_timeout_ms" (600000)     bound of pp_loss_exchange_wait's poll in wall-clock milliseconds
+ *                                (0 = unbounded); on expiry the sums are NaN and *status is set
  */
 int pp_set_option(const char *name, int value);
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     "pp_chamfer_fwd_bwd_uniform": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "pp_fps": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pp_fps_gather": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "pp_fps_last_plan": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "pp_gather_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_gather_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_ball_query": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _i, _vp]),
@@ -128,6 +129,13 @@ def timing_collect(name):
     count = _i(0)
     check(lib.pp_timing_collect(name.encode(), ctypes.byref(total), ctypes.byref(count)), "pp_timing_collect")
     return total.value, count.value
+
+
+def fps_last_plan():
+    """(cluster width, points per thread) of the last FPS call made from this thread."""
+    c, p = _i(0), _i(0)
+    check(lib.pp_fps_last_plan(ctypes.byref(c), ctypes.byref(p)), "pp_fps_last_plan")
+    return c.value, p.value
 
 
 def knn_stats():

@@ -40,10 +40,24 @@ def _check_f32(*ts):
             raise RuntimeError("pytorch_points_b200: only float32 point clouds are supported, got %s" % t.dtype)
 
 
-def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None):
+def _scratch(dev, B, N, M, workspace, workspace_clean):
+    """(tensor, flags) for a Chamfer forward: the caller's own buffer (`workspace`, a CUDA uint8 tensor of
+    at least pp_chamfer_fwd_workspace_bytes; `workspace_clean` = the caller filled it with 0xff once and
+    only ever passes it to these functions on one stream -> PP_CHAMFER_WS_CLEAN, no per-call fill), or the
+    module's per-stream buffer with flags 0."""
+    nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
+    if workspace is None:
+        return _workspace(dev, nbytes), 0
+    if not workspace.is_cuda or workspace.device != dev or workspace.dtype != torch.uint8 \
+            or not workspace.is_contiguous() or workspace.numel() < nbytes:
+        raise RuntimeError("chamfer workspace must be a contiguous CUDA uint8 tensor of >= %d bytes on %s" % (nbytes, dev))
+    return workspace, (_C.PP_CHAMFER_WS_CLEAN if workspace_clean else 0)
+
+
+def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None, workspace=None, workspace_clean=False):
     """losses.nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2) -> int
     (_ext/nmdistance.cpp:13-15).  `sums` (optional, 2 floats) is an extension: fused
-    [sum(dist1), sum(dist2)]."""
+    [sum(dist1), sum(dist2)]; `workspace` / `workspace_clean`: see _scratch."""
     dev = _C.require_cuda(xyz1, xyz2, dist1, dist2, idx1, idx2)
     _C.require_contiguous(xyz1, xyz2, dist1, dist2, idx1, idx2)
     _check_f32(xyz1, xyz2, dist1, dist2)
@@ -59,11 +73,10 @@ def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None):
         _C.require_cuda(xyz1, sums)
         if sums.dtype != torch.float32 or sums.numel() != 2 or not sums.is_contiguous():
             raise RuntimeError("nmdistance_forward: sums must be 2 contiguous float32 values")
-    nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
-    ws = _workspace(dev, nbytes)
+    ws, flags = _scratch(dev, B, N, M, workspace, workspace_clean)
     rc = _C.lib.pp_chamfer_fwd(_C.ptr(xyz1), _C.ptr(xyz2), B, N, M, c, _C.ptr(dist1), _C.ptr(dist2),
                                _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums), _C.ptr(ws), ws.numel(),
-                               0, dev.index, _C.stream_of(dev))
+                               flags, dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_fwd")
     return 1
 
@@ -129,7 +142,8 @@ def nmdistance_backward_uniform(xyz1, xyz2, gradxyz1, gradxyz2, gw, idx1, idx2):
     return 1
 
 
-def nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, sums, gw, gradxyz1, gradxyz2):
+def nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, sums, gw, gradxyz1, gradxyz2,
+                                        workspace=None, workspace_clean=False):
     """Extension: `nmdistance_forward(..., sums=sums)` followed by `nmdistance_backward_uniform` in
     two launches instead of four -- the backward rides in the kernel that resolves the indices.
     For losses that depend on dist1/dist2 only through their sums with weights `gw` known up
@@ -145,11 +159,10 @@ def nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, su
         raise RuntimeError("nmdistance_forward_backward_uniform: idx tensors must be int32")
     if gw.numel() != 2 or gradxyz1.shape != xyz1.shape or gradxyz2.shape != xyz2.shape:
         raise RuntimeError("nmdistance_forward_backward_uniform: gw must hold 2 floats, gradients match the clouds")
-    nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
-    ws = _workspace(dev, nbytes)
+    ws, flags = _scratch(dev, B, N, M, workspace, workspace_clean)
     rc = _C.lib.pp_chamfer_fwd_bwd_uniform(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(gw), B, N, M, _C.ptr(dist1),
                                            _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums),
                                            _C.ptr(gradxyz1), _C.ptr(gradxyz2), _C.ptr(ws), ws.numel(),
-                                           0, dev.index, _C.stream_of(dev))
+                                           flags, dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_chamfer_fwd_bwd_uniform")
     return 1

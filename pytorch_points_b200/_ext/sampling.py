@@ -96,6 +96,9 @@ def three_nn(unknown, known):
     (_ext/sampling.cpp:163-176)."""
     dev = _C.require_cuda(unknown, known)
     _C.require_contiguous(unknown, known)
+    _check(unknown.dtype == torch.float32 and known.dtype == torch.float32, "three_nn: float32 only")
+    _check(unknown.dim() == 3 and known.dim() == 3 and unknown.shape[2] == 3 and known.shape[2] == 3
+           and known.shape[0] == unknown.shape[0], "three_nn: unknown (B,n,3) and known (B,m,3)")
     B, N, _ = unknown.shape
     M = known.shape[1]
     dist2 = torch.empty(B, N, 3, dtype=torch.float32, device=dev)
@@ -111,6 +114,11 @@ def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
     the exact pybind signature of the reference (_ext/sampling.cpp:163-173,213)."""
     dev = _C.require_cuda(unknown, known, dist2, idx)
     _C.require_contiguous(unknown, known, dist2, idx)
+    _check(unknown.dtype == torch.float32 and known.dtype == torch.float32 and dist2.dtype == torch.float32,
+           "three_nn_wrapper: float32 only")
+    _check(idx.dtype == torch.int32, "three_nn_wrapper: idx must be int32")
+    _check(unknown.numel() == b * n * 3 and known.numel() == b * m * 3 and dist2.numel() == b * n * 3
+           and idx.numel() == b * n * 3, "three_nn_wrapper: tensor sizes disagree with (b, n, m)")
     rc = _C.lib.pp_three_nn(_C.ptr(unknown), _C.ptr(known), b, n, m, _C.ptr(dist2), _C.ptr(idx), dev.index,
                             _C.stream_of(dev))
     _C.check(rc, "pp_three_nn")
@@ -122,6 +130,10 @@ def three_interpolate_wrapper(b, c, m, n, points, idx, weight, out):
     dev = _C.require_cuda(points, idx, weight, out)
     _C.require_contiguous(points, idx, weight, out)
     _check(idx.dtype == torch.int32, "three_interpolate: idx must be int32")
+    _check(points.dtype == torch.float32 and weight.dtype == torch.float32 and out.dtype == torch.float32,
+           "three_interpolate: float32 only")
+    _check(points.numel() == b * c * m and idx.numel() == b * n * 3 and weight.numel() == b * n * 3
+           and out.numel() == b * c * n, "three_interpolate: tensor sizes disagree with (b, c, m, n)")
     rc = _C.lib.pp_three_interpolate_fwd(_C.ptr(points), _C.ptr(idx), _C.ptr(weight), b, c, m, n, _C.ptr(out),
                                          dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_three_interpolate_fwd")
@@ -133,6 +145,10 @@ def three_interpolate_grad_wrapper(b, c, n, m, grad_out, idx, weight, grad_point
     dev = _C.require_cuda(grad_out, idx, weight, grad_points)
     _C.require_contiguous(grad_out, idx, weight, grad_points)
     _check(idx.dtype == torch.int32, "three_interpolate_grad: idx must be int32")
+    _check(grad_out.dtype == torch.float32 and weight.dtype == torch.float32 and grad_points.dtype == torch.float32,
+           "three_interpolate_grad: float32 only")
+    _check(grad_out.numel() == b * c * n and idx.numel() == b * n * 3 and weight.numel() == b * n * 3
+           and grad_points.numel() == b * c * m, "three_interpolate_grad: tensor sizes disagree with (b, c, n, m)")
     rc = _C.lib.pp_three_interpolate_bwd(_C.ptr(grad_out), _C.ptr(idx), _C.ptr(weight), b, c, n, m,
                                          _C.ptr(grad_points), dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_three_interpolate_bwd")

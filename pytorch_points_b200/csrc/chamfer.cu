@@ -585,6 +585,24 @@ chamfer_bwd_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz
 
 using namespace pp;
 
+// Debug aid (option "chamfer_ws_check"): verifies the promise a caller makes with PP_CHAMFER_WS_CLEAN.
+// Synchronises the stream; returns the number of 64-bit words that are not all-ones, or -1 on a CUDA error.
+__global__ void keys_check_kernel(const unsigned long long *k, size_t n, unsigned *bad) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (k[i] != 0xffffffffffffffffull) atomicAdd(bad, 1u);
+}
+
+static long long keys_all_ones(const void *workspace, size_t bytes, cudaStream_t st) {
+    unsigned *bad = nullptr, host = 0;
+    if (cudaMalloc(&bad, sizeof(unsigned)) != cudaSuccess) return -1;
+    cudaMemsetAsync(bad, 0, sizeof(unsigned), st);
+    keys_check_kernel<<<296, 256, 0, st>>>((const unsigned long long *)workspace, bytes / 8, bad);
+    const cudaError_t e = cudaMemcpyAsync(&host, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+    const cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(bad);
+    return (e != cudaSuccess || e2 != cudaSuccess) ? -1 : (long long)host;
+}
+
 static size_t chamfer_keys_bytes(int B, int N, int M) {
     return sizeof(unsigned long long) * ((size_t)B * N + (size_t)B * M);
 }
@@ -711,6 +729,8 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     // The finalize kernel leaves the keys all-ones again; callers that own a persistent
     // workspace say so with PP_CHAMFER_WS_CLEAN and save the fill.
     if (!(flags & PP_CHAMFER_WS_CLEAN)) PP_CUDA(cudaMemsetAsync(workspace, 0xff, need, st));
+    else if (get_option("chamfer_ws_check", 0)) PP_REQUIRE(keys_all_ones(workspace, need, st) == 0,
+                                                           "chamfer_fwd: PP_CHAMFER_WS_CLEAN passed but the key workspace is not all-ones");
     if (pick == 0) {
         // Smaller reference blocks keep small clouds spread over all SMs.  A warp takes 32*Q = 256
         // queries: when 4-warp CTAs would leave two or more warp slots of the last query split

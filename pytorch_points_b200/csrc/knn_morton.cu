@@ -676,7 +676,7 @@ struct KmLayout {
 };
 
 // One set of buffers sized for max(nq, np) elements is laid out twice (points, then queries).
-KmLayout km_layout(size_t n) {
+KmLayout km_layout(size_t n, size_t clouds) {
     KmLayout L;
     size_t off = 0;
     L.bbox = off; off = align_up(off + 6 * sizeof(int) + 64, 256);  // + a 64-bit visit counter at byte 32
@@ -686,9 +686,8 @@ KmLayout km_layout(size_t n) {
     L.vals_out = off; off = align_up(off + n * 4, 256);
     L.sorted_xyz = off; off = align_up(off + n * 12, 256);
     L.sorted_idx = off; off = align_up(off + n * 4, 256);
-    // one 32-byte box per tile; clouds on this path hold >= 4096 points, so there are at most
-    // n/KM_TILE + n/4096 tiles
-    L.boxes = off; off = align_up(off + (n / KM_TILE + n / 4096 + 2) * 32, 256);
+    // one 32-byte box per tile: every cloud has ceil(points / KM_TILE) <= points / KM_TILE + 1 tiles
+    L.boxes = off; off = align_up(off + (n / KM_TILE + clouds + 2) * 32, 256);
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (const unsigned long long *)nullptr, (unsigned long long *)nullptr,
                                     (const unsigned *)nullptr, (unsigned *)nullptr, (long long)n, 0, 64);
@@ -729,14 +728,14 @@ double g_knn_tiles_visited = 0, g_knn_tiles_total = 0;
 
 size_t knn_morton_workspace_bytes(int B, int M, int N) {
     const size_t n = (size_t)B * (size_t)(M > N ? M : N);
-    return 2 * km_layout(n).total + 256;
+    return 2 * km_layout(n, (size_t)B).total + 256;
 }
 
 // Returns PP_OK after launching everything, or a negative/positive error.
 int knn_morton_launch(const float *query, const float *points, int B, int M, int N, int k, float *dist, int *idx,
                       void *workspace, size_t workspace_bytes, cudaStream_t st) {
     const size_t n = (size_t)B * (size_t)(M > N ? M : N);
-    const KmLayout L = km_layout(n);
+    const KmLayout L = km_layout(n, (size_t)B);
     unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     if (workspace == nullptr || (size_t)(ws - (unsigned char *)workspace) + 2 * L.total > workspace_bytes) {
         set_error("knn: workspace %zu < %zu bytes", workspace_bytes, 2 * L.total + 256);

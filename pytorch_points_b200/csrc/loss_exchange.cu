@@ -58,7 +58,8 @@ lx_send_kernel(const float *__restrict__ sums, LxMailbox *box, int rank, int wor
 }
 
 __global__ void __launch_bounds__(32)
-lx_wait_kernel(LxMailbox *box, int world, float *__restrict__ out, int *__restrict__ status) {
+lx_wait_kernel(LxMailbox *box, int world, float *__restrict__ out, int *__restrict__ status,
+               unsigned long long timeout_ns) {
     pdl_wait();
     pdl_launch_dependents();
     const int lane = threadIdx.x;
@@ -67,15 +68,20 @@ lx_wait_kernel(LxMailbox *box, int world, float *__restrict__ out, int *__restri
     bool ok = true;
     if (lane < world) {
         const LxSlot *src = &box->slot[seq & 1u][lane];
-        const long long t0 = clock64();
+        unsigned long long t0;  // wall-clock nanoseconds, independent of the SM clock
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         unsigned long long a, b;
         for (;;) {
             a = ld_sys_u64(&src->w0);
             b = ld_sys_u64(&src->w1);
             if ((unsigned)a == seq && (unsigned)b == seq) break;
-            if (clock64() - t0 > 20000000000ll) {  // ~10 s at 1.9 GHz: give up, never hang the GPU
-                ok = false;
-                break;
+            if (timeout_ns != 0ull) {  // 0 = wait for ever, like a blocking collective
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (now - t0 > timeout_ns) {  // give up: NaN sums + sticky status flag, never a hung GPU
+                    ok = false;
+                    break;
+                }
             }
             __nanosleep(64);
         }
@@ -170,8 +176,12 @@ extern "C" int pp_loss_exchange_wait(void *mailbox, int world, float *sums_out, 
     PP_REQUIRE(world >= 1 && world <= LX_MAX_WORLD, "loss_exchange_wait: bad world %d", world);
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
+    // "lx_timeout_ms" (default 600000 = 10 minutes; 0 = unbounded): ordinary rank skew -- a checkpoint, an
+    // evaluation pass on rank 0, a data-loader stall -- must not turn into a NaN loss
+    const long long ms = get_option("lx_timeout_ms", 600000);
+    const unsigned long long timeout_ns = ms <= 0 ? 0ull : (unsigned long long)ms * 1000000ull;
     PP_CUDA(launch_pdl(lx_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (LxMailbox *)mailbox, world, sums_out,
-                       (int *)status));
+                       (int *)status, timeout_ns));
     PP_LAUNCH_CHECK();
     return PP_OK;
 }

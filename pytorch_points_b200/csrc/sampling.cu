@@ -552,6 +552,10 @@ int dispatch_fps(int C, int P, const float *xyz, int B, int N, int m, int seed, 
 
 using namespace pp;
 
+// launch shape of the last FPS call on this thread (pp_fps_last_plan): cluster width (0 = streaming
+// fallback) and points per thread
+static thread_local int g_fps_last_cluster = 0, g_fps_last_points = 0;
+
 static int fps_impl(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,
                     float *new_xyz, int device, void *stream) {
     PP_REQUIRE(B >= 0 && N >= 1, "fps: bad sizes B=%d N=%d", B, N);
@@ -600,6 +604,8 @@ static int fps_impl(const float *xyz, int B, int N, int m, int seed, float *temp
         }
     }
     const int P = ceil_div(N, C * FPS_T);
+    g_fps_last_cluster = (P > 16 || get_option("fps_stream", 0)) ? 0 : C;
+    g_fps_last_points = P;
     if (P > 16 || get_option("fps_stream", 0)) {
         KernelTimer timer("fps", st);
         fps_stream_kernel<<<B, 1024, 0, st>>>(xyz, N, m, seed, temp, idx, new_xyz, bs_log2);
@@ -607,6 +613,12 @@ static int fps_impl(const float *xyz, int B, int N, int m, int seed, float *temp
         return PP_OK;
     }
     return dispatch_fps(C, P, xyz, B, N, m, seed, temp, idx, new_xyz, bs_log2, st, nullptr);
+}
+
+extern "C" int pp_fps_last_plan(int *cluster_width, int *points_per_thread) {
+    if (cluster_width) *cluster_width = g_fps_last_cluster;
+    if (points_per_thread) *points_per_thread = g_fps_last_points;
+    return PP_OK;
 }
 
 extern "C" int pp_fps(const float *xyz, int B, int N, int m, int seed, float *temp, int32_t *idx,

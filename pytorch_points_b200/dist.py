@@ -163,5 +163,21 @@ class LossExchange:
         return out
 
     def timed_out(self):
-        """True if any wait() so far gave up on a peer (synchronises)."""
+        """True if any wait() so far gave up on a peer (synchronises).  The poll is bounded by the
+        library option "lx_timeout_ms" (default 10 minutes, 0 = unbounded); a wait that gives up
+        writes NaN sums and sets this sticky flag."""
         return bool(self.status.item())
+
+    def close(self):
+        """Unmap the peers' mailboxes and free this rank's (synchronises the device).  Every rank
+        should call it once no step is in flight any more; safe to call twice."""
+        if getattr(self, "mailbox", None) is not None and self.mailbox.value:
+            C = self._C
+            C.lib.pp_loss_exchange_close(self.mailbox, self.peers, self.rank, self.world, self.device.index)
+            self.mailbox = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown: the driver reclaims the memory anyway
+            pass

@@ -128,6 +128,13 @@ class QueryAndGroup(torch.nn.Module):
         return grouped_features
 
 
+def _gather_index(idx):
+    """int64 copy of a KNN index tensor that is safe to gather / scatter with: a list slot that found
+    no neighbour (k > N, or non-finite coordinates -- the kernels only accept d < threshold) carries
+    -1 with distance +inf; it is mapped to 0 here instead of tripping a device-side assert."""
+    return idx.long().clamp_(min=0)
+
+
 class _KNNFunction(torch.autograd.Function):
     """dist/idx of the k nearest `points` for every `query` point; distances are differentiable
     w.r.t. both clouds (d/dq = 2 (q - p), d/dp = -2 (q - p))."""
@@ -144,7 +151,7 @@ class _KNNFunction(torch.autograd.Function):
         query, points, idx = ctx.saved_tensors
         B, M, c = query.shape
         k = idx.shape[2]
-        lidx = idx.long()
+        lidx = _gather_index(idx)
         nn = torch.gather(points.unsqueeze(1).expand(B, M, points.shape[1], c), 2,
                           lidx.unsqueeze(-1).expand(B, M, k, c))
         g = 2.0 * grad_dist.unsqueeze(-1) * (query.unsqueeze(2) - nn)  # (B,M,k,c)
@@ -173,7 +180,7 @@ def group_knn(k, query, points, unique=True, NCHW=True):
     B, M, _ = q.shape
     c = p.shape[2]
     nn = torch.gather(p.unsqueeze(1).expand(B, M, p.shape[1], c), 2,
-                      idx.long().unsqueeze(-1).expand(B, M, k, c))  # (B,M,k,C)
+                      _gather_index(idx).unsqueeze(-1).expand(B, M, k, c))  # (B,M,k,C)
     if NCHW:
         nn = nn.permute(0, 3, 1, 2).contiguous()
     return nn, idx, dist
@@ -189,5 +196,5 @@ def knn_points(p1, p2, K=1, return_nn=False):
         B, M, _ = p1.shape
         c = p2.shape[2]
         nn = torch.gather(p2.unsqueeze(1).expand(B, M, p2.shape[1], c), 2,
-                          idx.long().unsqueeze(-1).expand(B, M, K, c))
+                          _gather_index(idx).unsqueeze(-1).expand(B, M, K, c))
     return dist, idx.long(), nn

@@ -117,6 +117,11 @@ class GraphedChamferStep:
         self.grad1 = torch.empty(B, N, 3, device=dev)
         self.grad2 = torch.empty(B, M, 3, device=dev)
         self.sums_host = [torch.zeros(2).pin_memory() for _ in range(2)]  # per buffer set
+        # The step owns its scratch: the graphs bake its address in, nothing else ever writes it, and
+        # every forward leaves the packed keys all-ones again -> filled once, PP_CHAMFER_WS_CLEAN after.
+        from . import _C
+        self.workspace = torch.full((max(int(_C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)), 16),), 0xFF,
+                                    dtype=torch.uint8, device=dev)
         self.compute_stream = torch.cuda.Stream(dev)
         self.copy_stream = torch.cuda.Stream(dev)
         # chamfer_fwd, chamfer_finalize[, chamfer_bwd<0>, chamfer_bwd<1>] (+ lx_send, lx_wait)
@@ -131,10 +136,10 @@ class GraphedChamferStep:
             if self.fused_backward:
                 losses.nmdistance_forward_backward_uniform(self.xyz1[s], self.xyz2[s], self.dist1, self.dist2,
                                                            self.idx1, self.idx2, self.sums, self.gw, self.grad1,
-                                                           self.grad2)
+                                                           self.grad2, workspace=self.workspace, workspace_clean=True)
             else:
                 losses.nmdistance_forward(self.xyz1[s], self.xyz2[s], self.dist1, self.dist2, self.idx1, self.idx2,
-                                          sums=self.sums)
+                                          sums=self.sums, workspace=self.workspace, workspace_clean=True)
 
         def bwd_body(s):
             if not self.fused_backward:
@@ -229,7 +234,11 @@ class GraphedChamferStep:
         until the second `submit()` after it."""
         self.done[ticket].synchronize()
         h = self.sums_host[ticket]
-        return float(h[0]) * self.scale[0] + float(h[1]) * self.scale[1]
+        value = float(h[0]) * self.scale[0] + float(h[1]) * self.scale[1]
+        if value != value and self.exchange is not None and self.exchange.timed_out():
+            raise RuntimeError("GraphedChamferStep: the peer-memory loss exchange gave up waiting for a rank "
+                               "(library option lx_timeout_ms); the loss of this step is undefined")
+        return value
 
     def run(self):
         """One step, blocking: returns the loss (host float) once it is on the host."""
