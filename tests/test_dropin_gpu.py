@@ -12,8 +12,9 @@ The package is imported twice under its own name:
 
 The reference's `nndistance`, `labeled_nndistance`, `furthest_point_sample`, `gather_points`,
 `ball_query`, `QueryAndGroup`, `three_nn` / `three_interpolate`, `PointnetSAModuleMSG`,
-`PointnetSAModule` (GroupAll), `PointnetFPModule` and `DenseEdgeConv` then run UNCHANGED on both and
-must agree: indices and distances bit for bit, gradients to 1e-5 (atomic summation order).
+`PointnetSAModule` (GroupAll) and `PointnetFPModule` then run UNCHANGED on both and must agree: indices
+and distances bit for bit, gradients to 1e-5 (atomic summation order); `pointUniformLaplacian` (a
+pytorch3d.knn_points caller) runs on this repo's KNN against a brute-force restatement.
 Nothing here touches /root/reference at run time.  Skipped when baseline/_ref or oracle/_ref is absent.
 """
 import importlib
@@ -222,18 +223,30 @@ def test_reference_three_nn_interpolate_on_the_plugin(both):
     _grad_close(res[0][3], res[1][3], "three_interpolate grad")
 
 
-def test_reference_dense_edge_conv_on_the_plugin_knn(both):
-    """network/layers.py:24-82 unchanged, with `pytorch3d.ops.knn_points` served by this repo's KNN:
-    the neighbour graph equals a brute-force float64 k-NN with the point itself dropped."""
+def test_reference_knn_callers_on_the_plugin_knn(both):
+    """The snapshot's KNN callers import `pytorch3d.ops.knn_points` (un-vendored, unpinned, not installed:
+    KNN parity is UNPINNED).  Its published contract -- `knn_points(p1 (N,P1,D), p2 (N,P2,D),
+    K, return_nn) -> (dists (N,P1,K) squared L2 ascending, idx int64 (N,P1,K), nn (N,P1,K,D))`,
+    pytorch3d/ops/knn.py -- is what `pytorch_points_b200.network.operations.knn_points` serves.
+      * network/geo_operations.py:128-152 `pointUniformLaplacian` (K = nn_size + 1, self dropped) runs
+        unchanged on it and equals a brute-force float64 restatement;
+      * network/layers.py:41-62 `DenseEdgeConv.get_local_graph` permutes the returned neighbours with
+        (0, 2, 3, 1), which fits the upstream project's own retired group_knn layout, not pytorch3d's:
+        the reference raises on its own shape mismatch whatever serves knn_points (upstream defect,
+        recorded here so that nobody reads it as a plugin failure).  This repo's DenseEdgeConv
+        (tests/test_parity_gpu.py) builds the same graph with the documented layout."""
     ours, _ = both
-    torch.manual_seed(6)
-    B, C, N, k = 2, 3, 1200, 8
-    x = uniform_cloud(B, N, 351).transpose(1, 2).contiguous().cuda().requires_grad_(True)
-    conv = ours.layers.DenseEdgeConv(C, 12, n=3, k=k).cuda()
-    y, idx = conv(x)
-    d = torch.cdist(x.detach().transpose(1, 2).double(), x.detach().transpose(1, 2).double())
-    want = d.topk(k + 1, dim=-1, largest=False).indices[:, :, 1:]
-    assert torch.equal(idx.long(), want)
-    assert y.shape[0] == B and y.shape[2] == N
-    y.square().mean().backward()
-    assert torch.isfinite(x.grad).all() and x.grad.abs().sum() > 0
+    B, N, k = 2, 1500, 5
+    pts = uniform_cloud(B, N, 351).cuda()
+    lap, idx = ours.geo_operations.pointUniformLaplacian(pts, nn_size=k)
+    d = torch.cdist(pts.double(), pts.double())
+    want_idx = d.topk(k + 1, dim=-1, largest=False).indices[:, :, 1:]
+    assert idx.dtype == torch.int64 and torch.equal(idx, want_idx)
+    nbr = torch.gather(pts.unsqueeze(1).expand(B, N, N, 3), 2, want_idx.unsqueeze(-1).expand(B, N, k, 3))
+    assert torch.allclose(lap, pts - nbr.mean(dim=2), rtol=1e-5, atol=1e-6)
+    dists, idx_k, nn = sys.modules["pytorch3d.ops"].knn_points(pts, pts, K=k + 1, return_nn=True)
+    assert dists.shape == (B, N, k + 1) and nn.shape == (B, N, k + 1, 3) and bool((dists[..., 1:] >= dists[..., :-1]).all())
+    assert torch.equal(nn, torch.gather(pts.unsqueeze(1).expand(B, N, N, 3), 2, idx_k.unsqueeze(-1).expand(B, N, k + 1, 3)))
+    conv = ours.layers.DenseEdgeConv(3, 12, n=3, k=k).cuda()
+    with pytest.raises(RuntimeError, match="expanded size"):
+        conv(pts.transpose(1, 2).contiguous())
