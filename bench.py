@@ -120,7 +120,10 @@ def cpu_threads_setup():
     os.environ["OMP_NUM_THREADS"] = str(n)
     os.environ.setdefault("OMP_PROC_BIND", "spread")
     os.environ.setdefault("OMP_WAIT_POLICY", "active")
-    return n
+    import oracle
+    lib = oracle.lib()
+    lib.oracle_set_threads(n)  # libgomp may already have read OMP_NUM_THREADS=1
+    return int(lib.oracle_get_max_threads())
 
 
 def cpu_chamfer_step(a, b, total_batch):

@@ -449,3 +449,14 @@ int oracle_three_interpolate_bwd(const float *grad_out, const int32_t *idx, cons
 }
 
 int oracle_version(void) { return 1; }
+
+/* Thread count of the OpenMP loops above (bench.py's CPU arms: torch.distributed.run exports
+ * OMP_NUM_THREADS=1 and libgomp has usually read it before this library is loaded). */
+#ifdef _OPENMP
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_get_max_threads(void) { return omp_get_max_threads(); }
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_get_max_threads(void) { return 1; }
+#endif
