@@ -716,9 +716,10 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     // 50 = approximate sweep (GEMM-expansion distances on the FFMA pipe) + exact resolution,
     // chamfer_sweep.cu: bit-identical results, measured SLOWER than the exact one-pass kernel below on
     // B200 (profiles/r02_*), so it is an option, not the default.
-    if (pick == 50)
+    // 51 = the same scheme with the distances from tcgen05.mma (3xTF32 split operands, TMEM accumulators).
+    if (pick == 50 || pick == 51)
         return chamfer_sweep_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, sums, workspace, workspace_bytes, gw,
-                                    g1, g2, st);
+                                    g1, g2, st, pick == 51);
     const size_t need = chamfer_keys_bytes(B, N, M);
     if (workspace_bytes < need) {
         set_error("chamfer_fwd: workspace %zu < %zu bytes", workspace_bytes, need);

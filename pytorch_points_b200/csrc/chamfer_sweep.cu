@@ -47,14 +47,18 @@ constexpr int CS_STAGES = 4;   // reference blocks in flight per CTA
 constexpr int CS_RS = 32;      // entries a rescan CTA handles at once
 constexpr unsigned CS_INF_BITS = 0x7f800000u;
 constexpr unsigned long long CS_KEY_INIT = 0x7f800000ffffffffull;
-// TAU = 2.5 * EPS, EPS = 64 u R^2, u = 2^-24
+// TAU = 2.5 * EPS.  FFMA sweep: EPS = 64 u R^2 (u = 2^-24).  Tensor-core sweep (3xTF32 split): the dropped
+// low*low products and the tensor core's accumulation add to the budget: EPS = 128 u R^2.
 constexpr float CS_TAU_PER_R2 = 160.f * 5.9604644775390625e-8f;
+constexpr float CS_TAU_PER_R2_TC = 320.f * 5.9604644775390625e-8f;
 
 // One direction of the problem: `nq` query points (cloud A) against `nr` reference points (cloud B).
 struct CsDir {
     const float *qxyz, *rxyz;        // original clouds (B,nq,3) / (B,nr,3)
     const float4 *qform;             // (B, npad) prepared queries
     const float *rform;              // (B, rblk, 4, 128) prepared references
+    const float *aform;              // (B, ceil(nq/128), 4 chunks, 128 rows, 4) tensor-core A operand of the queries
+    const float *bform;              // (B, rblk, 4 chunks, 128 rows, 4) tensor-core B operand of the references
     unsigned long long *key;         // (B, nq) value bits << 32 | granule
     unsigned *sec;                   // (B, nq) runner-up value bits
     uint2 *list;                     // (B, nq) ambiguous points: (index in cloud, best value bits)
@@ -69,17 +73,19 @@ struct CsDir {
 struct CsArgs {
     CsDir d[2];
     const unsigned *r2bits;  // (B) bits of the largest centred squared norm
+    float tau_per_r2;        // TAU = tau_per_r2 * R^2
+    float rescan_per_r2;     // the rescan's window above the recorded best value (it re-approximates with FFMA)
     float *sums;             // [sum(dist1), sum(dist2)] or null
     const float *gw;         // fused backward weights or null
     int B;
 };
 
 struct CsLayout {
-    size_t ctrl, qform[2], rform[2], key[2], sec[2], list[2], total;
+    size_t ctrl, qform[2], rform[2], key[2], sec[2], list[2], aform[2], bform[2], total;
     int npad[2], blk[2];
 };
 
-CsLayout cs_layout(int B, int N, int M) {
+CsLayout cs_layout(int B, int N, int M, bool tc = false) {
     CsLayout L;
     const int n[2] = {N, M};
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -93,6 +99,11 @@ CsLayout cs_layout(int B, int N, int M) {
         L.key[s] = o;   o += up(8 * (size_t)B * n[s]);
         L.sec[s] = o;   o += up(4 * (size_t)B * n[s]);
         L.list[s] = o;  o += up(8 * (size_t)B * n[s]);
+        L.aform[s] = L.bform[s] = 0;
+        if (tc) {  // 16 tf32 values per point and role
+            L.aform[s] = o; o += up(64 * (size_t)B * L.blk[s] * CS_RB);
+            L.bform[s] = o; o += up(64 * (size_t)B * L.blk[s] * CS_RB);
+        }
     }
     L.total = o;
     return L;
@@ -351,7 +362,7 @@ cs_rowpass_kernel(const CsArgs args) {
     if (!live) return;
 
     // ---- publish (value + |q|^2 + TAU keeps every published value positive: its bits order like values)
-    const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * CS_TAU_PER_R2;
+    const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * args.tau_per_r2;
     unsigned long long *K = D.key + (size_t)b * D.nq;
     unsigned *S = D.sec + (size_t)b * D.nq;
     unsigned long long key[8], old[8];
@@ -385,6 +396,223 @@ cs_rowpass_kernel(const CsArgs args) {
     }
 }
 
+// ---- the one-sided pass on the tensor cores (chamfer_variant 51) ----------------------------------
+// Same contract as cs_rowpass_kernel, but e = |r|^2 - 2 q.r comes out of tcgen05.mma (kind::tf32, fp32
+// accumulators in TMEM) instead of 3 FFMA per pair.  fp32 accuracy from TF32 operands by splitting every
+// coordinate into hi + lo (each exactly representable in TF32) and spending 12 of K = 16 slots:
+//      A row (query):     qh.x qh.y qh.z qh.x | qh.y qh.z ql.x ql.y | ql.z 1 1 1 | 0 0 0 0        (q = -2 * centred point)
+//      B row (reference): rh.x rh.y rh.z rl.x | rl.y rl.z rh.x rh.y | rh.z n0 n1 n2 | 0 0 0 0    (|r|^2 = n0 + n1 + n2)
+// -> sum = qh.rh + qh.rl + ql.rh + |r|^2; only ql.rl (<= 2^-22 |q||r|) is dropped.  Every product of two
+// TF32 values is exact in fp32; what the tensor core's adder tree loses is covered by EPS.
+// Operands are K-major without swizzle: 16-byte chunk c of row r sits at c * 2048 + r * 16 of an 8 KB
+// tile (8 rows x 16 B core matrices, SBO = 128 B, LBO = 2048 B), so ONE cp.async.bulk moves a whole block.
+// CTA = 128 queries (TMEM lane = query) x a chunk of 128-reference blocks; 6 warps: 0-3 epilogue (each
+// reads its 32 lanes with tcgen05.ld 32x32b.x32 and keeps one query per thread), 4 = copy issuer + TMEM
+// owner, 5 = MMA issuer.  Two 128-column accumulators alternate, so the MMA of block i+1 runs while
+// block i is scanned; 256 TMEM columns per CTA -> two CTAs per SM.
+constexpr int TC_STAGES = 3;         // B blocks in flight
+constexpr int TC_TILE_BYTES = 8192;  // 128 rows x 16 tf32
+
+__device__ __forceinline__ float to_tf32(float v) {  // round to nearest TF32; the low 13 bits come out zero
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// grid (ceil(npad/256), B, 2): blockIdx.z = cloud.  Reads the query form written by cs_prep_kernel.
+__global__ void __launch_bounds__(256)
+cs_prep_tc_kernel(const float4 *__restrict__ qf0, const float4 *__restrict__ qf1, int N, int M,
+                  float *__restrict__ af0, float *__restrict__ af1, float *__restrict__ bf0, float *__restrict__ bf1) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int b = blockIdx.y, s = blockIdx.z;
+    const int n = s ? M : N;
+    const int npad = ceil_div(n, CS_WT) * CS_WT, rows = ceil_div(n, CS_RB) * CS_RB;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float4 q = (s ? qf1 : qf0)[(size_t)b * npad + i];  // {-2x, -2y, -2z, |p|^2}; padding: {0,0,0,inf}
+    float *at = (s ? af1 : af0) + ((size_t)b * (rows / CS_RB) + i / CS_RB) * (TC_TILE_BYTES / 4) + (i % CS_RB) * 4;
+    float *bt = (s ? bf1 : bf0) + ((size_t)b * (rows / CS_RB) + i / CS_RB) * (TC_TILE_BYTES / 4) + (i % CS_RB) * 4;
+    const bool pad = i >= n;
+    const float qhx = to_tf32(q.x), qhy = to_tf32(q.y), qhz = to_tf32(q.z);
+    const float qlx = to_tf32(q.x - qhx), qly = to_tf32(q.y - qhy), qlz = to_tf32(q.z - qhz);
+    const float x = -0.5f * q.x, y = -0.5f * q.y, z = -0.5f * q.z;  // exact
+    const float rhx = to_tf32(x), rhy = to_tf32(y), rhz = to_tf32(z);
+    const float rlx = to_tf32(x - rhx), rly = to_tf32(y - rhy), rlz = to_tf32(z - rhz);
+    // padding references carry a huge (finite, TF32-exact) norm: never a minimum, no inf * 0 in the MMA
+    const float nn = pad ? 1.0e30f : q.w;
+    const float n0 = to_tf32(nn), n1 = pad ? 0.f : to_tf32(nn - n0), n2 = pad ? 0.f : to_tf32(nn - n0 - n1);
+    constexpr int CH = TC_TILE_BYTES / 16;  // floats between two 16-byte chunks of one row
+    *reinterpret_cast<float4 *>(at) = make_float4(qhx, qhy, qhz, qhx);
+    *reinterpret_cast<float4 *>(at + CH) = make_float4(qhy, qhz, qlx, qly);
+    *reinterpret_cast<float4 *>(at + 2 * CH) = make_float4(qlz, 1.f, 1.f, 1.f);
+    *reinterpret_cast<float4 *>(at + 3 * CH) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4 *>(bt) = make_float4(rhx, rhy, rhz, rlx);
+    *reinterpret_cast<float4 *>(bt + CH) = make_float4(rly, rlz, rhx, rhy);
+    *reinterpret_cast<float4 *>(bt + 2 * CH) = make_float4(rhz, n0, n1, n2);
+    *reinterpret_cast<float4 *>(bt + 3 * CH) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// shared-memory matrix descriptor of a K-major, un-swizzled 128-row operand tile (layout above)
+__device__ __forceinline__ unsigned long long tc_smem_desc(unsigned smem_addr) {
+    return (unsigned long long)((smem_addr >> 4) & 0x3fffu)        // start address
+           | ((unsigned long long)((CS_RB * 16) >> 4) << 16)      // leading byte offset: next 16-byte K chunk
+           | ((unsigned long long)(128 >> 4) << 32)               // stride byte offset: next 8-row core matrix
+           | (1ull << 46);                                        // descriptor version (Blackwell); no swizzle
+}
+
+__device__ __forceinline__ void tc_mma_tf32(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                            unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(unsigned bar) {  // the mbarrier completes when every MMA issued so far has
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, float (&v)[32]) {
+    unsigned r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(192, 2)
+cs_rowpass_tc_kernel(const CsArgs args) {
+    __shared__ __align__(128) unsigned char sA[TC_TILE_BYTES];
+    __shared__ __align__(128) unsigned char sB[TC_STAGES][TC_TILE_BYTES];
+    // a_full | b_full[S] | b_empty[S] | t_full[2] | t_empty[2]
+    __shared__ __align__(8) unsigned long long sBar[1 + 2 * TC_STAGES + 4];
+    __shared__ unsigned sTmem;
+
+    pdl_launch_dependents();
+    const CsDir &D = args.d[blockIdx.z];
+    const int b = blockIdx.y;
+    if ((int)blockIdx.x >= D.tiles * D.nchunks) return;
+    const int tile = blockIdx.x / D.nchunks, chunk = blockIdx.x % D.nchunks;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int blk0 = chunk * D.chunk_blocks;
+    const int nblk = min(D.rblk, blk0 + D.chunk_blocks) - blk0;
+    const unsigned bar_a = smem_u32(sBar), bar_bf = smem_u32(sBar + 1), bar_be = smem_u32(sBar + 1 + TC_STAGES);
+    const unsigned bar_tf = smem_u32(sBar + 1 + 2 * TC_STAGES), bar_te = smem_u32(sBar + 3 + 2 * TC_STAGES);
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+#pragma unroll
+        for (int i = 0; i < TC_STAGES; i++) { mbar_init(bar_bf + 8 * i, 1); mbar_init(bar_be + 8 * i, 1); }
+#pragma unroll
+        for (int i = 0; i < 2; i++) { mbar_init(bar_tf + 8 * i, 1); mbar_init(bar_te + 8 * i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (w == 4) {  // one warp owns the tensor-memory allocation: 256 columns = two 128-column accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&sTmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = sTmem;
+    pdl_wait();  // the prepared operands, R^2 and the reset keys are complete and visible
+
+    if (w == 4) {
+        if (lane == 0) {  // ---- copy issuer: the query tile once, then the reference blocks through the ring
+            mbar_expect_tx(bar_a, TC_TILE_BYTES);
+            bulk_g2s(smem_u32(sA), D.aform + ((size_t)b * D.tiles + tile) * (TC_TILE_BYTES / 4), TC_TILE_BYTES, bar_a);
+            const float *src = D.bform + ((size_t)b * D.rblk + blk0) * (TC_TILE_BYTES / 4);
+            for (int i = 0; i < nblk; i++) {
+                const int st = i % TC_STAGES;
+                if (i >= TC_STAGES) mbar_wait(bar_be + 8 * st, (unsigned)(i / TC_STAGES - 1) & 1u);
+                mbar_expect_tx(bar_bf + 8 * st, TC_TILE_BYTES);
+                bulk_g2s(smem_u32(sB[st]), src + (size_t)i * (TC_TILE_BYTES / 4), TC_TILE_BYTES, bar_bf + 8 * st);
+            }
+        }
+    } else if (w == 5) {
+        if (lane == 0) {  // ---- MMA issuer: D[128 x 128] = A[128 x 16] * B[128 x 16]^T as two K = 8 instructions
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+            constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+            const unsigned long long adesc = tc_smem_desc(smem_u32(sA));
+            mbar_wait(bar_a, 0);
+            for (int i = 0; i < nblk; i++) {
+                const int st = i % TC_STAGES, acc = i & 1;
+                mbar_wait(bar_bf + 8 * st, (unsigned)(i / TC_STAGES) & 1u);
+                if (i >= 2) mbar_wait(bar_te + 8 * acc, (unsigned)(i / 2 - 1) & 1u);  // the epilogue drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned long long bdesc = tc_smem_desc(smem_u32(sB[st]));
+                const unsigned d = tmem + (unsigned)acc * 128u;
+                // descriptor start addresses count 16-byte units: K chunks 2 and 3 start 2 * 2048 B further on
+                tc_mma_tf32(d, adesc, bdesc, idesc, 0u);
+                tc_mma_tf32(d, adesc + (2 * 2048 >> 4), bdesc + (2 * 2048 >> 4), idesc, 1u);
+                tc_commit(bar_be + 8 * st);   // the block's shared-memory stage is free once both MMAs have read it
+                tc_commit(bar_tf + 8 * acc);  // ... and the accumulator is complete
+            }
+        }
+    } else {
+        // ---- epilogue warps: thread = query = TMEM lane.  Per block four granules of 32 references.
+        const int i_q = tile * CS_RB + (int)threadIdx.x;
+        float best = PP_INF, second = PP_INF;
+        int gran = 0;
+        for (int i = 0; i < nblk; i++) {
+            const int acc = i & 1;
+            mbar_wait(bar_tf + 8 * acc, (unsigned)(i / 2) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned t0 = tmem + ((unsigned)(w * 32) << 16) + (unsigned)acc * 128u;
+#pragma unroll
+            for (int gi = 0; gi < CS_RB / CS_GR; gi++) {
+                float v[32];
+                tc_ld32(t0 + gi * CS_GR, v);
+                float m0 = fmin3(v[0], v[1], v[2]), m1 = fmin3(v[3], v[4], v[5]);
+                float m2 = fmin3(v[6], v[7], v[8]), m3 = fmin3(v[9], v[10], v[11]);
+                m0 = fmin3(m0, v[12], v[13]); m1 = fmin3(m1, v[14], v[15]);
+                m2 = fmin3(m2, v[16], v[17]); m3 = fmin3(m3, v[18], v[19]);
+                m0 = fmin3(m0, v[20], v[21]); m1 = fmin3(m1, v[22], v[23]);
+                m2 = fmin3(m2, v[24], v[25]); m3 = fmin3(m3, v[26], v[27]);
+                m0 = fmin3(m0, v[28], v[29]); m1 = fmin3(m1, v[30], v[31]);
+                const float gm = fminf(fmin3(m0, m1, m2), m3);
+                const int gid = (blk0 + i) * (CS_RB / CS_GR) + gi;
+                second = fminf(second, fmaxf(best, gm));
+                if (gm < best) gran = gid;
+                best = fminf(best, gm);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_te + 8 * acc);
+        }
+        if (i_q < D.nq) {
+            const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * args.tau_per_r2;
+            const float qq = __fadd_rn(__ldg(&D.qform[(size_t)b * D.npad + i_q].w), tau);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(__fadd_rn(best, qq)) << 32) | (unsigned)gran;
+            const unsigned sb = __float_as_uint(__fadd_rn(second, qq));
+            unsigned long long *K = D.key + (size_t)b * D.nq + i_q;
+            unsigned *S = D.sec + (size_t)b * D.nq + i_q;
+            if (D.nchunks == 1) {
+                *K = key; *S = sb;
+            } else {
+                const unsigned long long old = atomicMin(K, key);
+                atomicMin(S, min((unsigned)((old > key ? old : key) >> 32), sb));
+            }
+        }
+    }
+    // every tcgen05 operation of this CTA has completed (the epilogue waited for the last accumulator)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 // ---- exact resolution ------------------------------------------------------------------------------
 // One launch for both directions: blocks [0, blocks0) take the points of cloud 1 (dist1 / idx1), the
 // rest those of cloud 2.  A warp takes 32 points; for each, its 32 lanes evaluate the 32 references of
@@ -407,7 +635,7 @@ cs_finalize_kernel(const CsArgs args, int blocks0) {
         const unsigned vb = (unsigned)(key >> 32);
         gran = (int)(unsigned)key;
         b = (int)(t / D.nq);
-        const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * CS_TAU_PER_R2;
+        const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * args.tau_per_r2;
         if (sec <= __float_as_uint(__fadd_rn(__uint_as_float(vb), tau))) {
             const unsigned pos = atomicAdd(D.count + b, 1u);
             D.list[(size_t)b * D.nq + pos] = make_uint2((unsigned)(t - (long long)b * D.nq), vb);
@@ -482,7 +710,7 @@ cs_rescan_kernel(const CsArgs args) {
     const CsDir &D = args.d[blockIdx.z];
     const int b = blockIdx.y;
     const unsigned n = __ldcg(D.count + b);
-    const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * CS_TAU_PER_R2;
+    const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * args.tau_per_r2;
     const float *rf = D.rform + (size_t)b * D.rblk * (4 * CS_RB);
     const float *rx = D.rxyz + (size_t)b * D.nr * 3;
     for (unsigned e0 = blockIdx.x * CS_RS; e0 < n; e0 += gridDim.x * CS_RS) {
@@ -496,7 +724,7 @@ cs_rescan_kernel(const CsArgs args) {
                 // recorded value = rn(e_best + qq), qq = rn(|q|^2 + TAU).  Candidates: rn(e + qq) <= value + TAU.
                 // Tested as e <= thr_e with thr_e rounded up generously (a superset is harmless).
                 const float qq = __fadd_rn(q.w, tau);
-                const float lim = __fadd_rn(__uint_as_float(ent.y), tau);
+                const float lim = __fadd_rn(__uint_as_float(ent.y), __uint_as_float(__ldcg(args.r2bits + b)) * args.rescan_per_r2);
                 float thr_e = __fsub_ru(lim, qq);
                 thr_e = __fadd_ru(thr_e, fmaxf(fabsf(lim), fabsf(qq)) * 2.4e-7f);
                 v = make_float4(q.x, q.y, q.z, thr_e);
@@ -546,13 +774,13 @@ cs_rescan_kernel(const CsArgs args) {
 
 }  // namespace
 
-size_t chamfer_sweep_workspace_bytes(int B, int N, int M) { return cs_layout(B, N, M).total; }
+size_t chamfer_sweep_workspace_bytes(int B, int N, int M) { return cs_layout(B, N, M, true).total; }
 
 // gw / g1 / g2 != nullptr: fused uniform backward.  `sums` has been cleared by the caller.
 int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int M, float *dist1, float *dist2,
                          int *idx1, int *idx2, float *sums, void *workspace, size_t workspace_bytes,
-                         const float *gw, float *g1, float *g2, cudaStream_t st) {
-    const CsLayout L = cs_layout(B, N, M);
+                         const float *gw, float *g1, float *g2, cudaStream_t st, bool tc) {
+    const CsLayout L = cs_layout(B, N, M, tc);
     if (workspace_bytes < L.total) {
         set_error("chamfer_fwd: workspace %zu < %zu bytes", workspace_bytes, L.total);
         return PP_ENOSPC;
@@ -563,6 +791,11 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
     unsigned *r2bits = (unsigned *)(ws + L.ctrl);
     CsArgs A;
     A.r2bits = r2bits; A.sums = sums; A.gw = gw; A.B = B;
+    A.tau_per_r2 = tc ? CS_TAU_PER_R2_TC : CS_TAU_PER_R2;
+    // FFMA sweep: the rescan recomputes the sweep's own values -> the same window.  Tensor-core sweep: the
+    // rescan's FFMA value of the true minimiser may sit EPS_tc + EPS_ffma above its tensor-core value, which
+    // itself is within 2 EPS_tc of the recorded best: 3 * 128 u + 64 u, rounded up to 560 u.
+    A.rescan_per_r2 = tc ? 560.f * 5.9604644775390625e-8f : CS_TAU_PER_R2;
     const int n[2] = {N, M};
     const float *xyz[2] = {xyz1, xyz2};
     float *dist[2] = {dist1, dist2};
@@ -583,6 +816,8 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
         D.qxyz = xyz[s]; D.rxyz = xyz[1 - s];
         D.qform = (const float4 *)(ws + L.qform[s]);
         D.rform = (const float *)(ws + L.rform[1 - s]);
+        D.aform = (const float *)(ws + L.aform[s]);
+        D.bform = (const float *)(ws + L.bform[1 - s]);
         D.key = (unsigned long long *)(ws + L.key[s]);
         D.sec = (unsigned *)(ws + L.sec[s]);
         D.list = (uint2 *)(ws + L.list[s]);
@@ -591,7 +826,7 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
         D.gq = g[s]; D.gr = g[1 - s];
         D.nq = n[s]; D.nr = n[1 - s];
         D.npad = L.npad[s]; D.rblk = L.blk[1 - s];
-        D.tiles = ceil_div(n[s], CS_WT * warps);
+        D.tiles = tc ? ceil_div(n[s], CS_RB) : ceil_div(n[s], CS_WT * warps);
         const long long base = 2ll * B * D.tiles;
         int chunks = (int)ceil_div_ll(want_ctas, base);
         const int max_chunks = max(1, D.rblk / 4);  // at least four blocks (512 references) per chunk
@@ -615,9 +850,20 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
             (unsigned *)(ws + L.sec[0]), (unsigned *)(ws + L.sec[1]), r2bits, g[0], g[1]);
         PP_LAUNCH_CHECK();
     }
+    if (tc) {
+        KernelTimer timer("chamfer_prep_tc", st);
+        const int rows = max(L.blk[0], L.blk[1]) * CS_RB;
+        PP_CUDA(launch_pdl(cs_prep_tc_kernel, dim3(ceil_div(rows, 256), B, 2), dim3(256), 0, st,
+                           (const float4 *)(ws + L.qform[0]), (const float4 *)(ws + L.qform[1]), N, M,
+                           (float *)(ws + L.aform[0]), (float *)(ws + L.aform[1]), (float *)(ws + L.bform[0]),
+                           (float *)(ws + L.bform[1])));
+        PP_LAUNCH_CHECK();
+    }
     {
         KernelTimer timer("chamfer_fwd", st);
-        if (warps == 4)
+        if (tc)
+            PP_CUDA(launch_pdl(cs_rowpass_tc_kernel, dim3(grid_x, B, 2), dim3(192), 0, st, A));
+        else if (warps == 4)
             PP_CUDA(launch_pdl(cs_rowpass_kernel<4>, dim3(grid_x, B, 2), dim3(128), 0, st, A));
         else
             PP_CUDA(launch_pdl(cs_rowpass_kernel<2>, dim3(grid_x, B, 2), dim3(64), 0, st, A));
