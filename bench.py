@@ -22,8 +22,9 @@ Legs printed in ONE JSON line by rank 0:
             `sharded_chamfer_loss`, `loss.backward()`, and every step's loss read on the host
             (one step behind, like a logging training loop); the CUDA-graph pipeline
             (`pipeline.GraphedChamferStep`) and the plugin-level calls are reported next to it;
-  roofline  dominant kernel (chamfer_fwd_kernel), duration from CUDA events on the launching
-            stream (library timing hooks), against the FP32 pipe peak measured live;
+  roofline  dominant kernel (cs_rowpass_tc_kernel: tensor-core sweep; chamfer_fwd_kernel for small clouds),
+            duration from CUDA events on the launching stream (library timing hooks); algorithmic 8 FLOP per
+            unique pair against the FP32 pipe peak measured live, plus the TMEM-read and tensor-pipe figures;
   cpu_baseline  the CPU oracle port (oracle/pp_oracle.c, OpenMP) on the box's host cores;
   extras    (N=1 only) the other BASELINE.json configs: Chamfer B=32 N=M=8192, FPS
             16384->1024 + ball_query (B=16), group_knn k=16 (B=32 N=8192; B=4 N=131072).
@@ -518,10 +519,12 @@ def main():
     # separate short pass with the library's per-kernel CUDA events switched on, so the event
     # records do not perturb the two timed legs above
     _C.set_option("timing", 1)
-    for nm in ("chamfer_fwd", "chamfer_finalize", "chamfer_bwd"):
+    knames = ("chamfer_prep", "chamfer_fwd", "chamfer_finalize", "chamfer_rescan", "chamfer_bwd")
+    for nm in knames:
         _C.timing_collect(nm)
     timed(step_device, min(args.steps, 50), 3)
-    kt = {nm: _C.timing_collect(nm) for nm in ("chamfer_fwd", "chamfer_finalize", "chamfer_bwd")}
+    kt = {nm: _C.timing_collect(nm) for nm in knames}
+    tensor_path = bool(_C.lib.pp_chamfer_last_path())
     _C.set_option("timing", 0)
     clocks = sampler.stop()
     loss_dev = float((total[0] / (total_B * N) + total[1] / (total_B * M)).item())
@@ -542,11 +545,12 @@ def main():
     pipe_pairs = mix_pairs / (mix_ms * 1e-3)
     achieved = flops_per_launch / (fwd_ms * 1e-3) / 1e12
     # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload -- used only
-    # if it was taken from the kernel source that is running now (hash of csrc/chamfer.cu)
+    # if it was taken from the kernel source that is running now (hash of csrc/chamfer.cu + chamfer_sweep.cu)
     traffic, traffic_note = None, "no ncu capture committed for this workload"
     try:
         import hashlib
-        sha = hashlib.sha256(open(os.path.join(ROOT, "pytorch_points_b200", "csrc", "chamfer.cu"), "rb").read()).hexdigest()[:16]
+        sha = hashlib.sha256(b"".join(open(os.path.join(ROOT, "pytorch_points_b200", "csrc", f), "rb").read()
+                                      for f in ("chamfer.cu", "chamfer_sweep.cu"))).hexdigest()[:16]
         ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(args.workload)
         if ent:
             if ent.get("chamfer_cu_sha16") == sha:
@@ -556,23 +560,57 @@ def main():
                 traffic_note = "stale capture (kernel source changed since %s): not reported" % ent.get("capture", "?")
     except Exception as e:  # noqa: BLE001
         traffic_note = "unreadable profiles/ncu_summary.json: %r" % (e,)
+    per = lambda nm: kt[nm][0] / max(kt[nm][1], 1)
+    others = {("chamfer_finalize(+fused backward)" if fused else "chamfer_finalize"): per("chamfer_finalize")}
+    if not fused:
+        others["chamfer_bwd(2 launches)"] = per("chamfer_bwd")
+    if tensor_path:
+        others["cs_prep_kernel"] = per("chamfer_prep")
+        others["cs_rescan_kernel"] = per("chamfer_rescan")
     roofline = {
-        "kernel": "chamfer_fwd_kernel", "bound": "fp32", "achieved": achieved, "peak": peak_tflops,
+        "kernel": "cs_rowpass_tc_kernel" if tensor_path else "chamfer_fwd_kernel",
+        "bound": "tensor" if tensor_path else "fp32",
+        "achieved": achieved, "peak": peak_tflops,
         "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic, "traffic_note": traffic_note,
-        "peak_source": "FFMA peak measured live by pp_microbench (MEASURED_PEAKS.json holds no FP32 entry)",
+        "peak_source": "FP32 FFMA peak measured live by pp_microbench (MEASURED_PEAKS.json holds no FP32 entry); achieved = "
+                       "ALGORITHMIC work, 8 FLOP per unique pair (SURVEY.md 8d), per launch / CUDA-event duration",
         "kernel_ms": fwd_ms, "kernel_launches_timed": kt["chamfer_fwd"][1],
         "algorithmic_flop_per_launch": flops_per_launch,
         "pair_rate": B * N * M / (fwd_ms * 1e-3),
         "op_mix_ceiling_pairs_per_s": pipe_pairs,
         "frac_of_op_mix_ceiling": B * N * M / (fwd_ms * 1e-3) / pipe_pairs,
-        "note": "the reference rounding order needs 6 FP32 lane-ops per pair (3 sub, 1 mul, 2 fma = 8 FLOP in "
-                "12 FLOP slots), so 0.667 of the FFMA peak is the hard ceiling; op_mix_ceiling is that bound "
-                "measured live with the packed FADD2/FMUL2/FFMA2+FMNMX3 mix",
-        "other_kernels_ms": ({"chamfer_finalize(+fused backward)": kt["chamfer_finalize"][0] / max(kt["chamfer_finalize"][1], 1)}
-                             if fused else
-                             {"chamfer_finalize": kt["chamfer_finalize"][0] / max(kt["chamfer_finalize"][1], 1),
-                              "chamfer_bwd(2 launches)": kt["chamfer_bwd"][0] / max(kt["chamfer_bwd"][1], 1)}),
+        "other_kernels_ms": others,
     }
+    if tensor_path:
+        # what actually bounds the tensor-core sweep: every accumulator element (one per pair and direction) is read
+        # out of TMEM once, 4 bytes, at 64 B/clk per SM sub-partition (B300_MICROARCH.md: LDTM throughput)
+        clk = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965) * 1e6
+        tmem_peak = 148 * 4 * 64.0 * clk
+        tmem_bytes = 2.0 * 4.0 * B * N * M
+        mma_flop = 2.0 * 2.0 * 16.0 * B * N * M  # two directions, K = 16 (3xTF32 split + norms, padded)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        roofline.update({
+            "note": "distances come from tcgen05.mma kind::tf32 (3xTF32-split operands, K = 16, accumulators in TMEM); the FP32 "
+                    "pipe only resolves the surviving candidates exactly, so the algorithmic 8-FLOP/pair rate is no longer "
+                    "tied to the 0.667 ceiling of the exact FFMA chain.  The kernel's own bound is the TMEM read path: "
+                    "see tmem_read_frac",
+            "tmem_read_bytes_per_launch": tmem_bytes,
+            "tmem_read_TBps": tmem_bytes / (fwd_ms * 1e-3) / 1e12,
+            "tmem_read_peak_TBps": tmem_peak / 1e12,
+            "tmem_read_frac": tmem_bytes / (fwd_ms * 1e-3) / tmem_peak,
+            "tensor_flop_per_launch_executed": mma_flop,
+            "tensor_TFLOPs_executed": mma_flop / (fwd_ms * 1e-3) / 1e12,
+            "tensor_frac_of_measured_bf16_peak": (mma_flop / (fwd_ms * 1e-3) / 1e12 / peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None,
+            "tensor_peak_note": "kind::tf32 runs at half the bf16 rate; MEASURED_PEAKS.json holds the bf16 figure only",
+        })
+    else:
+        roofline["note"] = ("the reference rounding order needs 6 FP32 lane-ops per pair (3 sub, 1 mul, 2 fma = 8 FLOP in "
+                            "12 FLOP slots), so 0.667 of the FFMA peak is the hard ceiling; op_mix_ceiling is that bound "
+                            "measured live with the packed FADD2/FMUL2/FFMA2+FMNMX3 mix")
 
     line = {
         "metric": "chamfer_fwd_bwd_point_pairs_per_s", "value": pairs_per_step / (ms_step * 1e-3),
@@ -604,10 +642,13 @@ def main():
                                       "nmdistance_backward_uniform (the reference-shaped plugin boundary) + D2H of the loss sums"},
                 "timing": "one CUDA-event region over all K steps; every step copies its inputs from pinned host memory and has its loss read on the host"},
         "fused_step": {"state": fused_note, "ms_per_step_four_launch_sequence": ms_step_unfused},
-        "gpu_launches": ((2 if fused else 4) + (2 if exchange is not None else 0)) * args.steps,
-        "gpu_launches_note": ("per step: chamfer_fwd_kernel, chamfer_finalize_kernel<fused backward>" if fused else
-                              "per step: chamfer_fwd_kernel, chamfer_finalize_kernel, chamfer_bwd_kernel<0>, <1>")
-                             + (", lx_send_kernel, lx_wait_kernel" if exchange is not None else ""),
+        "gpu_launches": (((4 if fused else 6) if tensor_path else (2 if fused else 4)) + (2 if exchange is not None else 0)) * args.steps,
+        "gpu_launches_note": ("per step: " + (("cs_prep_kernel, cs_rowpass_tc_kernel, cs_finalize_kernel" +
+                                               ("<fused backward>" if fused else "") + ", cs_rescan_kernel")
+                                              if tensor_path else
+                                              ("chamfer_fwd_kernel, chamfer_finalize_kernel" + ("<fused backward>" if fused else "")))
+                              + ("" if fused else ", chamfer_bwd_kernel<0>, <1>")
+                              + (", lx_send_kernel, lx_wait_kernel" if exchange is not None else "")),
         "clocks": clocks, "roofline": roofline,
         "loss": {"device_leg": loss_dev, "e2e_plugin_leg": loss_e2e, "e2e_graph_leg": loss_graph},
     }

@@ -41,8 +41,9 @@ const char *pp_last_error_string(void);
 /* ------------------------------------------------------------------ losses */
 
 /* Scratch bytes pp_chamfer_fwd needs for (B,N,M): the larger of the exact one-pass kernel's packed
- * keys (8 per point of either cloud) and the sweep path's layout (chamfer_variant 50: prepared
- * clouds in query and reference form, keys, runner-up words and rescan lists, about 52 per point). */
+ * keys (8 per point of either cloud) and the tensor-core sweep's layout (operand tiles of every point
+ * in query and in reference role, norms, keys, runner-up words, block masks, rescan lists: about 160
+ * per point, clouds padded to multiples of 128). */
 size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M);
 
 /*
@@ -58,6 +59,10 @@ size_t pp_chamfer_fwd_workspace_bytes(int B, int N, int M);
  *   successful pp_chamfer_fwd calls on the same stream (each call restores that state).
  */
 #define PP_CHAMFER_WS_CLEAN 1
+/* Which forward the last pp_chamfer_fwd / pp_chamfer_fwd_bwd_uniform call on this thread ran (diagnostics;
+ * bench.py labels its roofline with it): 0 = exact FFMA one-pass kernel (or the generic c != 3 kernel),
+ * 1 = tensor-core sweep (tcgen05.mma kind::tf32 into TMEM) + exact resolution.  Same results either way. */
+int pp_chamfer_last_path(void);
 int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
                    float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,
                    void *workspace, size_t workspace_bytes, int flags, int device, void *stream);
@@ -293,16 +298,17 @@ int pp_knn_stats(double *tiles_visited, double *tiles_total);
  * Process-wide integer options (diagnostics and A/B switches; results never depend on them):
  *   "timing" (0)                 per-kernel CUDA events, see pp_timing_collect
  *   "pdl" (1)                    programmatic dependent launch of the short follow-up kernels
- *   "chamfer_variant" (0)        0 = automatic (1 above 4096 points, else 32 / 35); 1 / 2 = 256- /
+ *   "chamfer_variant" (0)        0 = automatic: the tensor-core sweep (51) from "chamfer_tc_min_pairs"
+ *                                (default 2048 * 2048) pairs per cloud on, else the exact FFMA kernel
+ *                                (1 above 4096 points, else 32 / 35); 51 = tensor-core sweep: distances
+ *                                from tcgen05.mma (3xTF32-split operands, TMEM accumulators), exact
+ *                                resolution of the surviving candidates, identical results; 1 / 2 = 256- /
  *                                128-point reference blocks, 128-thread CTAs; 5 = 128-point
  *                                blocks, 64-thread CTAs; 21 / 22 / 25 = 1 / 2 / 5 with the
  *                                query tile staged through shared memory; 31 / 32 / 35 = those
  *                                with the election-free column publish; 13 / 14 = 1 / 2
- *                                without the per-warp sweep rotation; 50 = approximate
- *                                sweep (GEMM-expansion distances on the FFMA pipe, TMA-fed
- *                                reference ring) + exact resolution: identical results,
- *                                measured slower on B200
- *   "chamfer_sweep_warps" (0), "chamfer_sweep_ctas_per_sm" (10/20)   launch shape of variant 50
+ *                                without the per-warp sweep rotation
+ *   "chamfer_sweep_ctas_per_sm" (8)   CTA target of the tensor-core sweep (reference chunks per query tile)
  *   "chamfer_noelect" (1)        automatic choice below 4097 points uses 32 / 35 (1) or 22 / 25 (0)
  *   "chamfer_blocks_per_sm" (24) target CTA count per SM for the query split heuristic
  *   "chamfer_generic" (0)        force the generic (any point dimension) kernel

@@ -20,6 +20,7 @@ SIGNATURES = {
     "pp_version": (_i, []),
     "pp_last_error_string": (ctypes.c_char_p, []),
     "pp_chamfer_fwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pp_chamfer_last_path": (_i, []),
     "pp_chamfer_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "pp_chamfer_labeled_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "pp_chamfer_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp]),

@@ -682,6 +682,10 @@ static int launch_generic(bool labeled, const float *xyz1, const float *xyz2, co
     return PP_OK;
 }
 
+// which forward the last pp_chamfer_fwd / pp_chamfer_fwd_bwd_uniform call on this thread ran (pp_chamfer_last_path):
+// 0 = exact FFMA one-pass kernel (or the generic kernel), 1 = tensor-core sweep + exact resolution
+static thread_local int g_chamfer_last_path = 0;
+
 // gw/g1/g2 != nullptr: the fused forward + uniform backward (c == 3 only).
 static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
                             float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,
@@ -713,13 +717,16 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     }
     PP_REQUIRE(workspace != nullptr && ((uintptr_t)workspace & 15) == 0, "chamfer_fwd: workspace null or misaligned");
     int pick = get_option("chamfer_variant", 0);
-    // 50 = approximate sweep (GEMM-expansion distances on the FFMA pipe) + exact resolution,
-    // chamfer_sweep.cu: bit-identical results, measured SLOWER than the exact one-pass kernel below on
-    // B200 (profiles/r02_*), so it is an option, not the default.
-    // 51 = the same scheme with the distances from tcgen05.mma (3xTF32 split operands, TMEM accumulators).
-    if (pick == 50 || pick == 51)
+    // Tensor-core path (chamfer_sweep.cu): approximate sweep with tcgen05.mma + exact resolution, bit-identical
+    // results.  Automatic choice: it wins once the clouds are large enough for its fixed costs (preparation,
+    // resolution and rescan launches) to disappear behind the sweep; 51 forces it, 1..35 force the exact FFMA kernel.
+    const long long pairs_per_cloud = (long long)N * M;
+    g_chamfer_last_path = 0;
+    if (pick == 51 || (pick == 0 && pairs_per_cloud >= get_option("chamfer_tc_min_pairs", 2048 * 2048))) {
+        g_chamfer_last_path = 1;
         return chamfer_sweep_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, sums, workspace, workspace_bytes, gw,
-                                    g1, g2, st, pick == 51);
+                                    g1, g2, st);
+    }
     const size_t need = chamfer_keys_bytes(B, N, M);
     if (workspace_bytes < need) {
         set_error("chamfer_fwd: workspace %zu < %zu bytes", workspace_bytes, need);
@@ -760,6 +767,8 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     set_error("chamfer_fwd: unknown variant %d", pick);
     return PP_EINVAL;
 }
+
+extern "C" int pp_chamfer_last_path(void) { return g_chamfer_last_path; }
 
 extern "C" int pp_chamfer_fwd(const float *xyz1, const float *xyz2, int B, int N, int M, int c,
                               float *dist1, float *dist2, int32_t *idx1, int32_t *idx2, float *sums,

@@ -24,7 +24,7 @@ int knn_morton_launch(const float *query, const float *points, int B, int M, int
 size_t chamfer_sweep_workspace_bytes(int B, int N, int M);
 int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int M, float *dist1, float *dist2,
                          int *idx1, int *idx2, float *sums, void *workspace, size_t workspace_bytes,
-                         const float *gw, float *g1, float *g2, cudaStream_t st, bool tensor_cores);
+                         const float *gw, float *g1, float *g2, cudaStream_t st);
 
 // Optional per-kernel timing (option "timing" = 1): CUDA events recorded on the launching
 // stream right around one kernel; read back with pp_timing_collect().  Used by bench.py to

@@ -42,10 +42,10 @@ def test_argument_errors_without_gpu():
     assert rc == -22 and b"k=0" in _C.lib.pp_last_error_string()
     rc = _C.lib.pp_fps(None, 1, 0, 4, 0, None, None, 0, None)
     assert rc == -22
-    # at least the packed keys of the exact kernel; the sweep path's layout (~52 B per point, padded) is larger
+    # at least the packed keys of the exact kernel; the tensor-core sweep's layout (~160 B per point, padded) is larger
     assert _C.lib.pp_chamfer_fwd_workspace_bytes(2, 10, 20) >= 8 * (2 * 10 + 2 * 20)
     need = _C.lib.pp_chamfer_fwd_workspace_bytes(3, 2500, 2500)
-    assert 52 * 3 * 5000 <= need <= 64 * 3 * 5000 + 8192
+    assert 150 * 3 * 5000 <= need <= 180 * 3 * 5120 + 8192
     assert _C.lib.pp_chamfer_fwd_workspace_bytes(0, 10, 10) == 0
     # fused forward + backward: weight vector and gradient pointers are checked up front
     rc = _C.lib.pp_chamfer_fwd_bwd_uniform(None, None, None, 1, 4, 4, None, None, None, None, None, None, None,

@@ -67,7 +67,7 @@ def test_chamfer_forward_bit_exact(pp, oracle_mod, B, N, M, maker, seed):
     assert np.array_equal(np32(d2).view(np.uint32), e2.view(np.uint32)), "dist2 bits"
 
 
-_VARIANTS = [1, 2, 5, 13, 14, 21, 22, 25, 31, 32, 35]
+_VARIANTS = [1, 2, 5, 13, 14, 21, 22, 25, 31, 32, 35, 51]
 
 
 @pytest.mark.parametrize("variant", _VARIANTS)

@@ -1,12 +1,12 @@
 """Parity at BASELINE.json's full sizes (VERDICT r01 "missing" #2 / weak #1) and of the optional Chamfer
-sweep path (chamfer_variant 50) against the default exact kernel.
+sweep path (chamfer_variant 51) against the default exact kernel.
 
   * config 4: group_knn k=16, B=4, N=131072 -- 4096 sampled queries per cloud against the CPU oracle
     (their rows of the self-KNN must agree bit for bit), and the pruned sweep == the unpruned sweep on
     every row;
   * config 5 per-rank job: Chamfer B=32, N=M=8192, the FULL batch against the reference's own kernels
     (oracle/_ref, 7.5 ms) -- forward bit for bit, backward to 1e-5;
-  * chamfer_variant 50 (approximate sweep + exact resolution): dist / idx bit-equal to variant 0 on
+  * chamfer_variant 51 (approximate sweep + exact resolution): dist / idx bit-equal to variant 1 (exact FFMA kernel) on
     plain, tied, lattice, far-from-origin, clustered and degenerate inputs, fused gradients close.
 """
 import os
@@ -134,9 +134,9 @@ def test_chamfer_sweep_variant_is_bit_exact(pp, case):
         torch.cuda.synchronize()
         return d1, d2, i1, i2, sums, g1, g2
 
-    want = run(0, False)
+    want = run(1, False)
     for fused in (False, True, True):  # twice: the scratch buffer carries no state between calls
-        got = run(50, fused)
+        got = run(51, fused)
         for x, y, name in zip(got[:4], want[:4], ["dist1", "dist2", "idx1", "idx2"]):
             assert torch.equal(x, y), "%s (fused=%s)" % (name, fused)
         assert torch.allclose(got[4], want[4], rtol=1e-4)

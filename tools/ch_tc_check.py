@@ -32,7 +32,7 @@ cases = [("u", uniform_cloud(1, 128, 1), uniform_cloud(1, 128, 2)), ("u", unifor
          ("tiny_scale", uniform_cloud(2, 3000, 17) * 1e-4, uniform_cloud(2, 3000, 18) * 1e-4)]
 for name, a, b in cases:
     a, b = a.cuda().contiguous(), b.cuda().contiguous()
-    want = run(a, b, 0)
+    want = run(a, b, 1 if a.shape[1] > 4096 else 32)
     for rep in range(2):
         got = run(a, b, 51)
         nd = [int((x != y).sum()) for x, y in zip(got[:4], want[:4])]
@@ -45,13 +45,13 @@ print("exactness:", "OK" if bad == 0 else "%d problems" % bad, flush=True)
 if "quick" in sys.argv:
     sys.exit(1 if bad else 0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for B, N in [(32, 2500), (32, 8192), (256, 8192)]:
+for B, N in [(32, 2500), (32, 4096), (32, 8192), (256, 8192)]:
     a, b = uniform_cloud(B, N, 1).cuda(), uniform_cloud(B, N, 2).cuda()
     d1 = torch.empty(B, N, device="cuda"); d2 = torch.empty(B, N, device="cuda")
     i1 = torch.empty(B, N, dtype=torch.int32, device="cuda"); i2 = torch.empty(B, N, dtype=torch.int32, device="cuda")
     gw = torch.full((2,), 1.0 / (B * N), device="cuda"); g1, g2 = torch.empty_like(a), torch.empty_like(b)
     sums = torch.zeros(2, device="cuda")
-    for v in (0, 50, 51):
+    for v in (1, 51):
         _C.set_option("chamfer_variant", v)
         fn = lambda: losses.nmdistance_forward_backward_uniform(a, b, d1, d2, i1, i2, sums, gw, g1, g2)
         for _ in range(3): fn()
@@ -65,7 +65,7 @@ for B, N in [(32, 2500), (32, 8192), (256, 8192)]:
         for _ in range(3): fn()
         torch.cuda.synchronize()
         parts = []
-        for k in ("chamfer_prep", "chamfer_prep_tc", "chamfer_fwd", "chamfer_finalize", "chamfer_rescan"):
+        for k in ("chamfer_prep", "chamfer_fwd", "chamfer_finalize", "chamfer_rescan"):
             tot, cnt = _C.timing_collect(k)
             if cnt: parts.append("%s %.4f" % (k, tot / cnt))
         _C.set_option("timing", 0)

@@ -12,7 +12,11 @@ KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__b
         'smsp__thread_inst_executed_per_inst_executed.ratio']
 STALLS = 'smsp__average_warps_issue_stalled_'
 out = {}
-for name in sys.argv[1:]:
+args = sys.argv[1:]
+dest = 'r01_ncu_full_summary.json'
+if args and args[0].startswith('--out='):
+    dest = args.pop(0)[6:]
+for name in args:
     rep = os.path.join(ROOT, 'gpurun_out', name + '.ncu-rep')
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -25,7 +29,7 @@ for name in sys.argv[1:]:
                                    if k.startswith(STALLS) and k.endswith('_per_issue_active.ratio') and float(d[k]) >= 0.05}
         launches.append(rec)
     out[name] = launches
-json.dump(out, open(os.path.join(ROOT, 'profiles', 'r01_ncu_full_summary.json'), 'w'), indent=1)
+json.dump(out, open(os.path.join(ROOT, 'profiles', dest), 'w'), indent=1)
 for k, v in out.items():
     for rec in v:
         print(k, rec['Kernel Name'][:60], rec.get('gpu__time_duration.sum'), 'fma%', rec.get('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'),
