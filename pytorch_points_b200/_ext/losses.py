@@ -13,7 +13,7 @@ _workspaces = {}   # (device index, stream handle) -> current scratch tensor
 _retired = []      # outgrown scratch tensors: kept alive, a CUDA graph may have baked their address in
 
 
-def _workspace(device, nbytes):
+def _workspace(device, nbytes, stream_handle=None):
     """Scratch for the Chamfer forward (prepared clouds, packed keys, candidate lists).  The library
     initialises what it reads, so the buffer carries no state between calls (flags = 0).
     One buffer per (device, stream): calls on one stream never overlap.  A buffer that has been
@@ -23,7 +23,9 @@ def _workspace(device, nbytes):
     different graphs (or a replay racing an eager call) then never share scratch."""
     if torch.cuda.is_current_stream_capturing():
         return torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=device)
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    if stream_handle is None:
+        stream_handle = torch.cuda.current_stream(device).cuda_stream
+    key = (device.index, stream_handle)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         if buf is not None:
@@ -40,14 +42,21 @@ def _check_f32(*ts):
             raise RuntimeError("pytorch_points_b200: only float32 point clouds are supported, got %s" % t.dtype)
 
 
-def _scratch(dev, B, N, M, workspace, workspace_clean):
+_ws_bytes = {}
+
+
+def _scratch(dev, B, N, M, workspace, workspace_clean, stream_handle=None):
     """(tensor, flags) for a Chamfer forward: the caller's own buffer (`workspace`, a CUDA uint8 tensor of
     at least pp_chamfer_fwd_workspace_bytes; `workspace_clean` = the caller filled it with 0xff once and
     only ever passes it to these functions on one stream -> PP_CHAMFER_WS_CLEAN, no per-call fill), or the
     module's per-stream buffer with flags 0."""
-    nbytes = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
+    nbytes = _ws_bytes.get((B, N, M))
+    if nbytes is None:
+        if len(_ws_bytes) > 256:
+            _ws_bytes.clear()
+        nbytes = _ws_bytes[(B, N, M)] = _C.lib.pp_chamfer_fwd_workspace_bytes(B, N, M)
     if workspace is None:
-        return _workspace(dev, nbytes), 0
+        return _workspace(dev, nbytes, stream_handle), 0
     if not workspace.is_cuda or workspace.device != dev or workspace.dtype != torch.uint8 \
             or not workspace.is_contiguous() or workspace.numel() < nbytes:
         raise RuntimeError("chamfer workspace must be a contiguous CUDA uint8 tensor of >= %d bytes on %s" % (nbytes, dev))
@@ -73,10 +82,11 @@ def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None, workspac
         _C.require_cuda(xyz1, sums)
         if sums.dtype != torch.float32 or sums.numel() != 2 or not sums.is_contiguous():
             raise RuntimeError("nmdistance_forward: sums must be 2 contiguous float32 values")
-    ws, flags = _scratch(dev, B, N, M, workspace, workspace_clean)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws, flags = _scratch(dev, B, N, M, workspace, workspace_clean, stream)
     rc = _C.lib.pp_chamfer_fwd(_C.ptr(xyz1), _C.ptr(xyz2), B, N, M, c, _C.ptr(dist1), _C.ptr(dist2),
                                _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums), _C.ptr(ws), ws.numel(),
-                               flags, dev.index, _C.stream_of(dev))
+                               flags, dev.index, stream)
     _C.check(rc, "pp_chamfer_fwd")
     return 1
 
@@ -159,10 +169,11 @@ def nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, su
         raise RuntimeError("nmdistance_forward_backward_uniform: idx tensors must be int32")
     if gw.numel() != 2 or gradxyz1.shape != xyz1.shape or gradxyz2.shape != xyz2.shape:
         raise RuntimeError("nmdistance_forward_backward_uniform: gw must hold 2 floats, gradients match the clouds")
-    ws, flags = _scratch(dev, B, N, M, workspace, workspace_clean)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    ws, flags = _scratch(dev, B, N, M, workspace, workspace_clean, stream)
     rc = _C.lib.pp_chamfer_fwd_bwd_uniform(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(gw), B, N, M, _C.ptr(dist1),
                                            _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums),
                                            _C.ptr(gradxyz1), _C.ptr(gradxyz2), _C.ptr(ws), ws.numel(),
-                                           flags, dev.index, _C.stream_of(dev))
+                                           flags, dev.index, stream)
     _C.check(rc, "pp_chamfer_fwd_bwd_uniform")
     return 1

@@ -44,44 +44,29 @@ def sharded_chamfer_loss(xyz1, xyz2, total_batch=None, group=None, local_op=None
     mean, so `loss.backward()` needs no communication.  `local_op` defaults to the CUDA
     `nndistance`; tests inject a CPU stand-in to exercise the host logic under gloo."""
     world = _world(group)
-    if local_op is None:
-        # fused path: the forward kernel's epilogue already produced the two partial sums and the
-        # backward kernel takes the two scalar weights directly
-        from .network.model_loss import chamfer_sums
-        sums = chamfer_sums(xyz1, xyz2)
-        n, m = xyz1.shape[1], xyz2.shape[1]
-    else:
-        d1, d2, _, _ = local_op(xyz1, xyz2)
-        n, m = d1.shape[1], d2.shape[1]
-        sums = torch.stack([d1.sum(), d2.sum()])
     if total_batch is None:
-        tb = torch.tensor([float(xyz1.shape[0])], device=sums.device)
+        tb = torch.tensor([float(xyz1.shape[0])], device=xyz1.device)
         if world > 1:
             dist.all_reduce(tb, op=dist.ReduceOp.SUM, group=group)
         total_batch = int(tb.item())
-    scale = _scale_vector(total_batch, n, m, sums.dtype, sums.device)
-    local = (sums * scale).sum()
+    n, m = xyz1.shape[1], xyz2.shape[1]
+    w1, w2 = 1.0 / (total_batch * max(n, 1)), 1.0 / (total_batch * max(m, 1))
+    if local_op is None:
+        # one library call: forward, fused loss sums and -- the weights being constants -- the backward
+        from .network.model_loss import chamfer_weighted_loss
+        local, sums = chamfer_weighted_loss(xyz1, xyz2, w1, w2)
+    else:
+        d1, d2, _, _ = local_op(xyz1, xyz2)
+        sums = torch.stack([d1.sum(), d2.sum()])
+        local = sums[0] * w1 + sums[1] * w2
+        sums = sums.detach()
     if world == 1:
         return local
-    total = sums.detach().clone()
+    total = sums.clone()
     dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
-    global_loss = (total * scale).sum()
+    global_loss = total[0] * w1 + total[1] * w2
     # value = global mean, gradient = this rank's share of it
     return local + (global_loss - local).detach()
-
-
-_scale_cache = {}
-
-
-def _scale_vector(total_batch, n, m, dtype, device):
-    key = (total_batch, n, m, dtype, str(device))
-    v = _scale_cache.get(key)
-    if v is None:
-        v = torch.tensor([1.0 / (total_batch * max(n, 1)), 1.0 / (total_batch * max(m, 1))], dtype=dtype, device=device)
-        if len(_scale_cache) > 64:
-            _scale_cache.clear()
-        _scale_cache[key] = v
-    return v
 
 
 def allreduce_chamfer_sums(sums, group=None):

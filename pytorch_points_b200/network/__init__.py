@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's `pytorch_points.network` entry points that sit on the
 hot path (same names, argument order and defaults)."""
 from .model_loss import (NmDistanceFunction, LabeledNmdistanceFunction, nndistance, labeled_nndistance,  # noqa: F401
-                         ChamferSumsFunction, chamfer_sums, chamfer_mean_loss, PointLaplacianLoss,
+                         ChamferSumsFunction, chamfer_sums, ChamferWeightedLossFunction, chamfer_weighted_loss,
+                         chamfer_mean_loss, PointLaplacianLoss,
                          PointEdgeLengthLoss, PointStretchLoss, SimplePointRepulsionLoss, NormalLoss)
 from .geo_operations import (FurthestPointSampling, FurthestPointSampleGather, furthest_point_sample,  # noqa: F401
                              pointUniformLaplacian, batch_normals)

@@ -116,12 +116,78 @@ class ChamferSumsFunction(torch.autograd.Function):
 chamfer_sums = ChamferSumsFunction.apply  # type: ignore
 
 
+_weight_cache = {}
+
+
+def _weights(w1, w2, device):
+    """The 2-float device vector [w1, w2] (d loss / d [sum(dist1), sum(dist2)]), cached per value and device."""
+    key = (w1, w2, device)
+    v = _weight_cache.get(key)
+    if v is None:
+        if len(_weight_cache) > 64:
+            _weight_cache.clear()
+        v = _weight_cache[key] = torch.tensor([w1, w2], dtype=torch.float32, device=device)
+    return v
+
+
+class ChamferWeightedLossFunction(torch.autograd.Function):
+    """loss = w1 * sum(dist1) + w2 * sum(dist2) for Python floats w1, w2 (mean-type Chamfer losses), in ONE
+    library call (extension; the reference leaves the reduction and its backward to user code).
+
+    When a cloud needs a gradient, the forward already runs `pp_chamfer_fwd_bwd_uniform`: the weights are
+    known up front, so the kernel that resolves the neighbours also scatters d loss / d xyz; backward only
+    scales those by the incoming scalar.  Returns (loss, sums): `sums` = [sum(dist1), sum(dist2)] of this
+    call, not differentiable (the multi-GPU caller all-reduces it for the global value)."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2, w1, w2):
+        xyz1 = xyz1.contiguous()
+        xyz2 = xyz2.contiguous()
+        B, n, c = xyz1.shape
+        m = xyz2.shape[1]
+        dev = xyz1.device
+        # one allocation for dist1 | dist2 | sums, one for idx1 | idx2
+        fbuf = torch.empty(B * (n + m) + 2, dtype=torch.float32, device=dev)
+        ibuf = torch.empty(B * (n + m), dtype=torch.int32, device=dev)
+        dist1, dist2, sums = fbuf[:B * n].view(B, n), fbuf[B * n:B * (n + m)].view(B, m), fbuf[B * (n + m):]
+        idx1, idx2 = ibuf[:B * n].view(B, n), ibuf[B * n:].view(B, m)
+        gw = _weights(w1, w2, dev)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        if need and c == 3:
+            g1, g2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+            losses.nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, sums, gw, g1, g2)
+            ctx.save_for_backward(g1, g2)
+            ctx.fused = True
+        else:
+            losses.nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=sums)
+            ctx.save_for_backward(xyz1, xyz2, idx1, idx2, gw)
+            ctx.fused = False
+        loss = torch.dot(sums, gw)
+        ctx.mark_non_differentiable(sums)
+        return loss, sums
+
+    @staticmethod
+    def backward(ctx, gloss, gsums_unused):
+        if ctx.fused:
+            g1, g2 = ctx.saved_tensors
+            return (g1 * gloss if ctx.needs_input_grad[0] else None,
+                    g2 * gloss if ctx.needs_input_grad[1] else None, None, None)
+        xyz1, xyz2, idx1, idx2, gw = ctx.saved_tensors
+        gradxyz1, gradxyz2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
+        losses.nmdistance_backward_uniform(xyz1, xyz2, gradxyz1, gradxyz2, (gw * gloss).contiguous(), idx1, idx2)
+        return gradxyz1, gradxyz2, None, None
+
+
+def chamfer_weighted_loss(xyz1, xyz2, w1, w2):
+    """(w1 * sum(dist1) + w2 * sum(dist2), [sum(dist1), sum(dist2)]) -- see ChamferWeightedLossFunction."""
+    return ChamferWeightedLossFunction.apply(xyz1, xyz2, float(w1), float(w2))
+
+
 def chamfer_mean_loss(xyz1, xyz2):
-    """mean(dist1) + mean(dist2) with the reduction fused into the kernels (extension)."""
-    s = chamfer_sums(xyz1, xyz2)
+    """mean(dist1) + mean(dist2) with the reduction and the backward fused into the kernels (extension)."""
     B, n, _ = xyz1.shape
     m = xyz2.shape[1]
-    return s[0] / (B * n) + s[1] / (B * m)
+    return chamfer_weighted_loss(xyz1, xyz2, 1.0 / (B * max(n, 1)), 1.0 / (B * max(m, 1)))[0]
 
 
 # ---------------------------------------------------------------------------
