@@ -52,17 +52,16 @@ def sharded_chamfer_loss(xyz1, xyz2, total_batch=None, group=None, local_op=None
     n, m = xyz1.shape[1], xyz2.shape[1]
     w1, w2 = 1.0 / (total_batch * max(n, 1)), 1.0 / (total_batch * max(m, 1))
     if local_op is None:
-        # one library call: forward, fused loss sums and -- the weights being constants -- the backward
+        # one library call: forward, fused loss sums and -- the weights being constants -- the backward;
+        # the 8-byte all-reduce of the sums happens inside the same autograd node
         from .network.model_loss import chamfer_weighted_loss
-        local, sums = chamfer_weighted_loss(xyz1, xyz2, w1, w2)
-    else:
-        d1, d2, _, _ = local_op(xyz1, xyz2)
-        sums = torch.stack([d1.sum(), d2.sum()])
-        local = sums[0] * w1 + sums[1] * w2
-        sums = sums.detach()
+        return chamfer_weighted_loss(xyz1, xyz2, w1, w2, (group if group is not None else True) if world > 1 else None)[0]
+    d1, d2, _, _ = local_op(xyz1, xyz2)
+    sums = torch.stack([d1.sum(), d2.sum()])
+    local = sums[0] * w1 + sums[1] * w2
     if world == 1:
         return local
-    total = sums.clone()
+    total = sums.detach().clone()
     dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     global_loss = total[0] * w1 + total[1] * w2
     # value = global mean, gradient = this rank's share of it

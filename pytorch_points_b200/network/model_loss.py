@@ -136,11 +136,13 @@ class ChamferWeightedLossFunction(torch.autograd.Function):
 
     When a cloud needs a gradient, the forward already runs `pp_chamfer_fwd_bwd_uniform`: the weights are
     known up front, so the kernel that resolves the neighbours also scatters d loss / d xyz; backward only
-    scales those by the incoming scalar.  Returns (loss, sums): `sums` = [sum(dist1), sum(dist2)] of this
-    call, not differentiable (the multi-GPU caller all-reduces it for the global value)."""
+    scales those by the incoming scalar.  Returns (loss, sums): `sums` = [sum(dist1), sum(dist2)], not
+    differentiable.  With a process `group` the sums are all-reduced (SUM) inside forward, so `loss` is
+    the job-wide value while the gradient stays this rank's share of it (batch-sharded training: the
+    weights already carry 1 / global batch, backward needs no communication)."""
 
     @staticmethod
-    def forward(ctx, xyz1, xyz2, w1, w2):
+    def forward(ctx, xyz1, xyz2, w1, w2, group=None):
         xyz1 = xyz1.contiguous()
         xyz2 = xyz2.contiguous()
         B, n, c = xyz1.shape
@@ -162,6 +164,10 @@ class ChamferWeightedLossFunction(torch.autograd.Function):
             losses.nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=sums)
             ctx.save_for_backward(xyz1, xyz2, idx1, idx2, gw)
             ctx.fused = False
+        if group is not None:
+            import torch.distributed as dist
+            sums = sums.clone()  # (a view of the output buffer: keep dist1/dist2 intact for their consumers)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=None if group is True else group)
         loss = torch.dot(sums, gw)
         ctx.mark_non_differentiable(sums)
         return loss, sums
@@ -171,16 +177,17 @@ class ChamferWeightedLossFunction(torch.autograd.Function):
         if ctx.fused:
             g1, g2 = ctx.saved_tensors
             return (g1 * gloss if ctx.needs_input_grad[0] else None,
-                    g2 * gloss if ctx.needs_input_grad[1] else None, None, None)
+                    g2 * gloss if ctx.needs_input_grad[1] else None, None, None, None)
         xyz1, xyz2, idx1, idx2, gw = ctx.saved_tensors
         gradxyz1, gradxyz2 = torch.empty_like(xyz1), torch.empty_like(xyz2)
         losses.nmdistance_backward_uniform(xyz1, xyz2, gradxyz1, gradxyz2, (gw * gloss).contiguous(), idx1, idx2)
-        return gradxyz1, gradxyz2, None, None
+        return gradxyz1, gradxyz2, None, None, None
 
 
-def chamfer_weighted_loss(xyz1, xyz2, w1, w2):
-    """(w1 * sum(dist1) + w2 * sum(dist2), [sum(dist1), sum(dist2)]) -- see ChamferWeightedLossFunction."""
-    return ChamferWeightedLossFunction.apply(xyz1, xyz2, float(w1), float(w2))
+def chamfer_weighted_loss(xyz1, xyz2, w1, w2, group=None):
+    """(w1 * sum(dist1) + w2 * sum(dist2), [sum(dist1), sum(dist2)]) -- see ChamferWeightedLossFunction.
+    `group`: a torch.distributed group (or True for the default group) whose ranks' sums are added."""
+    return ChamferWeightedLossFunction.apply(xyz1, xyz2, float(w1), float(w2), group)
 
 
 def chamfer_mean_loss(xyz1, xyz2):

@@ -16,8 +16,10 @@ class HostPrefetcher:
         self.depth = depth
         self.stream = torch.cuda.Stream(self.device)
         self._bufs = [None] * depth
-        self._ready = [None] * depth
-        self._consumed = [None] * depth
+        # one event pair per slot, re-recorded every cycle (creating events costs more than recording them)
+        self._ready = [torch.cuda.Event() for _ in range(depth)]
+        self._consumed = [torch.cuda.Event() for _ in range(depth)]
+        self._used = [False] * depth
         self._head = 0   # next slot to fill
         self._tail = 0   # next slot to hand out
         self._inflight = 0
@@ -30,13 +32,11 @@ class HostPrefetcher:
                                            for b, h in zip(self._bufs[slot], host_tensors)):
             self._bufs[slot] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors)
         with torch.cuda.stream(self.stream):
-            if self._consumed[slot] is not None:
+            if self._used[slot]:
                 self.stream.wait_event(self._consumed[slot])  # previous user of this slot is done
             for b, h in zip(self._bufs[slot], host_tensors):
                 b.copy_(h, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self._ready[slot] = ev
+            self._ready[slot].record(self.stream)
         self._head = (slot + 1) % self.depth
         self._inflight += 1
 
@@ -53,9 +53,8 @@ class HostPrefetcher:
     def release(self):
         """Call after the last kernel that reads the tensors returned by the latest `get()` has been
         enqueued: records the event the copy stream waits on before overwriting that slot."""
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
-        self._consumed[self._last] = ev
+        self._consumed[self._last].record(torch.cuda.current_stream(self.device))
+        self._used[self._last] = True
 
 
 class GraphedChamferStep:
