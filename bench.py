@@ -525,6 +525,8 @@ def main():
     timed(step_device, min(args.steps, 50), 3)
     kt = {nm: _C.timing_collect(nm) for nm in knames}
     tensor_path = bool(_C.lib.pp_chamfer_last_path())
+    # from ~3M points per call the library runs the uniform backward as its two streaming kernels again
+    split_bwd = tensor_path and fused and B * (N + M) >= (3 << 20)
     _C.set_option("timing", 0)
     clocks = sampler.stop()
     loss_dev = float((total[0] / (total_B * N) + total[1] / (total_B * M)).item())
@@ -562,7 +564,7 @@ def main():
         traffic_note = "unreadable profiles/ncu_summary.json: %r" % (e,)
     per = lambda nm: kt[nm][0] / max(kt[nm][1], 1)
     others = {("chamfer_finalize(+fused backward)" if fused else "chamfer_finalize"): per("chamfer_finalize")}
-    if not fused:
+    if not fused or split_bwd:
         others["chamfer_bwd(2 launches)"] = per("chamfer_bwd")
     if tensor_path:
         others["cs_prep_kernel"] = per("chamfer_prep")
@@ -642,12 +644,12 @@ def main():
                                       "nmdistance_backward_uniform (the reference-shaped plugin boundary) + D2H of the loss sums"},
                 "timing": "one CUDA-event region over all K steps; every step copies its inputs from pinned host memory and has its loss read on the host"},
         "fused_step": {"state": fused_note, "ms_per_step_four_launch_sequence": ms_step_unfused},
-        "gpu_launches": (((4 if fused else 6) if tensor_path else (2 if fused else 4)) + (2 if exchange is not None else 0)) * args.steps,
+        "gpu_launches": (((4 if fused and not split_bwd else 6) if tensor_path else (2 if fused else 4)) + (2 if exchange is not None else 0)) * args.steps,
         "gpu_launches_note": ("per step: " + (("cs_prep_kernel, cs_rowpass_tc_kernel, cs_finalize_kernel" +
                                                ("<fused backward>" if fused else "") + ", cs_rescan_kernel")
                                               if tensor_path else
                                               ("chamfer_fwd_kernel, chamfer_finalize_kernel" + ("<fused backward>" if fused else "")))
-                              + ("" if fused else ", chamfer_bwd_kernel<0>, <1>")
+                              + ("" if fused and not split_bwd else ", chamfer_bwd_kernel<0>, <1>")
                               + (", lx_send_kernel, lx_wait_kernel" if exchange is not None else "")),
         "clocks": clocks, "roofline": roofline,
         "loss": {"device_leg": loss_dev, "e2e_plugin_leg": loss_e2e, "e2e_graph_leg": loss_graph},

@@ -682,6 +682,10 @@ static int launch_generic(bool labeled, const float *xyz1, const float *xyz2, co
     return PP_OK;
 }
 
+static int chamfer_bwd_impl(const float *xyz1, const float *xyz2, const float *graddist1, const float *graddist2,
+                            const float *gw, const int32_t *idx1, const int32_t *idx2, int B, int N, int M, int c,
+                            float *gradxyz1, float *gradxyz2, int device, void *stream);
+
 // which forward the last pp_chamfer_fwd / pp_chamfer_fwd_bwd_uniform call on this thread ran (pp_chamfer_last_path):
 // 0 = exact FFMA one-pass kernel (or the generic kernel), 1 = tensor-core sweep + exact resolution
 static thread_local int g_chamfer_last_path = 0;
@@ -724,8 +728,14 @@ static int chamfer_fwd_impl(const float *xyz1, const float *xyz2, int B, int N, 
     g_chamfer_last_path = 0;
     if (pick == 51 || (pick == 0 && pairs_per_cloud >= get_option("chamfer_tc_min_pairs", 2048 * 2048))) {
         g_chamfer_last_path = 1;
-        return chamfer_sweep_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, sums, workspace, workspace_bytes, gw,
-                                    g1, g2, st);
+        // Very large batches (from ~3M points): the backward folded into the resolving kernels loses to the two
+        // streaming backward kernels (its scattered RED.ADDs stop fitting the L2 next to the operand tiles:
+        // B=256 N=M=8192: 3.22 vs 3.12 ms); below that the folded form wins (B=128: 1.57 vs 1.59 ms).
+        const bool split_bwd = gw != nullptr && (long long)B * ((long long)N + M) >= get_option("chamfer_split_bwd_points", 3 << 20);
+        const int rc = chamfer_sweep_launch(xyz1, xyz2, B, N, M, dist1, dist2, idx1, idx2, sums, workspace,
+                                            workspace_bytes, split_bwd ? nullptr : gw, g1, g2, st);
+        if (rc != PP_OK || !split_bwd) return rc;
+        return chamfer_bwd_impl(xyz1, xyz2, nullptr, nullptr, gw, idx1, idx2, B, N, M, 3, g1, g2, device, stream);
     }
     const size_t need = chamfer_keys_bytes(B, N, M);
     if (workspace_bytes < need) {

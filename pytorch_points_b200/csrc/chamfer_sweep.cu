@@ -508,16 +508,30 @@ cs_rescan_kernel(const CsArgs args) {
         const float *p = D.qxyz + t * 3;
         const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
         unsigned long long bestkey = 0xffffffffffffffffull;
+        const int span = CS_RB << D.mask_shift;  // references per mask bit
         while (mask) {
-            const int bit = __ffsll((long long)mask) - 1;
-            mask &= mask - 1;
-            const int j0 = (bit << D.mask_shift) * CS_RB, j1 = min(D.nr, ((bit + 1) << D.mask_shift) * CS_RB);
-#pragma unroll 4
-            for (int j = j0 + lane; j < j1; j += 32) {
-                const float d = sqdist_xyz(__ldg(rx + (size_t)j * 3), __ldg(rx + (size_t)j * 3 + 1),
-                                           __ldg(rx + (size_t)j * 3 + 2), px, py, pz);
-                const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
-                bestkey = k < bestkey ? k : bestkey;
+            // four flagged blocks per trip: their loads are independent, so they travel together
+            int start[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                start[k] = -1;
+                if (mask) {
+                    start[k] = (__ffsll((long long)mask) - 1) * span;
+                    mask &= mask - 1;
+                }
+            }
+#pragma unroll 2
+            for (int off = lane; off < span; off += 32) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int j = start[k] + off;
+                    if (start[k] >= 0 && j < D.nr) {
+                        const float d = sqdist_xyz(__ldg(rx + (size_t)j * 3), __ldg(rx + (size_t)j * 3 + 1),
+                                                   __ldg(rx + (size_t)j * 3 + 2), px, py, pz);
+                        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
+                        bestkey = key < bestkey ? key : bestkey;
+                    }
+                }
             }
         }
 #pragma unroll
