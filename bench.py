@@ -554,7 +554,9 @@ def main():
         sha = hashlib.sha256(b"".join(open(os.path.join(ROOT, "pytorch_points_b200", "csrc", f), "rb").read()
                                       for f in ("chamfer.cu", "chamfer_sweep.cu"))).hexdigest()[:16]
         ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(args.workload)
-        if ent:
+        if ent and world > 1:
+            traffic_note = "the committed capture is of the single-GPU launch (256 clouds); not reported for a sharded batch"
+        elif ent:
             if ent.get("chamfer_cu_sha16") == sha:
                 traffic = ent.get("chamfer_fwd_dram_bytes_per_launch")
                 traffic_note = "dram__bytes_read+write of %s, %s" % (ent.get("kernel", "?"), ent.get("capture", "?"))
