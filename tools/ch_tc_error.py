@@ -1,0 +1,65 @@
+"""Measured error of the tensor-core Chamfer sweep's approximate values against the exact chain, in units of
+u * R^2 (u = 2^-24), at the winning pairs: the value the sweep publishes per point is
+rn(e_best + |q|^2 + TAU); the exact kernel gives d*.  EPS (the bound the resolution logic assumes) is 128 u R^2.
+Reads the scratch layout of csrc/chamfer_sweep.cu (cs_layout)."""
+import sys, os, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from helpers import uniform_cloud, sphere_cloud
+from pytorch_points_b200 import _C
+from pytorch_points_b200._ext import losses
+U = 2.0 ** -24
+up = lambda x: (x + 255) & ~255
+
+
+def layout(B, N, M):
+    o = up(12 * B); L = {}
+    for s, n in enumerate((N, M)):
+        rows = B * ((n + 127) // 128) * 128
+        L["aform%d" % s] = o; o += up(64 * rows)
+        L["bform%d" % s] = o; o += up(64 * rows)
+        L["norm%d" % s] = o; o += up(4 * rows)
+        L["key%d" % s] = o; o += up(8 * B * n)
+        L["sec%d" % s] = o; o += up(4 * B * n)
+        L["mask%d" % s] = o; o += up(8 * B * n)
+        L["list%d" % s] = o; o += up(4 * B * n)
+    return L
+
+
+def clustered(B, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    c = torch.rand(B, 8, 3, generator=g) * 100.0
+    pick = torch.randint(0, 8, (B, N), generator=g)
+    return torch.gather(c, 1, pick.unsqueeze(-1).expand(B, N, 3)) + 1e-3 * torch.rand(B, N, 3, generator=g)
+
+
+cases = [("uniform cube", uniform_cloud(4, 8192, 1), uniform_cloud(4, 8192, 2)),
+         ("sphere surface", sphere_cloud(4, 8192, 3), sphere_cloud(4, 8192, 4)),
+         ("cube + 1000 offset", uniform_cloud(4, 4096, 5) + 1000.0, uniform_cloud(4, 4096, 6) + 1000.0),
+         ("two far clouds", uniform_cloud(4, 4096, 7) + 50.0, uniform_cloud(4, 4096, 8) - 50.0),
+         ("clusters of 1e-3 at 100", clustered(4, 4096, 9), clustered(4, 4096, 9) + 1e-4),
+         ("scale 1e-4", uniform_cloud(4, 4096, 10) * 1e-4, uniform_cloud(4, 4096, 11) * 1e-4)]
+for name, a, b in cases:
+    a, b = a.cuda().contiguous(), b.cuda().contiguous()
+    B, N, M = a.shape[0], a.shape[1], b.shape[1]
+    d1 = torch.empty(B, N, device="cuda"); d2 = torch.empty(B, M, device="cuda")
+    i1 = torch.empty(B, N, dtype=torch.int32, device="cuda"); i2 = torch.empty(B, M, dtype=torch.int32, device="cuda")
+    _C.set_option("chamfer_variant", 51)
+    losses.nmdistance_forward(a, b, d1, d2, i1, i2)
+    _C.set_option("chamfer_variant", 0)
+    torch.cuda.synchronize()
+    ws = next(iter(losses._workspaces.values()))
+    L = layout(B, N, M)
+    r2 = ws[:4 * B].view(torch.float32)  # per cloud pair
+    tau = (r2 * 320.0 * U).view(B, 1).double()
+    worst = 0.0
+    for s, n, d in ((0, N, d1), (1, M, d2)):
+        key = ws[L["key%d" % s]:L["key%d" % s] + 8 * B * n].view(torch.int64).view(B, n)
+        vbits = (key >> 32).to(torch.int32)
+        v = vbits.view(torch.float32).double()
+        # exact value in float64 from the inputs (the fp32 chain differs from it by a few ulp of d)
+        q, r, idx = (a, b, i1) if s == 0 else (b, a, i2)
+        nb = torch.gather(r, 1, idx.long().unsqueeze(-1).expand(B, n, 3))
+        dd = ((q.double() - nb.double()) ** 2).sum(-1)
+        err = ((v - tau) - dd).abs() / (U * r2.view(B, 1).double())
+        worst = max(worst, float(err.max()))
+    print("%-26s R^2 %.3e: max |published - exact| = %6.2f u R^2 (EPS budget 128, TAU 320)" % (name, float(r2.max()), worst), flush=True)
