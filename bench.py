@@ -519,7 +519,7 @@ def main():
     # separate short pass with the library's per-kernel CUDA events switched on, so the event
     # records do not perturb the two timed legs above
     _C.set_option("timing", 1)
-    knames = ("chamfer_prep", "chamfer_fwd", "chamfer_finalize", "chamfer_rescan", "chamfer_bwd")
+    knames = ("chamfer_prep", "chamfer_fwd", "chamfer_finalize", "chamfer_bwd")
     for nm in knames:
         _C.timing_collect(nm)
     timed(step_device, min(args.steps, 50), 3)
@@ -570,7 +570,6 @@ def main():
         others["chamfer_bwd(2 launches)"] = per("chamfer_bwd")
     if tensor_path:
         others["cs_prep_kernel"] = per("chamfer_prep")
-        others["cs_rescan_kernel"] = per("chamfer_rescan")
     roofline = {
         "kernel": "cs_rowpass_tc_kernel" if tensor_path else "chamfer_fwd_kernel",
         "bound": "tensor" if tensor_path else "fp32",
@@ -646,9 +645,9 @@ def main():
                                       "nmdistance_backward_uniform (the reference-shaped plugin boundary) + D2H of the loss sums"},
                 "timing": "one CUDA-event region over all K steps; every step copies its inputs from pinned host memory and has its loss read on the host"},
         "fused_step": {"state": fused_note, "ms_per_step_four_launch_sequence": ms_step_unfused},
-        "gpu_launches": (((4 if fused and not split_bwd else 6) if tensor_path else (2 if fused else 4)) + (2 if exchange is not None else 0)) * args.steps,
+        "gpu_launches": (((3 if fused and not split_bwd else 5) if tensor_path else (2 if fused else 4)) + (2 if exchange is not None else 0)) * args.steps,
         "gpu_launches_note": ("per step: " + (("cs_prep_kernel, cs_rowpass_tc_kernel, cs_finalize_kernel" +
-                                               ("<fused backward>" if fused else "") + ", cs_rescan_kernel")
+                                               ("<fused backward>" if fused else ""))
                                               if tensor_path else
                                               ("chamfer_fwd_kernel, chamfer_finalize_kernel" + ("<fused backward>" if fused else "")))
                               + ("" if fused and not split_bwd else ", chamfer_bwd_kernel<0>, <1>")

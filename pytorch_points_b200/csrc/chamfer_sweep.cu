@@ -12,10 +12,10 @@
 // value, the 32-reference granule it occurred in, the runner-up value over all OTHER granules, and a
 // 64-bit mask of the reference blocks that came within TAU = 2.5 EPS of the running best:
 //   runner-up > best + TAU  =>  every true minimiser (ties included) lies inside the recorded granule,
-//       whose 32 pairs are re-evaluated with the exact chain (cs_finalize_kernel);
+//       whose 32 pairs are re-evaluated with the exact chain;
 //   otherwise the point is "ambiguous" (2 % of a uniform cloud, 9 % of a sphere surface, every point
 //       of a lattice): the blocks in its mask -- a superset of wherever a minimiser can be -- are
-//       re-evaluated exactly and the lowest index among the exact minima is taken (cs_rescan_kernel).
+//       re-evaluated exactly and the lowest index among the exact minima is taken.
 // Results therefore equal the reference's on every input; only the time depends on the data.
 //
 // Both directions (dist1/idx1 and dist2/idx2) run the same one-sided pass with the roles of the
@@ -32,7 +32,8 @@
 //
 // Kernels (one stream, programmatic dependent launch):
 //   cs_prep_kernel        centre (mean of the leading points), centred coordinates, norms, R^2; every point
-//                         as an A row (query role) and a B row (reference role); resets keys, gradients.
+//                         as an A row (query role) and a B row (reference role); resets keys, gradients.  No
+//                         cleared memory is assumed anywhere: the scratch buffer carries no state between calls.
 //   cs_rowpass_tc_kernel  CTA = 128 queries (TMEM lane = query) x a chunk of 128-reference blocks.  6 warps:
 //                         0-3 epilogue (each reads its 32 lanes with tcgen05.ld 32x32b.x32, one query per
 //                         thread: FMNMX3 trees + granule bookkeeping), 4 = copy issuer + TMEM owner,
@@ -40,8 +41,8 @@
 //                         128-column accumulators alternate, so the MMA of block i+1 runs while block i is
 //                         scanned; 256 TMEM columns per CTA -> two CTAs per SM.  Bound: TMEM read bandwidth
 //                         (every accumulator element is read once: 4 bytes per pair and direction).
-//   cs_finalize_kernel    exact resolution of the recorded granule (dist / idx, loss sums, fused backward).
-//   cs_rescan_kernel      the ambiguous points: one warp each, exact over the blocks of the mask.
+//   cs_finalize_kernel    exact resolution: the recorded granule, or for ambiguous points the blocks of the mask
+//                         (dist / idx, loss sums, fused backward).
 #include "pp_common.cuh"
 
 namespace pp {
@@ -55,6 +56,7 @@ constexpr unsigned CS_INF_BITS = 0x7f800000u;
 constexpr unsigned long long CS_KEY_INIT = 0x7f800000ffffffffull;
 // TAU = 2.5 * EPS, EPS = 128 u R^2, u = 2^-24
 constexpr float CS_TAU_PER_R2 = 320.f * 5.9604644775390625e-8f;
+constexpr int CS_R2_SLOTS = 64;      // preparation CTAs per cloud pair (32 per cloud): each leaves its own maximum
 
 // One direction of the problem: `nq` query points (cloud A) against `nr` reference points (cloud B).
 struct CsDir {
@@ -65,8 +67,6 @@ struct CsDir {
     unsigned long long *key;         // (B, nq) value bits << 32 | granule
     unsigned *sec;                   // (B, nq) runner-up value bits
     unsigned long long *mask;        // (B, nq) reference blocks (groups of 2^mask_shift blocks) within TAU of the best
-    unsigned *list;                  // (B, nq) ambiguous points: index in cloud
-    unsigned *count;                 // (B) entries in list
     float *dist;                     // outputs (B, nq)
     int *idx;
     float *gq, *gr;                  // fused backward: gradient of the query / reference cloud (or null)
@@ -76,14 +76,15 @@ struct CsDir {
 
 struct CsArgs {
     CsDir d[2];
-    const unsigned *r2bits;  // (B) bits of the largest centred squared norm
+    const unsigned *r2part;  // (B, CS_R2_SLOTS) bits of the preparation CTAs' largest centred squared norms
+    unsigned *taubits;       // (B) bits of TAU, written by the sweep for the resolving kernel
     float *sums;             // [sum(dist1), sum(dist2)] or null
     const float *gw;         // fused backward weights or null
     int B;
 };
 
 struct CsLayout {
-    size_t ctrl, aform[2], bform[2], norm[2], key[2], sec[2], mask[2], list[2], total;
+    size_t ctrl, aform[2], bform[2], norm[2], key[2], sec[2], mask[2], total;
     int blk[2];
 };
 
@@ -92,7 +93,7 @@ CsLayout cs_layout(int B, int N, int M) {
     const int n[2] = {N, M};
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o = 0;
-    L.ctrl = o; o += up(4 * 3 * (size_t)B);  // r2bits[B], count[2][B]
+    L.ctrl = o; o += up(4 * (size_t)B * (CS_R2_SLOTS + 1));  // r2part[B][CS_R2_SLOTS], taubits[B]
     for (int s = 0; s < 2; s++) {
         L.blk[s] = ceil_div(n[s], CS_RB);
         const size_t rows = (size_t)B * L.blk[s] * CS_RB;
@@ -102,7 +103,6 @@ CsLayout cs_layout(int B, int N, int M) {
         L.key[s] = o;   o += up(8 * (size_t)B * n[s]);
         L.sec[s] = o;   o += up(4 * (size_t)B * n[s]);
         L.mask[s] = o;  o += up(8 * (size_t)B * n[s]);
-        L.list[s] = o;  o += up(4 * (size_t)B * n[s]);
     }
     L.total = o;
     return L;
@@ -161,7 +161,7 @@ cs_prep_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, i
                float *__restrict__ af1, float *__restrict__ bf0, float *__restrict__ bf1, float *__restrict__ nm0,
                float *__restrict__ nm1, unsigned long long *__restrict__ key0, unsigned long long *__restrict__ key1,
                unsigned *__restrict__ sec0, unsigned *__restrict__ sec1, unsigned long long *__restrict__ msk0,
-               unsigned long long *__restrict__ msk1, unsigned *__restrict__ r2bits, float *__restrict__ g1,
+               unsigned long long *__restrict__ msk1, unsigned *__restrict__ r2part, float *__restrict__ g1,
                float *__restrict__ g2) {
     pdl_launch_dependents();
     const int b = blockIdx.y, s = blockIdx.z;
@@ -234,8 +234,21 @@ cs_prep_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, i
         *reinterpret_cast<float4 *>(bt + 2 * CH) = make_float4(rhz, n0, n1, n2);
         *reinterpret_cast<float4 *>(bt + 3 * CH) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // this CTA's largest squared norm into its own slot (plain store: nothing has to be cleared beforehand);
+    // the consumers take the maximum over the CS_R2_SLOTS slots of the cloud pair
+    __shared__ unsigned s_r2[8];
     const unsigned rb = __reduce_max_sync(FULL_MASK, __float_as_uint(r2));  // r2 >= 0: bits order like values
-    if (lane == 0 && rb != 0u) atomicMax(r2bits + b, rb);
+    if (lane == 0) s_r2[threadIdx.x >> 5] = rb;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned m = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) m = max(m, s_r2[i]);
+        r2part[(size_t)b * CS_R2_SLOTS + s * (CS_R2_SLOTS / 2) + blockIdx.x] = m;
+    }
+    // slots of CTAs that do not exist
+    if (blockIdx.x == 0 && threadIdx.x >= 32 && (int)threadIdx.x - 32 + (int)gridDim.x < CS_R2_SLOTS / 2)
+        r2part[(size_t)b * CS_R2_SLOTS + s * (CS_R2_SLOTS / 2) + gridDim.x + threadIdx.x - 32] = 0u;
 }
 
 // ---- the one-sided pass on the tensor cores ---------------------------------------------------------
@@ -351,7 +364,10 @@ cs_rowpass_tc_kernel(const CsArgs args) {
     } else {
         // ---- epilogue warps: thread = query = TMEM lane.  Per block four granules of 32 references.
         const int i_q = tile * CS_RB + (int)threadIdx.x;
-        const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * CS_TAU_PER_R2;
+        const unsigned rb = __reduce_max_sync(FULL_MASK, max(__ldcg(args.r2part + (size_t)b * CS_R2_SLOTS + lane),
+                                                             __ldcg(args.r2part + (size_t)b * CS_R2_SLOTS + 32 + lane)));
+        const float tau = __uint_as_float(rb) * CS_TAU_PER_R2;
+        if (blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) args.taubits[b] = __float_as_uint(tau);
         float best = PP_INF, second = PP_INF;
         int gran = 0;
         unsigned long long mask = 0ull;
@@ -409,8 +425,12 @@ cs_rowpass_tc_kernel(const CsArgs args) {
 
 // ---- exact resolution ------------------------------------------------------------------------------
 // One launch for both directions: blocks [0, blocks0) take the points of cloud 1 (dist1 / idx1), the
-// rest those of cloud 2.  A warp takes 32 points; for each, its 32 lanes evaluate the 32 references of
-// the recorded granule at once (coalesced 384-byte read, REDUX.MIN, ballot, find-first-set).
+// rest those of cloud 2.  A warp takes 32 points, one after the other with all 32 lanes:
+//   decided point   -- the 32 references of its recorded granule at once (coalesced 384-byte read,
+//                      REDUX.MIN, ballot, find-first-set);
+//   ambiguous point -- every reference block of its mask (a superset of the blocks that can hold a
+//                      minimiser), four blocks per trip; the smallest (exact value, index) pair wins.
+// Either way the result is the lowest index among the exact minima, like the reference's strict '<' scan.
 __global__ void __launch_bounds__(256)
 cs_finalize_kernel(const CsArgs args, int blocks0) {
     const int lane = threadIdx.x & 31;
@@ -420,8 +440,9 @@ cs_finalize_kernel(const CsArgs args, int blocks0) {
     const CsDir &D = args.d[dir];
     const long long total = (long long)args.B * D.nq;
     const long long t = (long long)((int)blockIdx.x - (dir ? blocks0 : 0)) * 256 + threadIdx.x;
-    bool todo = false;
+    int state = 0;  // 0 = no point, 1 = decided, 2 = ambiguous
     int gran = 0, b = 0;
+    unsigned long long mask = 0ull;
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (t < total) {
         const unsigned long long key = __ldcg(D.key + t);
@@ -429,47 +450,88 @@ cs_finalize_kernel(const CsArgs args, int blocks0) {
         const unsigned vb = (unsigned)(key >> 32);
         gran = (int)(unsigned)key;
         b = (int)(t / D.nq);
-        const float tau = __uint_as_float(__ldcg(args.r2bits + b)) * CS_TAU_PER_R2;
+        const float tau = __uint_as_float(__ldcg(args.taubits + b));
+        state = 1;
         if (sec <= __float_as_uint(__fadd_rn(__uint_as_float(vb), tau))) {
-            const unsigned pos = atomicAdd(D.count + b, 1u);
-            D.list[(size_t)b * D.nq + pos] = (unsigned)(t - (long long)b * D.nq);
-        } else {
-            todo = true;
-            const float *q = D.qxyz + (size_t)t * 3;
-            qx = q[0]; qy = q[1]; qz = q[2];
+            state = 2;
+            mask = __ldcg(D.mask + t);
         }
+        const float *q = D.qxyz + (size_t)t * 3;
+        qx = q[0]; qy = q[1]; qz = q[2];
     }
     unsigned want = 0u;
     int found = 0;
-    const unsigned livemask = __ballot_sync(FULL_MASK, todo);
-#pragma unroll 8
+    const unsigned decided = __ballot_sync(FULL_MASK, state == 1), ambiguous = __ballot_sync(FULL_MASK, state == 2);
+    const int span = CS_RB << D.mask_shift;  // references per mask bit
+#pragma unroll 4
     for (int s = 0; s < 32; s++) {
-        if (!((livemask >> s) & 1u)) continue;  // warp-uniform
-        const int g_s = __shfl_sync(FULL_MASK, gran, s);
+        if (!(((decided | ambiguous) >> s) & 1u)) continue;  // warp-uniform
         const int b_s = __shfl_sync(FULL_MASK, b, s);
         const float x_s = __shfl_sync(FULL_MASK, qx, s);
         const float y_s = __shfl_sync(FULL_MASK, qy, s);
         const float z_s = __shfl_sync(FULL_MASK, qz, s);
-        const int j = g_s * CS_GR + lane;
-        unsigned db = 0xffffffffu;
-        if (j < D.nr) {
+        const float *rx = D.rxyz + (size_t)b_s * D.nr * 3;
+        if ((decided >> s) & 1u) {
+            const int g_s = __shfl_sync(FULL_MASK, gran, s);
+            const int j = g_s * CS_GR + lane;
+            unsigned db = 0xffffffffu;
             // (the squares make the operand order irrelevant: both of the reference's launches give these bits)
-            const float *r = D.rxyz + ((size_t)b_s * D.nr + j) * 3;
-            db = __float_as_uint(sqdist_xyz(__ldg(r), __ldg(r + 1), __ldg(r + 2), x_s, y_s, z_s));
-        }
-        const unsigned mn = __reduce_min_sync(FULL_MASK, db);
-        const unsigned hit = __ballot_sync(FULL_MASK, db == mn);
-        if (lane == s) {
-            want = mn;
-            found = g_s * CS_GR + __ffs(hit) - 1;  // lowest index among the exact minima
+            if (j < D.nr)
+                db = __float_as_uint(sqdist_xyz(__ldg(rx + (size_t)j * 3), __ldg(rx + (size_t)j * 3 + 1),
+                                                __ldg(rx + (size_t)j * 3 + 2), x_s, y_s, z_s));
+            const unsigned mn = __reduce_min_sync(FULL_MASK, db);
+            const unsigned hit = __ballot_sync(FULL_MASK, db == mn);
+            if (lane == s) {
+                want = mn;
+                found = g_s * CS_GR + __ffs(hit) - 1;
+            }
+        } else {
+            unsigned long long m = ((unsigned long long)__shfl_sync(FULL_MASK, (unsigned)(mask >> 32), s) << 32) |
+                                   __shfl_sync(FULL_MASK, (unsigned)mask, s);
+            unsigned long long bestkey = 0xffffffffffffffffull;
+            while (m) {
+                // four flagged blocks per trip: their loads are independent, so they travel together
+                int start[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    start[k] = -1;
+                    if (m) {
+                        start[k] = (__ffsll((long long)m) - 1) * span;
+                        m &= m - 1;
+                    }
+                }
+#pragma unroll 2
+                for (int off = lane; off < span; off += 32) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int j = start[k] + off;
+                        if (start[k] >= 0 && j < D.nr) {
+                            const float d = sqdist_xyz(__ldg(rx + (size_t)j * 3), __ldg(rx + (size_t)j * 3 + 1),
+                                                       __ldg(rx + (size_t)j * 3 + 2), x_s, y_s, z_s);
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
+                            bestkey = key < bestkey ? key : bestkey;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(FULL_MASK, bestkey, o);
+                bestkey = other < bestkey ? other : bestkey;
+            }
+            if (lane == s) {
+                want = (unsigned)(bestkey >> 32);
+                found = (int)(unsigned)bestkey;
+            }
         }
     }
     float s1 = 0.f;
-    if (todo) {
+    if (state != 0) {
         D.dist[t] = __uint_as_float(want);
         D.idx[t] = found;
         s1 = __uint_as_float(want);
-        if (args.gw != nullptr)
+        // (found is always in range: the block of the recorded best value is in the mask)
+        if (args.gw != nullptr && found >= 0 && found < D.nr)
             bwd_term(__fmul_rn(__ldg(args.gw + dir), 2.f), qx, qy, qz, D.rxyz + ((size_t)b * D.nr + found) * 3,
                      D.gq + (size_t)t * 3, D.gr + ((size_t)b * D.nr + found) * 3);
     }
@@ -484,72 +546,6 @@ cs_finalize_kernel(const CsArgs args, int blocks0) {
 #pragma unroll
             for (int i = 0; i < 8; i++) a += sh[i];
             atomicAdd(args.sums + dir, a);
-        }
-    }
-}
-
-// ---- ambiguous points -------------------------------------------------------------------------------
-// grid (groups, B, 2), one warp per listed point: every reference block in the point's mask -- a superset of
-// the blocks that can hold a minimiser -- is evaluated with the exact chain, 32 references per trip; the
-// smallest (exact value, index) pair wins, i.e. the lowest index among the exact minima.
-__global__ void __launch_bounds__(256)
-cs_rescan_kernel(const CsArgs args) {
-    pdl_wait();
-    const CsDir &D = args.d[blockIdx.z];
-    const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const unsigned n = __ldcg(D.count + b);
-    const float *rx = D.rxyz + (size_t)b * D.nr * 3;
-    const unsigned warps = gridDim.x * (blockDim.x >> 5);
-    for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
-        const unsigned i = D.list[(size_t)b * D.nq + e];
-        const size_t t = (size_t)b * D.nq + i;
-        unsigned long long mask = __ldcg(D.mask + t);
-        const float *p = D.qxyz + t * 3;
-        const float px = __ldg(p), py = __ldg(p + 1), pz = __ldg(p + 2);
-        unsigned long long bestkey = 0xffffffffffffffffull;
-        const int span = CS_RB << D.mask_shift;  // references per mask bit
-        while (mask) {
-            // four flagged blocks per trip: their loads are independent, so they travel together
-            int start[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                start[k] = -1;
-                if (mask) {
-                    start[k] = (__ffsll((long long)mask) - 1) * span;
-                    mask &= mask - 1;
-                }
-            }
-#pragma unroll 2
-            for (int off = lane; off < span; off += 32) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int j = start[k] + off;
-                    if (start[k] >= 0 && j < D.nr) {
-                        const float d = sqdist_xyz(__ldg(rx + (size_t)j * 3), __ldg(rx + (size_t)j * 3 + 1),
-                                                   __ldg(rx + (size_t)j * 3 + 2), px, py, pz);
-                        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
-                        bestkey = key < bestkey ? key : bestkey;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(FULL_MASK, bestkey, o);
-            bestkey = other < bestkey ? other : bestkey;
-        }
-        if (lane == 0) {
-            const float d = __uint_as_float((unsigned)(bestkey >> 32));
-            const int found = (int)(unsigned)bestkey;
-            D.dist[t] = d;
-            D.idx[t] = found;
-            if (found >= 0 && found < D.nr) {  // always: the block of the recorded best value is in the mask
-                if (args.sums != nullptr) atomicAdd(args.sums + blockIdx.z, d);
-                if (args.gw != nullptr)
-                    bwd_term(__fmul_rn(__ldg(args.gw + blockIdx.z), 2.f), px, py, pz, rx + (size_t)found * 3,
-                             D.gq + t * 3, D.gr + ((size_t)b * D.nr + found) * 3);
-            }
         }
     }
 }
@@ -570,9 +566,9 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
     PP_REQUIRE(B <= 65535, "chamfer: B=%d too large", B);
     PP_REQUIRE((long long)B * N < (1ll << 31) && (long long)B * M < (1ll << 31), "chamfer: B*N too large");
     char *ws = (char *)workspace;
-    unsigned *r2bits = (unsigned *)(ws + L.ctrl);
+    unsigned *r2part = (unsigned *)(ws + L.ctrl);
     CsArgs A;
-    A.r2bits = r2bits; A.sums = sums; A.gw = gw; A.B = B;
+    A.r2part = r2part; A.taubits = r2part + (size_t)B * CS_R2_SLOTS; A.sums = sums; A.gw = gw; A.B = B;
     const int n[2] = {N, M};
     const float *xyz[2] = {xyz1, xyz2};
     float *dist[2] = {dist1, dist2};
@@ -591,8 +587,6 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
         D.key = (unsigned long long *)(ws + L.key[s]);
         D.sec = (unsigned *)(ws + L.sec[s]);
         D.mask = (unsigned long long *)(ws + L.mask[s]);
-        D.list = (unsigned *)(ws + L.list[s]);
-        D.count = r2bits + B * (1 + s);
         D.dist = dist[s]; D.idx = idx[s];
         D.gq = g[s]; D.gr = g[1 - s];
         D.nq = n[s]; D.nr = n[1 - s];
@@ -609,19 +603,19 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
         grid_x = max(grid_x, D.tiles * D.nchunks);
     }
 
-    PP_CUDA(cudaMemsetAsync(r2bits, 0, 4 * 3 * (size_t)B, st));
     {
         KernelTimer timer("chamfer_prep", st);
         const int rows = max(L.blk[0], L.blk[1]) * CS_RB;
         int chunks = ceil_div(rows, 256 * 2);
         const int want = ceil_div(NUM_SMS_B200, B);  // at least two CTAs per SM over the whole grid
         if (chunks < want) chunks = min(want, ceil_div(rows, 256));
+        chunks = min(chunks, CS_R2_SLOTS / 2);      // every CTA owns one R^2 slot; the kernel strides over the rest
         cs_prep_kernel<<<dim3(chunks, B, 2), 256, 0, st>>>(
             xyz1, xyz2, N, M, (float *)(ws + L.aform[0]), (float *)(ws + L.aform[1]), (float *)(ws + L.bform[0]),
             (float *)(ws + L.bform[1]), (float *)(ws + L.norm[0]), (float *)(ws + L.norm[1]),
             (unsigned long long *)(ws + L.key[0]), (unsigned long long *)(ws + L.key[1]), (unsigned *)(ws + L.sec[0]),
             (unsigned *)(ws + L.sec[1]), (unsigned long long *)(ws + L.mask[0]), (unsigned long long *)(ws + L.mask[1]),
-            r2bits, g[0], g[1]);
+            r2part, g[0], g[1]);
         PP_LAUNCH_CHECK();
     }
     {
@@ -633,14 +627,6 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
         KernelTimer timer("chamfer_finalize", st);
         const int blocks0 = (int)ceil_div_ll((long long)B * N, 256), blocks1 = (int)ceil_div_ll((long long)B * M, 256);
         PP_CUDA(launch_pdl(cs_finalize_kernel, dim3(blocks0 + blocks1), dim3(256), 0, st, A, blocks0));
-        PP_LAUNCH_CHECK();
-    }
-    {
-        KernelTimer timer("chamfer_rescan", st);
-        // a warp per listed point, eight warps per CTA: enough CTAs per cloud that a few per cent of its points
-        // are all in flight at once (the loop over a point's blocks is a chain of dependent L2 round trips)
-        const int groups = max(1, min(64, ceil_div(max(N, M), 1024)));
-        PP_CUDA(launch_pdl(cs_rescan_kernel, dim3(groups, B, 2), dim3(256), 0, st, A));
         PP_LAUNCH_CHECK();
     }
     return PP_OK;

@@ -65,7 +65,7 @@ for B, N in [(32, 2500), (32, 4096), (32, 8192), (256, 8192)]:
         for _ in range(3): fn()
         torch.cuda.synchronize()
         parts = []
-        for k in ("chamfer_prep", "chamfer_fwd", "chamfer_finalize", "chamfer_rescan"):
+        for k in ("chamfer_prep", "chamfer_fwd", "chamfer_finalize"):
             tot, cnt = _C.timing_collect(k)
             if cnt: parts.append("%s %.4f" % (k, tot / cnt))
         _C.set_option("timing", 0)

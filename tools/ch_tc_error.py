@@ -8,21 +8,8 @@ from helpers import uniform_cloud, sphere_cloud
 from pytorch_points_b200 import _C
 from pytorch_points_b200._ext import losses
 U = 2.0 ** -24
-up = lambda x: (x + 255) & ~255
-
-
-def layout(B, N, M):
-    o = up(12 * B); L = {}
-    for s, n in enumerate((N, M)):
-        rows = B * ((n + 127) // 128) * 128
-        L["aform%d" % s] = o; o += up(64 * rows)
-        L["bform%d" % s] = o; o += up(64 * rows)
-        L["norm%d" % s] = o; o += up(4 * rows)
-        L["key%d" % s] = o; o += up(8 * B * n)
-        L["sec%d" % s] = o; o += up(4 * B * n)
-        L["mask%d" % s] = o; o += up(8 * B * n)
-        L["list%d" % s] = o; o += up(4 * B * n)
-    return L
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from _cs_layout import layout, tau as cs_tau
 
 
 def clustered(B, N, seed):
@@ -49,8 +36,8 @@ for name, a, b in cases:
     torch.cuda.synchronize()
     ws = next(iter(losses._workspaces.values()))
     L = layout(B, N, M)
-    r2 = ws[:4 * B].view(torch.float32)  # per cloud pair
-    tau = (r2 * 320.0 * U).view(B, 1).double()
+    tau = cs_tau(ws, B).view(B, 1).double()  # per cloud pair: 320 u R^2
+    r2 = (tau / (320.0 * U)).float().view(B)
     worst = 0.0
     for s, n, d in ((0, N, d1), (1, M, d2)):
         key = ws[L["key%d" % s]:L["key%d" % s] + 8 * B * n].view(torch.int64).view(B, n)

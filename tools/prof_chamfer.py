@@ -22,9 +22,3 @@ for _ in range(3):
         losses.nmdistance_forward(a, b, *bufs)
         losses.nmdistance_backward(a, b, g1, g2, gd1, gd2, bufs[2], bufs[3])
 torch.cuda.synchronize()
-# sweep path: how many points went to the rescan lists (first two words of the scratch buffer)
-ws = None  # (lists are per cloud now; counts printed by tools/ch_sweep_check.py)
-ws_unused = next(iter(losses._workspaces.values()), None)
-if ws is not None and variant in (0, 50):
-    c = ws[:8].view(torch.int32).tolist()
-    print("ambiguous rows %d (%.2f%%)  columns %d (%.2f%%)" % (c[0], 100.0 * c[0] / (B * N), c[1], 100.0 * c[1] / (B * N)))
