@@ -274,7 +274,11 @@ int pp_loss_exchange_wait(void *mailbox, int world, float *sums_out, int32_t *st
  * Micro-benchmarks used to measure the roofline denominators that
  * MEASURED_PEAKS.json lacks (FP32 pipe, shared memory, L2).  `which` selects the
  * probe, `iters` its length; returns elapsed milliseconds in *ms and the work
- * (flop or bytes) in *work.  Not part of the reference surface.
+ * (flop or bytes) in *work.  Probes: 0 FFMA, 1 FFMA2, 2 / 3 the Chamfer op mix (scalar / packed),
+ * 4 shared memory, 5 L2, 6 REDUX, 7 tensor-memory reads (tcgen05.ld 32x32b.x32 from the sweep kernel's
+ * CTA shape, nothing behind them), 8 the same loads followed by the granule minimum tree,
+ * 9 / 10 / 11 FMNMX3 / FMNMX / FMNMX3 with rotating sources (work = warp instructions).
+ * Not part of the reference surface.
  */
 int pp_microbench(int which, int iters, float *ms, double *work, int device);
 

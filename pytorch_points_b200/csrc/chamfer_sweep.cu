@@ -36,13 +36,19 @@
 //                         cleared memory is assumed anywhere: the scratch buffer carries no state between calls.
 //   cs_rowpass_tc_kernel  CTA = 128 queries (TMEM lane = query) x a chunk of 128-reference blocks.  6 warps:
 //                         0-3 epilogue (each reads its 32 lanes with tcgen05.ld 32x32b.x32, one query per
-//                         thread: FMNMX3 trees + granule bookkeeping), 4 = copy issuer + TMEM owner,
-//                         5 = MMA issuer (two kind::tf32 M128 N128 K8 instructions per block).  Two
-//                         128-column accumulators alternate, so the MMA of block i+1 runs while block i is
-//                         scanned; 256 TMEM columns per CTA -> two CTAs per SM.  Bound: TMEM read bandwidth
-//                         (every accumulator element is read once: 4 bytes per pair and direction).
+//                         thread: FMNMX3 trees + granule bookkeeping), 4 = copy issuer + TMEM owner (ring of
+//                         8 reference blocks, one cp.async.bulk each), 5 = MMA issuer (two kind::tf32 M128 N128
+//                         K8 instructions per block).  Two 128-column accumulators alternate; an accumulator
+//                         goes back to the issuer as soon as its block sits in registers.  256 TMEM columns
+//                         per CTA -> two CTAs per SM.  What paces it (profiles/r02_chamfer_tc_pipeline_
+//                         experiments.txt): the accumulator hand-over between the issuing thread and the
+//                         epilogue (1.2 ms of 2.4 at 256 x 8192^2 with all work switched off) and the ALU pipe
+//                         (FMNMX3 issues every second cycle); the tcgen05.ld themselves run at a third of
+//                         the rate the same loads reach alone.
 //   cs_finalize_kernel    exact resolution: the recorded granule, or for ambiguous points the blocks of the mask
 //                         (dist / idx, loss sums, fused backward).
+#include <atomic>
+
 #include "pp_common.cuh"
 
 namespace pp {
@@ -50,7 +56,7 @@ namespace {
 
 constexpr int CS_RB = 128;           // references per block = queries per tile
 constexpr int CS_GR = 32;            // granule (references)
-constexpr int TC_STAGES = 3;         // reference blocks in flight per CTA
+constexpr int TC_STAGES = 8;         // reference blocks in flight per CTA
 constexpr int TC_TILE_BYTES = 8192;  // operand tile: 128 rows x 16 tf32
 constexpr unsigned CS_INF_BITS = 0x7f800000u;
 constexpr unsigned long long CS_KEY_INIT = 0x7f800000ffffffffull;
@@ -291,10 +297,43 @@ __device__ __forceinline__ void tc_ld32(unsigned taddr, float (&v)[32]) {
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-__global__ void __launch_bounds__(192, 2)
+// The same load without the wait, and the wait with the 32 destination registers tied through it (so that no
+// consumer can be scheduled above it): lets a warp put a whole block's loads in flight, release the
+// accumulator, and only then start on the values.
+__device__ __forceinline__ void tc_ld32_issue(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait(unsigned (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// Warp roles: four epilogue warps (warp w reads TMEM lanes 32 w ..., the hardware's lane window of that warp;
+// thread = query), one copy issuer that also owns the TMEM allocation, one MMA issuer.
+constexpr int TC_EPI = 4;
+constexpr int TC_THREADS = (TC_EPI + 2) * 32;
+constexpr int TC_GRAN_PER_WARP = CS_RB / CS_GR;
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
 cs_rowpass_tc_kernel(const CsArgs args) {
-    __shared__ __align__(128) unsigned char sA[TC_TILE_BYTES];
-    __shared__ __align__(128) unsigned char sB[TC_STAGES][TC_TILE_BYTES];
+    extern __shared__ __align__(128) unsigned char cs_dyn_smem[];  // A tile | TC_STAGES B tiles
+    unsigned char *sA = cs_dyn_smem;
+    unsigned char (*sB)[TC_TILE_BYTES] = reinterpret_cast<unsigned char (*)[TC_TILE_BYTES]>(cs_dyn_smem + TC_TILE_BYTES);
     // a_full | b_full[S] | b_empty[S] | t_full[2] | t_empty[2]
     __shared__ __align__(8) unsigned long long sBar[1 + 2 * TC_STAGES + 4];
     __shared__ unsigned sTmem;
@@ -315,11 +354,11 @@ cs_rowpass_tc_kernel(const CsArgs args) {
 #pragma unroll
         for (int i = 0; i < TC_STAGES; i++) { mbar_init(bar_bf + 8 * i, 1); mbar_init(bar_be + 8 * i, 1); }
 #pragma unroll
-        for (int i = 0; i < 2; i++) { mbar_init(bar_tf + 8 * i, 1); mbar_init(bar_te + 8 * i, 4); }
+        for (int i = 0; i < 2; i++) { mbar_init(bar_tf + 8 * i, 1); mbar_init(bar_te + 8 * i, TC_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (w == 4) {  // one warp owns the tensor-memory allocation: 256 columns = two 128-column accumulators
+    if (w == TC_EPI) {  // one warp owns the tensor-memory allocation: 256 columns = two 128-column accumulators
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&sTmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -329,7 +368,7 @@ cs_rowpass_tc_kernel(const CsArgs args) {
     const unsigned tmem = sTmem;
     pdl_wait();  // the prepared operands, R^2 and the reset keys are complete and visible
 
-    if (w == 4) {
+    if (w == TC_EPI) {
         if (lane == 0) {  // ---- copy issuer: the query tile once, then the reference blocks through the ring
             mbar_expect_tx(bar_a, TC_TILE_BYTES);
             bulk_g2s(smem_u32(sA), D.aform + ((size_t)b * D.tiles + tile) * (TC_TILE_BYTES / 4), TC_TILE_BYTES, bar_a);
@@ -341,24 +380,34 @@ cs_rowpass_tc_kernel(const CsArgs args) {
                 bulk_g2s(smem_u32(sB[st]), src + (size_t)i * (TC_TILE_BYTES / 4), TC_TILE_BYTES, bar_bf + 8 * st);
             }
         }
-    } else if (w == 5) {
+    } else if (w == TC_EPI + 1) {
         if (lane == 0) {  // ---- MMA issuer: D[128 x 128] = A[128 x 16] * B[128 x 16]^T as two K = 8 instructions
+            // This lone thread sets the pace of the CTA (every instruction of it is exposed latency), so its loop
+            // is unrolled over the ring: stage, accumulator and both wait parities are constants of the slot.
+            static_assert(TC_STAGES % 4 == 0, "the slot decides accumulator and its wait parity");
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
             constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
             const unsigned long long adesc = tc_smem_desc(smem_u32(sA));
+            const unsigned long long bdesc0 = tc_smem_desc(smem_u32(sB[0]));
             mbar_wait(bar_a, 0);
-            for (int i = 0; i < nblk; i++) {
-                const int st = i % TC_STAGES, acc = i & 1;
-                mbar_wait(bar_bf + 8 * st, (unsigned)(i / TC_STAGES) & 1u);
-                if (i >= 2) mbar_wait(bar_te + 8 * acc, (unsigned)(i / 2 - 1) & 1u);  // the epilogue drained this accumulator
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned long long bdesc = tc_smem_desc(smem_u32(sB[st]));
-                const unsigned d = tmem + (unsigned)acc * 128u;
-                // descriptor start addresses count 16-byte units: K chunks 2 and 3 start 2 * 2048 B further on
-                tc_mma_tf32(d, adesc, bdesc, idesc, 0u);
-                tc_mma_tf32(d, adesc + (2 * 2048 >> 4), bdesc + (2 * 2048 >> 4), idesc, 1u);
-                tc_commit(bar_be + 8 * st);   // the block's shared-memory stage is free once both MMAs have read it
-                tc_commit(bar_tf + 8 * acc);  // ... and the accumulator is complete
+            unsigned ring_parity = 0u;
+            for (int i0 = 0; i0 < nblk; i0 += TC_STAGES, ring_parity ^= 1u) {
+#pragma unroll
+                for (int u = 0; u < TC_STAGES; u++) {
+                    if (i0 + u >= nblk) break;
+                    const int acc = u & 1;
+                    mbar_wait(bar_bf + 8 * u, ring_parity);
+                    // the epilogue drained this accumulator: its use number (i0 + u) / 2 - 1 has the parity of u / 2 - 1
+                    if (i0 + u >= 2) mbar_wait(bar_te + 8 * acc, (unsigned)((u >> 1) + 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned long long bdesc = bdesc0 + (unsigned long long)(u * (TC_TILE_BYTES >> 4));
+                    const unsigned d = tmem + (unsigned)acc * 128u;
+                    // descriptor start addresses count 16-byte units: K chunks 2 and 3 start 2 * 2048 B further on
+                    tc_mma_tf32(d, adesc, bdesc, idesc, 0u);
+                    tc_mma_tf32(d, adesc + (2 * 2048 >> 4), bdesc + (2 * 2048 >> 4), idesc, 1u);
+                    tc_commit(bar_be + 8 * u);    // the block's shared-memory stage is free once both MMAs have read it
+                    tc_commit(bar_tf + 8 * acc);  // ... and the accumulator is complete
+                }
             }
         }
     } else {
@@ -376,11 +425,22 @@ cs_rowpass_tc_kernel(const CsArgs args) {
             mbar_wait(bar_tf + 8 * acc, (unsigned)(i / 2) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const unsigned t0 = tmem + ((unsigned)(w * 32) << 16) + (unsigned)acc * 128u;
-            bool near = false;
+            // the whole block into registers, then the accumulator goes back to the MMA issuer at once: the
+            // next-but-one block is computed while this one is still being reduced
+            unsigned raw[TC_GRAN_PER_WARP][32];
 #pragma unroll
-            for (int gi = 0; gi < CS_RB / CS_GR; gi++) {
+            for (int gi = 0; gi < TC_GRAN_PER_WARP; gi++) tc_ld32_issue(t0 + gi * CS_GR, raw[gi]);
+#pragma unroll
+            for (int gi = 0; gi < TC_GRAN_PER_WARP; gi++) tc_ld_wait(raw[gi]);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_te + 8 * acc);
+            float bm = PP_INF;
+#pragma unroll
+            for (int gi = 0; gi < TC_GRAN_PER_WARP; gi++) {
                 float v[32];
-                tc_ld32(t0 + gi * CS_GR, v);
+#pragma unroll
+                for (int k = 0; k < 32; k++) v[k] = __uint_as_float(raw[gi][k]);
                 float m0 = fmin3(v[0], v[1], v[2]), m1 = fmin3(v[3], v[4], v[5]);
                 float m2 = fmin3(v[6], v[7], v[8]), m3 = fmin3(v[9], v[10], v[11]);
                 m0 = fmin3(m0, v[12], v[13]); m1 = fmin3(m1, v[14], v[15]);
@@ -395,12 +455,11 @@ cs_rowpass_tc_kernel(const CsArgs args) {
                 second = fminf(second, fmaxf(best, gm));
                 if (gm < best) gran = gid;
                 best = fminf(best, gm);
-                near = near || gm <= __fadd_rn(best, tau);  // within TAU of the running best (>= the final one)
+                bm = fminf(bm, gm);
             }
-            if (near) mask |= 1ull << ((blk0 + i) >> D.mask_shift);  // (warp-uniform bit)
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_te + 8 * acc);
+            // the block is flagged when one of its granules lies within TAU of the best value seen so far
+            // (>= the final one, so the flagged blocks are a superset of those that can hold a minimiser)
+            if (bm <= __fadd_rn(best, tau)) mask |= 1ull << ((blk0 + i) >> D.mask_shift);
         }
         if (i_q < D.nq) {
             // published value = e + |q|^2 + TAU: positive, so its bits order like the values
@@ -420,7 +479,7 @@ cs_rowpass_tc_kernel(const CsArgs args) {
     // every tcgen05 operation of this CTA has completed (the epilogue waited for the last accumulator)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (w == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    if (w == TC_EPI) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
 // ---- exact resolution ------------------------------------------------------------------------------
@@ -550,7 +609,55 @@ cs_finalize_kernel(const CsArgs args, int blocks0) {
     }
 }
 
+// ---- tensor-memory read probe (pp_microbench 7 / 8) ---------------------------------------------------
+// What the sweep's epilogue can reach at best: the same 32x32b.x32 loads from the same CTA shape (four
+// warps per CTA, two CTAs of 256 columns per SM), mode 0 with nothing behind them, mode 1 with the granule
+// minimum tree (16 three-input minima per 32 values) and nothing else.
+__global__ void __launch_bounds__(128, 2) tmem_probe_kernel(float *out, int iters, int mode) {
+    __shared__ unsigned sTmem;
+    const int w = threadIdx.x >> 5;
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&sTmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = sTmem, t0 = tmem + ((unsigned)(w * 32) << 16);
+    float acc = PP_INF;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int gi = 0; gi < 8; gi++) {
+            float v[32];
+            tc_ld32(t0 + gi * 32, v);
+            if (mode == 0) {
+                acc = fminf(acc, v[gi]);
+            } else {
+                float m0 = fmin3(v[0], v[1], v[2]), m1 = fmin3(v[3], v[4], v[5]);
+                float m2 = fmin3(v[6], v[7], v[8]), m3 = fmin3(v[9], v[10], v[11]);
+                m0 = fmin3(m0, v[12], v[13]); m1 = fmin3(m1, v[14], v[15]);
+                m2 = fmin3(m2, v[16], v[17]); m3 = fmin3(m3, v[18], v[19]);
+                m0 = fmin3(m0, v[20], v[21]); m1 = fmin3(m1, v[22], v[23]);
+                m2 = fmin3(m2, v[24], v[25]); m3 = fmin3(m3, v[26], v[27]);
+                m0 = fmin3(m0, v[28], v[29]); m1 = fmin3(m1, v[30], v[31]);
+                acc = fminf(acc, fminf(fmin3(m0, m1, m2), m3));
+            }
+        }
+    }
+    if (acc == 12345.678f) out[0] = acc;  // (never: keeps the values alive)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace
+
+cudaError_t chamfer_sweep_tmem_probe(int mode, int iters, float *out, double *bytes) {
+    const int ctas = NUM_SMS_B200 * 2;
+    tmem_probe_kernel<<<ctas, 128>>>(out, iters, mode);
+    *bytes = (double)ctas * 128 * iters * 8 * 32 * 4.0;
+    return cudaGetLastError();
+}
 
 size_t chamfer_sweep_workspace_bytes(int B, int N, int M) { return cs_layout(B, N, M).total; }
 
@@ -620,7 +727,15 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
     }
     {
         KernelTimer timer("chamfer_fwd", st);
-        PP_CUDA(launch_pdl(cs_rowpass_tc_kernel, dim3(grid_x, B, 2), dim3(192), 0, st, A));
+        constexpr size_t smem = (size_t)(1 + TC_STAGES) * TC_TILE_BYTES;
+        static std::atomic<bool> opted_in[64];  // the opt-in to more than 48 KB is per device
+        int dev = 0;
+        PP_CUDA(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !opted_in[dev].load(std::memory_order_acquire)) {
+            PP_CUDA(cudaFuncSetAttribute(cs_rowpass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) opted_in[dev].store(true, std::memory_order_release);
+        }
+        PP_CUDA(launch_pdl(cs_rowpass_tc_kernel, dim3(grid_x, B, 2), dim3(TC_THREADS), smem, st, A));
         PP_LAUNCH_CHECK();
     }
     {

@@ -21,6 +21,7 @@ int knn_morton_launch(const float *query, const float *points, int B, int M, int
                       int *idx, void *workspace, size_t workspace_bytes, cudaStream_t st);
 
 // chamfer_sweep.cu
+cudaError_t chamfer_sweep_tmem_probe(int mode, int iters, float *out, double *bytes);  // pp_microbench 7 / 8
 size_t chamfer_sweep_workspace_bytes(int B, int N, int M);
 int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int M, float *dist1, float *dist2,
                          int *idx1, int *idx2, float *sums, void *workspace, size_t workspace_bytes,

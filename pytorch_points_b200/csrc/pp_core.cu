@@ -190,6 +190,26 @@ __global__ void __launch_bounds__(256) mb_redux(float *out, int iters) {
     if (acc == 0x12345678u) out[0] = acc;
 }
 
+// three-input / two-input float minima with all-distinct source registers, eight independent chains
+template <int KIND>
+__global__ void __launch_bounds__(256) mb_fmnmx(float *out, int iters) {
+    float a[8], x[8], y[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { a[u] = 1e30f - threadIdx.x; x[u] = 3.f + u + threadIdx.x; y[u] = 5.f + 2 * u + threadIdx.x; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (KIND == 0) asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[u]) : "f"(x[u]), "f"(y[u]));
+            else if (KIND == 1) asm volatile("min.f32 %0, %0, %1;" : "+f"(a[u]) : "f"(x[u]));
+            else asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(a[u]) : "f"(a[(u + 1) & 7]), "f"(x[u]), "f"(y[u]));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; u++) s += a[u];
+    if (s == 12345.678f) out[0] = s;
+}
+
 }  // namespace
 }  // namespace pp
 
@@ -259,6 +279,14 @@ extern "C" int pp_microbench(int which, int iters, float *ms, double *work, int 
             case 4: mb_smem<<<blocks, threads>>>(out, iters); *work = lanes * iters * 8 * 16.0; break;
             case 5: mb_l2<<<blocks, threads>>>(big, out, l2_bytes / 16, iters); *work = (double)l2_bytes * iters; break;
             case 6: mb_redux<<<blocks, threads>>>(out, iters); *work = lanes / 32 * iters * 8.0; break;
+            case 9: mb_fmnmx<0><<<blocks, threads>>>(out, iters); *work = lanes / 32 * iters * 8.0; break;
+            case 10: mb_fmnmx<1><<<blocks, threads>>>(out, iters); *work = lanes / 32 * iters * 8.0; break;
+            case 11: mb_fmnmx<2><<<blocks, threads>>>(out, iters); *work = lanes / 32 * iters * 8.0; break;
+            case 7: case 8: {
+                const cudaError_t pe = chamfer_sweep_tmem_probe(which - 7, iters, out, work);
+                if (pe != cudaSuccess) { set_error("microbench: %s", cudaGetErrorString(pe)); rc = (int)pe; }
+                break;
+            }
             default: set_error("microbench: unknown probe %d", which); rc = PP_EINVAL; break;
         }
         if (rc != PP_OK) break;

@@ -8,7 +8,6 @@ NCU="ncu --set full --import-source on --clock-control none -f"
 timeout 300 $NCU -k regex:cs_rowpass_tc -c 1 -s 1 -o gpurun_out/r02_tc_b256 python tools/prof_chamfer.py 256 8192 0 24 fused > gpurun_out/cap.log 2>&1
 timeout 300 $NCU -k regex:cs_rowpass_tc -c 1 -s 1 -o gpurun_out/r02_tc_b32 python tools/prof_chamfer.py 32 8192 0 24 fused >> gpurun_out/cap.log 2>&1
 timeout 300 $NCU -k regex:cs_finalize -c 1 -s 1 -o gpurun_out/r02_fin_b256 python tools/prof_chamfer.py 256 8192 0 24 fused >> gpurun_out/cap.log 2>&1
-timeout 300 $NCU -k regex:cs_rescan -c 1 -s 1 -o gpurun_out/r02_rescan_b256 python tools/prof_chamfer.py 256 8192 0 24 fused >> gpurun_out/cap.log 2>&1
 timeout 300 $NCU -k regex:cs_prep -c 1 -s 1 -o gpurun_out/r02_prep_b256 python tools/prof_chamfer.py 256 8192 0 24 fused >> gpurun_out/cap.log 2>&1
 timeout 300 $NCU -k regex:chamfer_fwd_kernel -c 1 -s 1 -o gpurun_out/r02_exact_b256 python tools/prof_chamfer.py 256 8192 1 24 fused >> gpurun_out/cap.log 2>&1
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_launches_bench_default.csv \
