@@ -925,6 +925,26 @@ def run_reference_cuda(dev, timeit):
     ctr = torch.gather(x, 1, idx.long().unsqueeze(-1).expand(16, 1024, 3)).contiguous()
     ms = timeit(lambda: ref_sampling.ball_query(ctr, x, 0.2, 32), iters=5, warm=2)
     res["ball_query_B16_N16384_M1024_r0.2_ns32"] = {"ms_per_step": ms}
+    # the reference's QueryAndGroup sequence on its own kernels (ball_query, 2x group_points, subtract, cat), C = 64
+    f64 = uniform_cloud(16, 16384, 5, c=64).transpose(1, 2).contiguous().to(dev)
+    xt = x.transpose(1, 2).contiguous()
+
+    def ref_query_and_group():
+        i_ = ref_sampling.ball_query(ctr, x, 0.2, 32)
+        g_ = ref_sampling.group_points(xt, i_)
+        g_ -= ctr.transpose(1, 2).unsqueeze(-1)
+        return torch.cat([g_, ref_sampling.group_points(f64, i_)], dim=1)
+    ms = timeit(ref_query_and_group, iters=5, warm=2)
+    res["query_and_group_B16_N16384_m1024_r0.2_ns32_C64"] = {"ms_per_step": ms}
+    # feature propagation: three_nn + three_interpolate
+    d3 = torch.empty(16, 16384, 3, device=dev); i3 = torch.empty(16, 16384, 3, dtype=torch.int32, device=dev)
+    ms = timeit(lambda: ref_sampling.three_nn_wrapper(16, 16384, 1024, x, ctr, d3, i3), iters=5, warm=2)
+    res["three_nn_B16_n16384_m1024"] = {"ms_per_step": ms, "pairs_per_s": 16.0 * 16384 * 1024 / (ms * 1e-3)}
+    w3 = torch.rand(16, 16384, 3, device=dev)
+    coarse = uniform_cloud(16, 1024, 6, c=64).transpose(1, 2).contiguous().to(dev)
+    interp = torch.empty(16, 64, 16384, device=dev)
+    ms = timeit(lambda: ref_sampling.three_interpolate_wrapper(16, 64, 1024, 16384, coarse, i3, w3, interp), iters=5, warm=2)
+    res["three_interpolate_B16_C64_n16384_m1024"] = {"ms_per_step": ms}
     return res
 
 

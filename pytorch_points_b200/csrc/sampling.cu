@@ -403,12 +403,16 @@ ball_query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ x
 // 1e40; every stored value is an exact float and (double)d < 1e40 <=> d < +inf for all
 // non-NaN d, so float bests initialised to +inf give identical results and outputs.
 // ===========================================================================
-constexpr int NN3_TILE = 512;
+// Four known points per step: their coordinates come as three broadcast LDS.128, the four distances as
+// packed FADD2 / FMUL2 / FFMA2 (same roundings per lane as the scalar chain; (k - u)^2 == (u - k)^2 bit for
+// bit), and ONE comparison of their minimum against the current third best decides whether any of them can
+// enter the list -- only then are they inserted one by one, in index order, with the reference's strict '<'.
+constexpr int NN3_TILE = 1024;
 
 __global__ void __launch_bounds__(256)
 three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known, int N, int M,
                 float *__restrict__ dist2, int *__restrict__ idx) {
-    __shared__ float sk[NN3_TILE * 3];
+    __shared__ __align__(16) float sx[NN3_TILE], sy[NN3_TILE], sz[NN3_TILE];
     const int b = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = j < N;
@@ -417,20 +421,33 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
     const float *kn = known + (size_t)b * M * 3;
     float b1 = PP_INF, b2 = PP_INF, b3 = PP_INF;
     int i1 = 0, i2 = 0, i3 = 0;
+    auto insert = [&](float d, int k) {
+        if (d < b1) {
+            b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k;
+        } else if (d < b2) {
+            b3 = b2; i3 = i2; b2 = d; i2 = k;
+        } else if (d < b3) {
+            b3 = d; i3 = k;
+        }
+    };
     for (int k0 = 0; k0 < M; k0 += NN3_TILE) {
-        const int cnt = min(NN3_TILE, M - k0);
+        const int cnt = min(NN3_TILE, M - k0), cnt4 = (cnt + 3) & ~3;
         __syncthreads();
-        for (int t = threadIdx.x; t < cnt * 3; t += blockDim.x) sk[t] = __ldg(kn + (size_t)k0 * 3 + t);
+        for (int t = threadIdx.x; t < cnt4; t += blockDim.x) {
+            const bool in = t < cnt;  // the padding sits at +inf: its distance is +inf, never below a best
+            sx[t] = in ? __ldg(kn + (size_t)(k0 + t) * 3) : PP_INF;
+            sy[t] = in ? __ldg(kn + (size_t)(k0 + t) * 3 + 1) : 0.f;
+            sz[t] = in ? __ldg(kn + (size_t)(k0 + t) * 3 + 2) : 0.f;
+        }
         __syncthreads();
-        for (int k = 0; k < cnt; k++) {
-            const float d = sqdist_yxz(__fsub_rn(ux, sk[k * 3]), __fsub_rn(uy, sk[k * 3 + 1]),
-                                       __fsub_rn(uz, sk[k * 3 + 2]));
-            if (d < b1) {
-                b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k0 + k;
-            } else if (d < b2) {
-                b3 = b2; i3 = i2; b2 = d; i2 = k0 + k;
-            } else if (d < b3) {
-                b3 = d; i3 = k0 + k;
+#pragma unroll 2
+        for (int k = 0; k < cnt4; k += 4) {
+            const float4 x = *reinterpret_cast<const float4 *>(sx + k), y = *reinterpret_cast<const float4 *>(sy + k),
+                         z = *reinterpret_cast<const float4 *>(sz + k);
+            const float2 da = sqdist2_yxz(make_float2(x.x, x.y), make_float2(y.x, y.y), make_float2(z.x, z.y), -ux, -uy, -uz);
+            const float2 db = sqdist2_yxz(make_float2(x.z, x.w), make_float2(y.z, y.w), make_float2(z.z, z.w), -ux, -uy, -uz);
+            if (fminf(fmin3(da.x, da.y, db.x), db.y) < b3) {
+                insert(da.x, k0 + k); insert(da.y, k0 + k + 1); insert(db.x, k0 + k + 2); insert(db.y, k0 + k + 3);
             }
         }
     }
