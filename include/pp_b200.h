@@ -199,6 +199,16 @@ int pp_query_group_fwd(const float *new_xyz, const float *xyz, const float *feat
 int pp_query_group_bwd(const float *grad_out, const int32_t *idx, int B, int N, int M, int C,
                        int nsample, int use_xyz, float *grad_features, float *grad_xyz,
                        float *grad_new_xyz, int device, void *stream);
+/*
+ * The same forward with the features staged point-major: features_pm (B,N,C), e.g. from
+ * pp_channels_to_points (in (B,C,N) -> out (B,N,C)).  Same idx and out, bit for bit; a ball member's
+ * channels are then read as full lines instead of one 32-byte sector per value.  A multi-scale level
+ * stages once and runs every scale on the copy.  (The backward pass is pp_query_group_bwd either way.)
+ */
+int pp_query_group_fwd_pm(const float *new_xyz, const float *xyz, const float *features_pm, int B, int N,
+                          int M, int C, float radius, int nsample, int use_xyz, int32_t *idx,
+                          float *out, int device, void *stream);
+int pp_channels_to_points(const float *in, int B, int C, int N, float *out, int device, void *stream);
 
 /* --------------------------------------------------------------------- knn */
 

@@ -35,6 +35,8 @@ SIGNATURES = {
     "pp_group_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_group_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_query_group_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _i, _vp]),
+    "pp_query_group_fwd_pm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp, _vp, _i, _vp]),
+    "pp_channels_to_points": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "pp_query_group_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "pp_knn_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "pp_knn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _i, _vp]),

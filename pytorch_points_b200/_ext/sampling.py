@@ -194,10 +194,29 @@ def furthest_sampling_gather(m, seedIdx, input, temp, idx, new_xyz):
     return idx
 
 
-def query_and_group(new_xyz, xyz, features, radius, nsample, use_xyz=True):
+def channels_to_points(features):
+    """(B, C, N) -> (B, N, C) copy: the staging a set-abstraction level does once for all of its scales."""
+    dev = _C.require_cuda(features)
+    _C.require_contiguous(features)
+    _check(features.dtype == torch.float32 and features.dim() == 3, "channels_to_points: float32 (B, C, N)")
+    B, C, N = features.shape
+    out = torch.empty(B, N, C, dtype=torch.float32, device=dev)
+    _C.check(_C.lib.pp_channels_to_points(_C.ptr(features), B, C, N, _C.ptr(out), dev.index, _C.stream_of(dev)),
+             "pp_channels_to_points")
+    return out
+
+
+def query_and_group(new_xyz, xyz, features, radius, nsample, use_xyz=True, features_pm=None):
     """ball_query + group xyz (centre-relative) + group features + concat in one kernel
     (QueryAndGroup.forward, network/operations.py:166-213).
-    -> (out (B, 3*use_xyz + C, M, nsample), idx (B, M, nsample) int32)."""
+    -> (out (B, 3*use_xyz + C, M, nsample), idx (B, M, nsample) int32).
+    `features_pm`: the same features staged as (B, N, C) (channels_to_points); read instead of `features`."""
+    if features_pm is not None:
+        _check(features is not None and features_pm.dim() == 3 and features_pm.dtype == torch.float32 and
+               tuple(features_pm.shape) == (features.shape[0], features.shape[2], features.shape[1]),
+               "query_and_group: features_pm must be the (B, N, C) copy of features")
+        dev = _C.require_cuda(features_pm)
+        _C.require_contiguous(features_pm)
     tensors = (new_xyz, xyz) if features is None else (new_xyz, xyz, features)
     dev = _C.require_cuda(*tensors)
     _C.require_contiguous(*tensors)
@@ -211,9 +230,14 @@ def query_and_group(new_xyz, xyz, features, radius, nsample, use_xyz=True):
     ch = (3 if use_xyz else 0) + C
     idx = torch.empty(B, M, int(nsample), dtype=torch.int32, device=dev)
     out = torch.empty(B, ch, M, int(nsample), dtype=torch.float32, device=dev)
-    rc = _C.lib.pp_query_group_fwd(_C.ptr(new_xyz), _C.ptr(xyz), _C.ptr(features) if C else None, B, N, M, C,
-                                   float(radius), int(nsample), int(bool(use_xyz)), _C.ptr(idx), _C.ptr(out),
-                                   dev.index, _C.stream_of(dev))
+    if features_pm is not None and C:
+        rc = _C.lib.pp_query_group_fwd_pm(_C.ptr(new_xyz), _C.ptr(xyz), _C.ptr(features_pm), B, N, M, C,
+                                          float(radius), int(nsample), int(bool(use_xyz)), _C.ptr(idx), _C.ptr(out),
+                                          dev.index, _C.stream_of(dev))
+    else:
+        rc = _C.lib.pp_query_group_fwd(_C.ptr(new_xyz), _C.ptr(xyz), _C.ptr(features) if C else None, B, N, M, C,
+                                       float(radius), int(nsample), int(bool(use_xyz)), _C.ptr(idx), _C.ptr(out),
+                                       dev.index, _C.stream_of(dev))
     _C.check(rc, "pp_query_group_fwd")
     return out, idx
 

@@ -21,11 +21,19 @@ namespace {
 
 constexpr int QG_WARPS = 8;
 
+// POINT_MAJOR: the features come as (B, N, C) -- the C channels of one source point are contiguous, so a ball
+// member is read as full 128-byte lines (one channel per lane) and a 32 x 32 tile is turned in shared memory
+// into nsample-contiguous output rows.  With the reference's (B, C, N) layout every gathered value drags a
+// 32-byte sector of its own through L2 (8x over-fetch); a multi-scale level stages its features once
+// (pp_channels_to_points) and runs every scale on the staged copy.
+constexpr int QG_TILE_PITCH = 33;
+
+template <bool POINT_MAJOR>
 __global__ void __launch_bounds__(QG_WARPS * 32)
 query_group_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz,
                    const float *__restrict__ features, int N, int M, int C, float r2, int nsample,
                    int use_xyz, int *__restrict__ idx, float *__restrict__ out) {
-    extern __shared__ int s_idx[];  // [QG_WARPS][nsample]
+    extern __shared__ int s_idx[];  // [QG_WARPS][nsample] (+ [QG_WARPS][32][33] floats if POINT_MAJOR)
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * QG_WARPS + warp;
@@ -64,6 +72,7 @@ query_group_kernel(const float *__restrict__ new_xyz, const float *__restrict__ 
             }
             os += 3 * plane;
         }
+        if (POINT_MAJOR) continue;  // (features below, tile by tile)
         if (C > 0 && ok) {
             const float *f = features + (size_t)b * C * N + k;
             int c = 0;
@@ -78,6 +87,46 @@ query_group_kernel(const float *__restrict__ new_xyz, const float *__restrict__ 
             for (; c < C; c++) __stcs(os + (size_t)c * plane, __ldg(f + (size_t)c * N));
         }
     }
+    if (POINT_MAJOR && C > 0) {
+        float *tile = reinterpret_cast<float *>(s_idx + QG_WARPS * nsample) + warp * 32 * QG_TILE_PITCH;
+        const float *f = features + (size_t)b * N * C;
+        float *of = o + (use_xyz ? 3 : 0) * plane;
+        for (int s0 = 0; s0 < nsample; s0 += 32) {
+            const int ns = min(32, nsample - s0);
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                const int nc = min(32, C - c0);
+                __syncwarp();
+                // member s of the chunk: channels c0 .. c0+31 of its point, one per lane
+#pragma unroll 8
+                for (int s = 0; s < ns; s++) {
+                    const int k = mine[s0 + s];
+                    if (lane < nc) tile[s * QG_TILE_PITCH + lane] = __ldg(f + (size_t)k * C + c0 + lane);
+                }
+                __syncwarp();
+                // channel c of the chunk: its ns samples, one per lane, contiguous in the output
+#pragma unroll 8
+                for (int c = 0; c < nc; c++)
+                    if (lane < ns) __stcs(of + (size_t)(c0 + c) * plane + s0 + lane, tile[lane * QG_TILE_PITCH + c]);
+            }
+        }
+    }
+}
+
+// (B, C, N) -> (B, N, C) through 32 x 32 shared-memory tiles: both sides move full lines
+__global__ void __launch_bounds__(256)
+channels_to_points_kernel(const float *__restrict__ in, int C, int N, float *__restrict__ out) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *src = in + (size_t)b * C * N;
+    float *dst = out + (size_t)b * N * C;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (c0 + r < C && n0 + tx < N) t[r][tx] = __ldg(src + (size_t)(c0 + r) * N + n0 + tx);
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (n0 + r < N && c0 + tx < C) dst[(size_t)(n0 + r) * C + c0 + tx] = t[tx][r];
 }
 
 // Backward of the fused stage.  A warp owns a centre again; lane s owns sample s.
@@ -135,9 +184,9 @@ query_group_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict
 
 using namespace pp;
 
-extern "C" int pp_query_group_fwd(const float *new_xyz, const float *xyz, const float *features, int B,
-                                  int N, int M, int C, float radius, int nsample, int use_xyz,
-                                  int32_t *idx, float *out, int device, void *stream) {
+static int query_group_fwd_impl(const float *new_xyz, const float *xyz, const float *features, int B, int N, int M,
+                                int C, float radius, int nsample, int use_xyz, int32_t *idx, float *out, int device,
+                                void *stream, bool point_major) {
     PP_REQUIRE(B >= 0 && N >= 0 && M >= 0 && C >= 0 && nsample >= 0, "query_group: bad sizes");
     PP_REQUIRE(use_xyz || C > 0, "query_group: nothing to group (use_xyz=0 and no features)");
     if (B == 0 || M == 0 || nsample == 0) return PP_OK;
@@ -145,14 +194,47 @@ extern "C" int pp_query_group_fwd(const float *new_xyz, const float *xyz, const 
     PP_REQUIRE(C == 0 || features, "query_group: C=%d but features is null", C);
     PP_REQUIRE(N > 0, "query_group: empty source cloud");
     PP_REQUIRE(B <= 65535, "query_group: B=%d too large", B);
-    PP_REQUIRE((size_t)QG_WARPS * nsample * sizeof(int) <= 48 * 1024, "query_group: nsample=%d too large", nsample);
+    const size_t smem = (size_t)QG_WARPS * nsample * sizeof(int) +
+                        (point_major ? (size_t)QG_WARPS * 32 * QG_TILE_PITCH * sizeof(float) : 0);
+    PP_REQUIRE(smem <= 48 * 1024, "query_group: nsample=%d too large", nsample);
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
     const float r2 = radius * radius;  // rn(r*r) in fp32 (_ext/sampling_cuda.cu:354)
     dim3 grid(ceil_div(M, QG_WARPS), B);
     KernelTimer timer("query_group", (cudaStream_t)stream);
-    query_group_kernel<<<grid, QG_WARPS * 32, (size_t)QG_WARPS * nsample * sizeof(int), (cudaStream_t)stream>>>(
-        new_xyz, xyz, features, N, M, C, r2, nsample, use_xyz ? 1 : 0, idx, out);
+    if (point_major)
+        query_group_kernel<true><<<grid, QG_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            new_xyz, xyz, features, N, M, C, r2, nsample, use_xyz ? 1 : 0, idx, out);
+    else
+        query_group_kernel<false><<<grid, QG_WARPS * 32, smem, (cudaStream_t)stream>>>(
+            new_xyz, xyz, features, N, M, C, r2, nsample, use_xyz ? 1 : 0, idx, out);
+    PP_LAUNCH_CHECK();
+    return PP_OK;
+}
+
+extern "C" int pp_query_group_fwd(const float *new_xyz, const float *xyz, const float *features, int B,
+                                  int N, int M, int C, float radius, int nsample, int use_xyz,
+                                  int32_t *idx, float *out, int device, void *stream) {
+    return query_group_fwd_impl(new_xyz, xyz, features, B, N, M, C, radius, nsample, use_xyz, idx, out, device, stream,
+                                false);
+}
+
+extern "C" int pp_query_group_fwd_pm(const float *new_xyz, const float *xyz, const float *features_pm, int B,
+                                     int N, int M, int C, float radius, int nsample, int use_xyz,
+                                     int32_t *idx, float *out, int device, void *stream) {
+    return query_group_fwd_impl(new_xyz, xyz, features_pm, B, N, M, C, radius, nsample, use_xyz, idx, out, device,
+                                stream, true);
+}
+
+extern "C" int pp_channels_to_points(const float *in, int B, int C, int N, float *out, int device, void *stream) {
+    PP_REQUIRE(B >= 0 && C >= 0 && N >= 0, "channels_to_points: bad sizes");
+    if (B == 0 || C == 0 || N == 0) return PP_OK;
+    PP_REQUIRE(in && out, "channels_to_points: null pointer");
+    PP_REQUIRE(B <= 65535 && ceil_div(C, 32) <= 65535, "channels_to_points: B=%d or C=%d too large", B, C);
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    KernelTimer timer("channels_to_points", (cudaStream_t)stream);
+    channels_to_points_kernel<<<dim3(ceil_div(N, 32), ceil_div(C, 32), B), 256, 0, (cudaStream_t)stream>>>(in, C, N, out);
     PP_LAUNCH_CHECK();
     return PP_OK;
 }

@@ -6,7 +6,7 @@ from .model_loss import (NmDistanceFunction, LabeledNmdistanceFunction, nndistan
                          PointEdgeLengthLoss, PointStretchLoss, SimplePointRepulsionLoss, NormalLoss)
 from .geo_operations import (FurthestPointSampling, FurthestPointSampleGather, furthest_point_sample,  # noqa: F401
                              pointUniformLaplacian, batch_normals)
-from .operations import (GatherFunction, gather_points, BallQuery, ball_query, GroupingOperation,  # noqa: F401
+from .operations import (stage_features, GatherFunction, gather_points, BallQuery, ball_query, GroupingOperation,  # noqa: F401
                          grouping_operation, QueryAndGroup, QueryAndGroupFunction, query_and_group, group_knn,
                          knn_points)
 from .pointnet2_utils import ThreeNN, three_nn, ThreeInterpolate, three_interpolate, GroupAll  # noqa: F401

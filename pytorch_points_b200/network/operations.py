@@ -75,11 +75,11 @@ class QueryAndGroupFunction(torch.autograd.Function):
     """The whole QueryAndGroup stage as one kernel each way (csrc/sa_group.cu)."""
 
     @staticmethod
-    def forward(ctx, xyz, new_xyz, features, radius, nsample, use_xyz):
+    def forward(ctx, xyz, new_xyz, features, radius, nsample, use_xyz, features_pm=None):
         xyz = xyz.contiguous()
         new_xyz = new_xyz.contiguous()
         feats = None if features is None else features.contiguous()
-        out, idx = sampling.query_and_group(new_xyz, xyz, feats, radius, nsample, use_xyz)
+        out, idx = sampling.query_and_group(new_xyz, xyz, feats, radius, nsample, use_xyz, features_pm=features_pm)
         ctx.save_for_backward(idx)
         ctx.meta = (xyz.size(1), 0 if feats is None else feats.size(1), bool(use_xyz))
         ctx.mark_non_differentiable(idx)
@@ -92,12 +92,20 @@ class QueryAndGroupFunction(torch.autograd.Function):
         need = ctx.needs_input_grad
         gf, gx, gn = sampling.query_and_group_grad(grad_out.contiguous(), idx, N, C, use_xyz,
                                                    need_features=need[2], need_xyz=need[0], need_new_xyz=need[1])
-        return gx, gn, gf, None, None, None
+        return gx, gn, gf, None, None, None, None
 
 
-def query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True):
-    """-> (new_features (B, 3*use_xyz + C, npoint, nsample), idx (B, npoint, nsample) int32)."""
-    return QueryAndGroupFunction.apply(xyz, new_xyz, features, radius, nsample, use_xyz)
+def query_and_group(xyz, new_xyz, features, radius, nsample, use_xyz=True, features_pm=None):
+    """-> (new_features (B, 3*use_xyz + C, npoint, nsample), idx (B, npoint, nsample) int32).
+    `features_pm`: detached (B, N, C) copy of `features` (stage_features) the kernel reads instead; the
+    gradient still flows to `features`."""
+    return QueryAndGroupFunction.apply(xyz, new_xyz, features, radius, nsample, use_xyz, features_pm)
+
+
+def stage_features(features):
+    """(B, C, N) features -> detached point-major (B, N, C) copy for `QueryAndGroup(..., features_pm=)`:
+    done once per set-abstraction level, shared by all of its scales."""
+    return sampling.channels_to_points(features.detach().contiguous())
 
 
 class QueryAndGroup(torch.nn.Module):
@@ -111,12 +119,13 @@ class QueryAndGroup(torch.nn.Module):
         super().__init__()
         self.radius, self.nsample, self.use_xyz, self.fused = radius, nsample, use_xyz, fused
 
-    def forward(self, xyz, new_xyz, features=None):
-        """xyz (B, N, 3), new_xyz (B, npoint, 3), features (B, C, N) -> (B, 3 + C, npoint, nsample)."""
+    def forward(self, xyz, new_xyz, features=None, features_pm=None):
+        """xyz (B, N, 3), new_xyz (B, npoint, 3), features (B, C, N) -> (B, 3 + C, npoint, nsample).
+        `features_pm` (optional, fused path): `stage_features(features)`, computed once by the caller."""
         if features is None:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
         if self.fused:
-            return query_and_group(xyz, new_xyz, features, self.radius, self.nsample, self.use_xyz)[0]
+            return query_and_group(xyz, new_xyz, features, self.radius, self.nsample, self.use_xyz, features_pm)[0]
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
         grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
         grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)

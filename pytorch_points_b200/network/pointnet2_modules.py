@@ -6,8 +6,9 @@ users who keep that file get this repo's kernels by pointing `pytorch_points._ex
 way).  This module is NOT a transcription of it: it is the stage as this repo would build it --
 
   * `SAStage` runs the sampling + grouping half of a level as ONE sequence on one stream:
-    `pp_fps_gather` (FPS with the gather fused) followed by one `pp_query_group_fwd` per scale, all
-    scales sharing the sampled centres, and -- for fixed shapes without autograd (inference, or
+    `pp_fps_gather` (FPS with the gather fused), one `pp_channels_to_points` staging of the features,
+    then one `pp_query_group_fwd_pm` per scale, all scales sharing the sampled centres and the staged
+    features, and -- for fixed shapes without autograd (inference, or
     the geometry half of a frozen encoder) -- replays that sequence as a single CUDA graph;
   * pooling is a reduction over the sample axis (`max` / `mean`), not a 2-D pooling window;
   * the caller's `mlp` lists are left untouched (the reference adds 3 to `mlp[0]` in place).
@@ -24,7 +25,7 @@ import torch.nn as nn
 from . import pointnet2_utils
 from .geo_operations import furthest_point_sample
 from .layers import SharedMLP
-from .operations import QueryAndGroup
+from .operations import QueryAndGroup, stage_features
 
 # max over the sample axis with the gradient routed to the first maximum, like the reference's max_pool2d
 _POOL = {"max_pool": lambda t: t.max(dim=-1).values, "avg_pool": lambda t: t.mean(dim=-1)}
@@ -45,7 +46,15 @@ class SAStage:
     def _run(self, xyz, features, new_xyz):
         if new_xyz is None and self.npoint is not None:
             new_xyz = furthest_point_sample(xyz, self.npoint, NCHW=False)[1]
-        return new_xyz, [g(xyz, new_xyz, features) for g in self.groupers]
+        # the features are staged point-major once and every scale gathers from the copy (full lines per ball
+        # member instead of a sector per value); a single scale with few channels does not repay the copy
+        staged = None
+        if features is not None and features.is_cuda and self.npoint is not None and (
+                len(self.groupers) > 1 or features.shape[1] >= 32):
+            staged = stage_features(features)
+        if staged is None:
+            return new_xyz, [g(xyz, new_xyz, features) for g in self.groupers]
+        return new_xyz, [g(xyz, new_xyz, features, staged) for g in self.groupers]
 
     def __call__(self, xyz, features=None, new_xyz=None):
         needs_grad = torch.is_grad_enabled() and (xyz.requires_grad or (features is not None and features.requires_grad))

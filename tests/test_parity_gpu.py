@@ -815,6 +815,12 @@ def test_query_and_group_fused_bit_exact(pp, oracle_mod, B, N, M, C, radius, nsa
     ref_module = pp.QueryAndGroup(radius, nsample, use_xyz=use_xyz, fused=False)
     assert torch.equal(out, ref_module(dev(xyz), dev(centres), dev(feats) if C else None))
     assert torch.equal(idx, pp.ball_query(radius, nsample, dev(xyz), dev(centres)))
+    if C:
+        # features staged point-major (what a set-abstraction level does once for all its scales): same bits
+        staged = pp.stage_features(dev(feats))
+        assert staged.shape == (B, N, C) and torch.equal(staged, dev(feats).transpose(1, 2))
+        out_pm, idx_pm = pp.query_and_group(dev(xyz), dev(centres), dev(feats), radius, nsample, use_xyz, staged)
+        assert torch.equal(out_pm, out) and torch.equal(idx_pm, idx)
     if B * N * M <= 2 * 4096 * 256:
         want, bq = _oracle_query_group(oracle_mod, xyz, centres, feats, radius, nsample, use_xyz)
         assert np.array_equal(np32(idx), bq)
@@ -830,7 +836,7 @@ def test_query_and_group_fused_backward(pp, oracle_mod, C, use_xyz):
     xd = dev(xyz).requires_grad_(True)
     cd = dev(centres).requires_grad_(True)
     fd = dev(feats).requires_grad_(True) if C else None
-    out, idx = pp.query_and_group(xd, cd, fd, 0.2, ns, use_xyz)
+    out, idx = pp.query_and_group(xd, cd, fd, 0.2, ns, use_xyz, pp.stage_features(fd) if C else None)
     go = torch.rand_like(out)
     out.backward(go)
     gon, bq = np32(go), np32(idx)

@@ -27,6 +27,12 @@ for (B, N, M, C, r, ns) in [(16, 16384, 1024, 0, 0.2, 32), (16, 16384, 1024, 16,
     comp = pp.QueryAndGroup(r, ns, fused=False)
     assert torch.equal(fused(xyz, ctr, feats), comp(xyz, ctr, feats))
     tf = timeit(lambda: fused(xyz, ctr, feats))
+    if C:
+        staged = pp.stage_features(feats)
+        assert torch.equal(fused(xyz, ctr, feats, staged), comp(xyz, ctr, feats))
+        tp = timeit(lambda: fused(xyz, ctr, feats, staged)); tt = timeit(lambda: pp.stage_features(feats))
+        print("   staged point-major: grouping %.3f ms (%.0f GB/s out) + staging %.3f ms (%.0f GB/s)" % (
+            tp, B * (3 + C) * M * ns * 4 / tp / 1e6, tt, 2 * B * C * N * 4 / tt / 1e6), flush=True)
     tc = timeit(lambda: comp(xyz, ctr, feats))
     tb = timeit(lambda: pp.ball_query(r, ns, xyz, ctr))
     out_bytes = B * (3 + C) * M * ns * 4
