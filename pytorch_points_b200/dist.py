@@ -35,14 +35,16 @@ def _world(group):
     return 1
 
 
-def sharded_chamfer_loss(xyz1, xyz2, total_batch=None, group=None, local_op=None):
+def sharded_chamfer_loss(xyz1, xyz2, total_batch=None, group=None, local_op=None, exchange=None):
     """Mean Chamfer loss  mean(dist1) + mean(dist2)  over a batch sharded across ranks.
 
     xyz1 (b_local, N, 3), xyz2 (b_local, M, 3): this rank's clouds.  `total_batch` is the global
     batch size (defaults to the all-reduced sum of local batch sizes).  Returns a scalar that is
     identical on every rank; its gradient w.r.t. the local clouds is the local share of the global
     mean, so `loss.backward()` needs no communication.  `local_op` defaults to the CUDA
-    `nndistance`; tests inject a CPU stand-in to exercise the host logic under gloo."""
+    `nndistance`; tests inject a CPU stand-in to exercise the host logic under gloo.  `exchange`: a
+    `LossExchange` of the same ranks; the two partial sums then travel through NVLink peer memory instead of
+    a `torch.distributed.all_reduce`."""
     world = _world(group)
     if total_batch is None:
         tb = torch.tensor([float(xyz1.shape[0])], device=xyz1.device)
@@ -55,7 +57,8 @@ def sharded_chamfer_loss(xyz1, xyz2, total_batch=None, group=None, local_op=None
         # one library call: forward, fused loss sums and -- the weights being constants -- the backward;
         # the 8-byte all-reduce of the sums happens inside the same autograd node
         from .network.model_loss import chamfer_weighted_loss
-        return chamfer_weighted_loss(xyz1, xyz2, w1, w2, (group if group is not None else True) if world > 1 else None)[0]
+        how = None if world == 1 else (exchange if exchange is not None else (group if group is not None else True))
+        return chamfer_weighted_loss(xyz1, xyz2, w1, w2, how)[0]
     d1, d2, _, _ = local_op(xyz1, xyz2)
     sums = torch.stack([d1.sum(), d2.sum()])
     local = sums[0] * w1 + sums[1] * w2

@@ -164,7 +164,11 @@ class ChamferWeightedLossFunction(torch.autograd.Function):
             losses.nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=sums)
             ctx.save_for_backward(xyz1, xyz2, idx1, idx2, gw)
             ctx.fused = False
-        if group is not None:
+        if group is not None and hasattr(group, "send") and hasattr(group, "wait"):
+            # a dist.LossExchange: the two sums go through the peers' NVLink mailboxes (two one-warp kernels)
+            group.send(sums)
+            sums = group.wait(torch.empty(2, dtype=torch.float32, device=dev))
+        elif group is not None:
             import torch.distributed as dist
             sums = sums.clone()  # (a view of the output buffer: keep dist1/dist2 intact for their consumers)
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=None if group is True else group)
@@ -186,7 +190,8 @@ class ChamferWeightedLossFunction(torch.autograd.Function):
 
 def chamfer_weighted_loss(xyz1, xyz2, w1, w2, group=None):
     """(w1 * sum(dist1) + w2 * sum(dist2), [sum(dist1), sum(dist2)]) -- see ChamferWeightedLossFunction.
-    `group`: a torch.distributed group (or True for the default group) whose ranks' sums are added."""
+    `group`: a torch.distributed group (or True for the default group) whose ranks' sums are added, or a
+    `dist.LossExchange` (peer-memory exchange instead of the library all-reduce)."""
     return ChamferWeightedLossFunction.apply(xyz1, xyz2, float(w1), float(w2), group)
 
 
