@@ -518,10 +518,14 @@ cs_finalize_kernel(const CsArgs args, int blocks0) {
         const float *q = D.qxyz + (size_t)t * 3;
         qx = q[0]; qy = q[1]; qz = q[2];
     }
-    unsigned want = 0u;
+    unsigned want = 0u, hit_mine = 1u;  // decided points: the exact minimum and the lanes of the granule that reach it
     int found = 0;
     const unsigned decided = __ballot_sync(FULL_MASK, state == 1), ambiguous = __ballot_sync(FULL_MASK, state == 2);
     const int span = CS_RB << D.mask_shift;  // references per mask bit
+    // the 32 points of a warp almost always belong to one cloud: its reference base is kept across points
+    int b_cur = __shfl_sync(FULL_MASK, b, 0);
+    const float *rx = D.rxyz + (size_t)b_cur * D.nr * 3;
+    const int last = D.nr - 1;
 #pragma unroll 4
     for (int s = 0; s < 32; s++) {
         if (!(((decided | ambiguous) >> s) & 1u)) continue;  // warp-uniform
@@ -529,20 +533,22 @@ cs_finalize_kernel(const CsArgs args, int blocks0) {
         const float x_s = __shfl_sync(FULL_MASK, qx, s);
         const float y_s = __shfl_sync(FULL_MASK, qy, s);
         const float z_s = __shfl_sync(FULL_MASK, qz, s);
-        const float *rx = D.rxyz + (size_t)b_s * D.nr * 3;
+        if (b_s != b_cur) {  // warp-uniform
+            b_cur = b_s;
+            rx = D.rxyz + (size_t)b_s * D.nr * 3;
+        }
         if ((decided >> s) & 1u) {
             const int g_s = __shfl_sync(FULL_MASK, gran, s);
-            const int j = g_s * CS_GR + lane;
-            unsigned db = 0xffffffffu;
+            // lanes past the end of the cloud repeat its last point: an equal value in a HIGHER lane than the
+            // real one, which the find-first-set below never picks
+            const float *r = rx + (size_t)min(g_s * CS_GR + lane, last) * 3;
             // (the squares make the operand order irrelevant: both of the reference's launches give these bits)
-            if (j < D.nr)
-                db = __float_as_uint(sqdist_xyz(__ldg(rx + (size_t)j * 3), __ldg(rx + (size_t)j * 3 + 1),
-                                                __ldg(rx + (size_t)j * 3 + 2), x_s, y_s, z_s));
+            const unsigned db = __float_as_uint(sqdist_xyz(__ldg(r), __ldg(r + 1), __ldg(r + 2), x_s, y_s, z_s));
             const unsigned mn = __reduce_min_sync(FULL_MASK, db);
             const unsigned hit = __ballot_sync(FULL_MASK, db == mn);
             if (lane == s) {
                 want = mn;
-                found = g_s * CS_GR + __ffs(hit) - 1;
+                hit_mine = hit;
             }
         } else {
             unsigned long long m = ((unsigned long long)__shfl_sync(FULL_MASK, (unsigned)(mask >> 32), s) << 32) |
@@ -584,6 +590,7 @@ cs_finalize_kernel(const CsArgs args, int blocks0) {
             }
         }
     }
+    if (state == 1) found = gran * CS_GR + __ffs(hit_mine) - 1;
     float s1 = 0.f;
     if (state != 0) {
         D.dist[t] = __uint_as_float(want);
