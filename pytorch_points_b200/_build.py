@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpp_b200.so")
-SOURCES = ["pp_core.cu", "chamfer.cu", "chamfer_sweep.cu", "sampling.cu", "knn.cu", "knn_morton.cu", "sa_group.cu", "loss_exchange.cu"]
+SOURCES = ["pp_core.cu", "chamfer.cu", "chamfer_sweep.cu", "sampling.cu", "knn.cu", "knn_morton.cu", "knn_tc.cu", "sa_group.cu", "loss_exchange.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-diag-suppress", "177",

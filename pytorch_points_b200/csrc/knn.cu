@@ -377,10 +377,24 @@ static bool knn_use_morton(int B, int M, int N, int c, int k) {
     return N >= 2048;
 }
 
+// Tensor-core path (knn_tc.cu): the dense contraction on tcgen05.mma, exact resolution on the FP32 pipe.
+static bool knn_use_tc(int B, int M, int N, int c, int k) {
+    if (c != 3 || !knn_tc_supported(B, M, N, k)) return false;
+    const int opt = get_option("knn_tc", -1);
+    if (opt >= 0) return opt != 0;
+    // measured on B200 (tools/knn_tc_check.py, profiles/r02_knn_tc.txt): on par with the ordered sweep for
+    // k <= 16 (0.49 vs 0.48 ms at B = 32, N = 8192), ahead for wider lists (k = 32: 0.90 vs 1.06 ms), whose
+    // per-candidate insertion the exact pass replaces by one rank count per query
+    return k > 16 && N >= 2048 && get_option("knn_morton", -1) < 0;
+}
+
 extern "C" size_t pp_knn_workspace_bytes(int B, int M, int N, int c, int k) {
     if (B <= 0 || M <= 0 || N <= 0) return 0;
     if (c != 3 || k > 32) return 0;
-    return knn_morton_workspace_bytes(B, M, N);  // upper bound: needed whenever the ordered sweep is chosen
+    // upper bound over the paths the options can select
+    const size_t a = knn_morton_workspace_bytes(B, M, N);
+    const size_t t = knn_tc_supported(B, M, N, k) ? knn_tc_workspace_bytes(B, M, N) : 0;
+    return a > t ? a : t;
 }
 
 extern "C" int pp_knn(const float *query, const float *points, int B, int M, int N, int c, int k,
@@ -401,6 +415,8 @@ extern "C" int pp_knn(const float *query, const float *points, int B, int M, int
         PP_LAUNCH_CHECK();
         return PP_OK;
     }
+    if (knn_use_tc(B, M, N, c, k) && !get_option("knn_smem_lists", 0))
+        return knn_tc_launch(query, points, B, M, N, k, dist, idx, workspace, workspace_bytes, st);
     if (knn_use_morton(B, M, N, c, k) && !get_option("knn_smem_lists", 0))
         return knn_morton_launch(query, points, B, M, N, k, dist, idx, workspace, workspace_bytes, st);
     if (k <= 32 && !get_option("knn_smem_lists", 0)) {

@@ -731,9 +731,11 @@ size_t knn_morton_workspace_bytes(int B, int M, int N) {
     return 2 * km_layout(n, (size_t)B).total + 256;
 }
 
-// Returns PP_OK after launching everything, or a negative/positive error.
-int knn_morton_launch(const float *query, const float *points, int B, int M, int N, int k, float *dist, int *idx,
-                      void *workspace, size_t workspace_bytes, cudaStream_t st) {
+// Sorts both clouds along the Morton curve (sorted coordinates, original indices, keys, 64-point tile
+// boxes of the points) into the caller's workspace; shared by the ordered sweep below and by the
+// tensor-core path (knn_tc.cu).
+int knn_morton_prepare(const float *query, const float *points, int B, int M, int N, void *workspace,
+                       size_t workspace_bytes, cudaStream_t st, KmSorted *out) {
     const size_t n = (size_t)B * (size_t)(M > N ? M : N);
     const KmLayout L = km_layout(n, (size_t)B);
     unsigned char *ws = (unsigned char *)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -781,14 +783,28 @@ int knn_morton_launch(const float *query, const float *points, int B, int M, int
             wsQ = wsP;
         }
     }
-    const float *sp = (const float *)(wsP + L.sorted_xyz), *sq = (const float *)(wsQ + L.sorted_xyz);
-    const int *spi = (const int *)(wsP + L.sorted_idx), *sqi = (const int *)(wsQ + L.sorted_idx);
-    const unsigned long long *pk = (const unsigned long long *)(wsP + L.keys_out), *qk = (const unsigned long long *)(wsQ + L.keys_out);
-    const float4 *boxes = (const float4 *)(wsP + L.boxes);
+    out->sp = (const float *)(wsP + L.sorted_xyz); out->sq = (const float *)(wsQ + L.sorted_xyz);
+    out->spi = (const int *)(wsP + L.sorted_idx); out->sqi = (const int *)(wsQ + L.sorted_idx);
+    out->pk = (const unsigned long long *)(wsP + L.keys_out); out->qk = (const unsigned long long *)(wsQ + L.keys_out);
+    out->boxes = (const float4 *)(wsP + L.boxes);
+    out->counter = (unsigned long long *)(wsP + L.bbox + 32);
+    return PP_OK;
+}
+
+// Returns PP_OK after launching everything, or a negative/positive error.
+int knn_morton_launch(const float *query, const float *points, int B, int M, int N, int k, float *dist, int *idx,
+                      void *workspace, size_t workspace_bytes, cudaStream_t st) {
+    KmSorted S;
+    const int rc = knn_morton_prepare(query, points, B, M, N, workspace, workspace_bytes, st, &S);
+    if (rc != PP_OK) return rc;
+    const float *sp = S.sp, *sq = S.sq;
+    const int *spi = S.spi, *sqi = S.sqi;
+    const unsigned long long *pk = S.pk, *qk = S.qk;
+    const float4 *boxes = S.boxes;
     const int prune = get_option("knn_prune", 1);
     unsigned long long *visited = nullptr;
     if (get_option("knn_stats", 0)) {
-        visited = (unsigned long long *)(wsP + L.bbox + 32);
+        visited = S.counter;
         PP_CUDA(cudaMemsetAsync(visited, 0, sizeof(unsigned long long), st));
     }
     {

@@ -17,6 +17,21 @@ int get_option(const char *name, int dflt);
 
 // knn_morton.cu
 size_t knn_morton_workspace_bytes(int B, int M, int N);
+struct KmSorted {  // both clouds in Morton order (device pointers into the caller's workspace)
+    const float *sp, *sq;                // sorted coordinates (B,N,3) / (B,M,3)
+    const int *spi, *sqi;                // original index of every sorted point / query
+    const unsigned long long *pk, *qk;   // sorted keys (batch << 32 | Morton code)
+    const float4 *boxes;                 // bounding boxes of the 64-point tiles of the points
+    unsigned long long *counter;         // a 64-bit scratch counter (statistics)
+};
+int knn_morton_prepare(const float *query, const float *points, int B, int M, int N, void *workspace,
+                       size_t workspace_bytes, cudaStream_t st, KmSorted *out);
+extern double g_knn_tiles_visited, g_knn_tiles_total;  // pp_knn_stats
+// knn_tc.cu
+bool knn_tc_supported(int B, int M, int N, int k);
+size_t knn_tc_workspace_bytes(int B, int M, int N);
+int knn_tc_launch(const float *query, const float *points, int B, int M, int N, int k, float *dist, int *idx,
+                  void *workspace, size_t workspace_bytes, cudaStream_t st);
 int knn_morton_launch(const float *query, const float *points, int B, int M, int N, int k, float *dist,
                       int *idx, void *workspace, size_t workspace_bytes, cudaStream_t st);
 

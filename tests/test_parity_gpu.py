@@ -653,6 +653,72 @@ def test_knn_morton_sweep_matches_oracle(pp, oracle_mod, maker, M, N, k):
     assert np.array_equal(np32(idx_s[:1, :ns]), ei2) and np.array_equal(np32(dist_s[:1, :ns]), ed2)
 
 
+KNN_TC_CASES = [
+    # (name, B, M, N, k): the tensor-core path (knn_tc.cu) forced on
+    ("uniform", 2, 2048, 2048, 16), ("ragged", 3, 1000, 2500, 16), ("sphere", 2, 3000, 3000, 8),
+    ("duplicates", 2, 2048, 2048, 16), ("lattice", 2, 1500, 1500, 16), ("offset", 2, 2048, 2048, 16),
+    ("tiny", 2, 2048, 2048, 16), ("fewpoints", 2, 300, 40, 32), ("k1", 2, 2048, 2048, 1), ("k32", 1, 4096, 4096, 32),
+    ("allequal", 1, 600, 600, 16), ("clusters", 2, 4096, 4096, 16), ("above16k", 1, 300, 16500, 8),
+]
+
+
+def _knn_tc_input(name, B, n, seed):
+    if name == "sphere":
+        return sphere_cloud(B, n, seed)
+    if name == "duplicates":
+        return with_duplicates(uniform_cloud(B, n, seed))
+    if name == "lattice":
+        return lattice_cloud(B, n, seed)
+    if name == "offset":
+        return uniform_cloud(B, n, seed) + 1000.0
+    if name == "tiny":
+        return uniform_cloud(B, n, seed) * 1e-4
+    if name == "allequal":
+        return torch.zeros(B, n, 3) + 0.25
+    if name == "clusters":  # two clusters of 1e-3 a hundred units apart: everything is within the approximation's error
+        g = torch.Generator().manual_seed(seed)
+        return uniform_cloud(B, n, seed) * 1e-3 + 100.0 * torch.randint(0, 2, (B, n, 1), generator=g).float()
+    return uniform_cloud(B, n, seed)
+
+
+@pytest.mark.parametrize("name,B,M,N,k", KNN_TC_CASES)
+def test_knn_tensor_core_path_matches_oracle(pp, oracle_mod, name, B, M, N, k):
+    """knn_tc.cu (tcgen05 flagging pass + exact resolution), forced on: distances and indices equal the
+    oracle's bit for bit -- ties, duplicates, lattices, far-from-origin and degenerate inputs, query != points."""
+    from pytorch_points_b200 import _C
+    p = _knn_tc_input(name, B, N, 11)
+    q = p if M == N else _knn_tc_input(name, B, M, 12)
+    ed, ei = oracle_mod.knn(k, np32(q), np32(p))
+    pd = dev(p)
+    qd = pd if q is p else dev(q)
+    _C.set_option("knn_tc", 1)
+    try:
+        _, idx, dist = pp.group_knn(k, qd, pd, NCHW=False)
+    finally:
+        _C.set_option("knn_tc", -1)
+    assert np.array_equal(np32(idx), ei) and np.array_equal(np32(dist), ed)
+
+
+def test_knn_tensor_core_path_nonfinite_points(pp):
+    """Non-finite points are never neighbours and a non-finite query gets (inf, -1): same as the ordered sweep."""
+    from pytorch_points_b200 import _C
+    from pytorch_points_b200._ext import sampling
+    p = uniform_cloud(1, 2048, 5)
+    p[0, 7] = float("nan")
+    p[0, 100, 1] = float("inf")
+    pd = dev(p)
+    out = []
+    for tc in (1, 0):
+        _C.set_option("knn_tc", tc)
+        try:
+            out.append(sampling.knn(8, pd, pd))
+        finally:
+            _C.set_option("knn_tc", -1)
+    assert torch.equal(out[0][1], out[1][1])
+    assert torch.equal(torch.nan_to_num(out[0][0], 7.0), torch.nan_to_num(out[1][0], 7.0))
+    assert out[0][1][0, 7].tolist() == [-1] * 8
+
+
 def test_knn_shared_list_kernel_matches(pp, oracle_mod):
     from pytorch_points_b200 import _C
     p = with_duplicates(uniform_cloud(2, 3000, 60), 0.2)

@@ -55,6 +55,13 @@ def test_knn_config4_size_sampled_oracle_and_pruning(pp, oracle_mod):
     finally:
         _C.set_option("knn_prune", 1)
     assert torch.equal(idx, idx_all) and torch.equal(dist, dist_all), "pruned != unpruned"
+    # the tensor-core path (knn_tc.cu) returns the same rows
+    _C.set_option("knn_tc", 1)
+    try:
+        dist_tc, idx_tc = sampling.knn(k, pd, pd)
+    finally:
+        _C.set_option("knn_tc", -1)
+    assert torch.equal(idx, idx_tc) and torch.equal(dist, dist_tc), "tensor-core path != ordered sweep"
 
 
 def test_chamfer_config5_rank_job_vs_reference_kernels(pp):
