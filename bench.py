@@ -872,6 +872,35 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
         _C.set_option("knn_prune", 0)
         ms_dense = timeit(lambda: sampling.knn(16, p, p), iters=2, warm=1)
         _C.set_option("knn_prune", 1)
+        # the tensor-core path on the same input (knn_tc.cu; automatic only for 16 < k <= 32), with its stage times
+        _C.set_option("knn_tc", 1)
+        try:
+            ms_tc = timeit(lambda: sampling.knn(16, p, p), iters=iters, warm=1)
+            _C.set_option("timing", 1)
+            for n_ in ("knn_sort", "knn_prep", "knn_seed", "knn", "knn_select"):
+                _C.timing_collect(n_)
+            sampling.knn(16, p, p)
+            torch.cuda.synchronize()
+            stages = {n_: _C.timing_collect(n_)[0] for n_ in ("knn_sort", "knn_prep", "knn_seed", "knn", "knn_select")}
+            _C.set_option("timing", 0)
+            _C.set_option("knn_stats", 1)
+            sampling.knn(16, p, p)
+            vis_tc, tot_tc = _C.knn_stats()
+        finally:
+            _C.set_option("knn_stats", 0)
+            _C.set_option("timing", 0)
+            _C.set_option("knn_tc", -1)
+        tc = {"ms_per_step": ms_tc, "stage_ms": stages, "blocks_128x128_evaluated_frac": vis_tc / max(tot_tc, 1.0),
+              "evaluated_pairs_per_s_in_flagging_kernel": float(B) * N * N * vis_tc / max(tot_tc, 1.0) / max(stages["knn"] * 1e-3, 1e-9),
+              "note": "tcgen05.mma flagging pass over Morton-ordered 128x128 blocks + exact seed / resolution kernels "
+                      "(knn_tc = 1); same bits as the ordered sweep"}
+        if (B, N) == (32, 8192):  # where the tensor path is the automatic choice: k = 32
+            _C.set_option("knn_tc", 0)
+            ms32_sweep = timeit(lambda: sampling.knn(32, p, p), iters=3, warm=1)
+            _C.set_option("knn_tc", -1)
+            ms32 = timeit(lambda: sampling.knn(32, p, p), iters=3, warm=1)
+            tc["k32_ms_per_step_automatic_choice"] = ms32
+            tc["k32_ms_per_step_ordered_sweep"] = ms32_sweep
         out["knn_k16_B%d_N%d" % (B, N)] = {
             "ms_per_step": ms, "point_pairs_per_s": float(B) * N * N / (ms * 1e-3), "sweep_kernel_ms": kms,
             "algorithmic_tflops": 8.0 * B * N * N / (ms * 1e-3) / 1e12,
@@ -879,6 +908,7 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
             "tiles_evaluated_frac": visited / max(total, 1.0),
             "evaluated_pairs_per_s_in_sweep_kernel": float(B) * N * N * visited / max(total, 1.0) / (kms * 1e-3),
             "ms_per_step_without_pruning": ms_dense,
+            "tensor_core_path": tc,
             "note": "algorithmic pairs = B*M*N (SURVEY.md 8d); exact bounding-box pruning skips the tiles that "
                     "cannot hold a neighbour, so the algorithmic rate may exceed the FP32 pipe"}
         del p
