@@ -417,7 +417,8 @@ def main():
 
     ag_prefetcher = HostPrefetcher(dev, depth=2)
     ag_prefetcher.prefetch((a_host, b_host))
-    ag_pending = []
+    from pytorch_points_b200.pipeline import HostScalarReader
+    ag_pending = HostScalarReader(dev, depth=4)
     ag_read = [0]
 
     def step_e2e_autograd():
@@ -425,21 +426,23 @@ def main():
         pinned host memory on the copy stream during the previous step (torch DataLoader-style
         prefetch), the autograd Function behind nndistance / sharded_chamfer_loss, loss.backward(),
         the next step's copies enqueued, then the PREVIOUS step's loss read on the host while this
-        step runs (every step's loss is read inside the timed region)."""
+        step runs (every step's loss is read inside the timed region: its device->host copy into pinned
+        memory is enqueued right behind the forward -- pipeline.HostScalarReader -- because `.item()`
+        would wait for everything launched so far and serialise host and GPU)."""
         xd, yd = ag_prefetcher.get()
         x, y = xd.detach().requires_grad_(True), yd.detach().requires_grad_(True)
         loss = sharded_chamfer_loss(x, y, total_batch=total_B, exchange=exchange)
+        ag_pending.push(loss)
         loss.backward()
         ag_prefetcher.release()
         ag_prefetcher.prefetch((a_host, b_host))
-        ag_pending.append(loss.detach())
         if len(ag_pending) > 1:
-            ag_pending.pop(0).item()
+            ag_pending.pop()
             ag_read[0] += 1
 
     def finish_autograd():
-        while ag_pending:
-            ag_pending.pop(0).item()
+        while len(ag_pending):
+            ag_pending.pop()
             ag_read[0] += 1
 
     def barrier():
@@ -634,8 +637,9 @@ def main():
                 "api": "reference-signature path: pipeline.HostPrefetcher (pinned host -> device on a copy stream, double "
                        "buffered) + dist.sharded_chamfer_loss (the torch.autograd Function behind nndistance, loss sums "
                        "exchanged inside the autograd node when N>1: NVLink peer mailboxes, torch.distributed.all_reduce if peer "
-                       "mapping is unavailable) + loss.backward(); the host reads step i's loss while "
-                       "step i+1 runs -- every step copies its inputs in and has its loss read inside the timed region",
+                       "mapping is unavailable) + loss.backward(); each loss travels to pinned host memory right behind its "
+                       "forward (pipeline.HostScalarReader) and is read while step i+1 runs -- every step copies its "
+                       "inputs in and has its loss read inside the timed region",
                 "autograd_blocking_api": {"value": pairs_per_step / (ms_e2e_autograd_blocking * 1e-3), "ms_per_step": ms_e2e_autograd_blocking,
                                           "api": "host .to(device) + dist.sharded_chamfer_loss + loss.backward() + loss.item(), nothing overlapped"},
                 "graph_api": {"value": pairs_per_step / (ms_e2e_graph * 1e-3), "ms_per_step": ms_e2e_graph,
@@ -701,7 +705,7 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
     # Chamfer fwd+bwd at configs[1] (AtlasNet shape) and at the north-star target shape, device-resident
     # and end to end (same two e2e paths as the headline workload)
     from pytorch_points_b200.dist import sharded_chamfer_loss
-    from pytorch_points_b200.pipeline import GraphedChamferStep, HostPrefetcher
+    from pytorch_points_b200.pipeline import GraphedChamferStep, HostPrefetcher, HostScalarReader
     for (B, N) in [(32, 2500), (32, 8192)]:
         a_host, b_host = uniform_cloud(B, N, 1).pin_memory(), uniform_cloud(B, N, 2).pin_memory()
         a, b = a_host.to(dev), b_host.to(dev)
@@ -724,19 +728,19 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
         _C.set_option("timing", 0)
         kms = tot / max(cnt, 1)
         # e2e, K steps in one region, every step's inputs from pinned host memory, every loss read on the host
-        K, pf, pending = 40, HostPrefetcher(dev, depth=2), []
+        K, pf, pending = 40, HostPrefetcher(dev, depth=2), HostScalarReader(dev, depth=4)
         pf.prefetch((a_host, b_host))
 
         def ag_step():
             xd, yd = pf.get()
             x, y = xd.detach().requires_grad_(True), yd.detach().requires_grad_(True)
             loss = sharded_chamfer_loss(x, y, total_batch=B)
+            pending.push(loss)  # D2H of the loss right behind the forward; read one step later
             loss.backward()
             pf.release()
             pf.prefetch((a_host, b_host))
-            pending.append(loss.detach())
             if len(pending) > 1:
-                pending.pop(0).item()
+                pending.pop()
         graphed = GraphedChamferStep([(a_host, b_host)], total_batch=B, device=dev, world_size=1, exchange=None,
                                      fused_backward=os.environ.get("PP_FUSED_BWD", "1") != "0")
         inflight = []
@@ -761,8 +765,8 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
             return e0.elapsed_time(e1) / K
 
         def drain_ag():
-            while pending:
-                pending.pop(0).item()
+            while len(pending):
+                pending.pop()
 
         def drain_graph():
             while inflight:

@@ -110,8 +110,19 @@ def ptr(t):
     return _vp(t.data_ptr()) if t is not None else _vp(0)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
+def raw_stream(device):
+    """cudaStream_t handle (an int) of torch's current stream on `device`; the raw query is ~10 us cheaper
+    per call than building a torch.cuda.Stream object."""
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream(device).cuda_stream
+
+
 def stream_of(device):
-    return _vp(torch.cuda.current_stream(device).cuda_stream)
+    return _vp(raw_stream(device))
 
 
 def set_option(name, value):

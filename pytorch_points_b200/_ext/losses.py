@@ -24,7 +24,7 @@ def _workspace(device, nbytes, stream_handle=None):
     if torch.cuda.is_current_stream_capturing():
         return torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=device)
     if stream_handle is None:
-        stream_handle = torch.cuda.current_stream(device).cuda_stream
+        stream_handle = _C.raw_stream(device)
     key = (device.index, stream_handle)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -82,7 +82,7 @@ def nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=None, workspac
         _C.require_cuda(xyz1, sums)
         if sums.dtype != torch.float32 or sums.numel() != 2 or not sums.is_contiguous():
             raise RuntimeError("nmdistance_forward: sums must be 2 contiguous float32 values")
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    stream = _C.raw_stream(dev)
     ws, flags = _scratch(dev, B, N, M, workspace, workspace_clean, stream)
     rc = _C.lib.pp_chamfer_fwd(_C.ptr(xyz1), _C.ptr(xyz2), B, N, M, c, _C.ptr(dist1), _C.ptr(dist2),
                                _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums), _C.ptr(ws), ws.numel(),
@@ -169,7 +169,7 @@ def nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, su
         raise RuntimeError("nmdistance_forward_backward_uniform: idx tensors must be int32")
     if gw.numel() != 2 or gradxyz1.shape != xyz1.shape or gradxyz2.shape != xyz2.shape:
         raise RuntimeError("nmdistance_forward_backward_uniform: gw must hold 2 floats, gradients match the clouds")
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    stream = _C.raw_stream(dev)
     ws, flags = _scratch(dev, B, N, M, workspace, workspace_clean, stream)
     rc = _C.lib.pp_chamfer_fwd_bwd_uniform(_C.ptr(xyz1), _C.ptr(xyz2), _C.ptr(gw), B, N, M, _C.ptr(dist1),
                                            _C.ptr(dist2), _C.ptr(idx1), _C.ptr(idx2), _C.ptr(sums),

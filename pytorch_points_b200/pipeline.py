@@ -57,6 +57,46 @@ class HostPrefetcher:
         self._used[self._last] = True
 
 
+class HostScalarReader:
+    """Reads small device results (a loss) on the host WITHOUT draining the stream.
+
+    `tensor.item()` enqueues its copy behind everything already launched on the stream and waits for all
+    of it: a loop that reads step i-1's loss after launching step i therefore runs the GPU and the host
+    strictly one after the other.  `push(t)` instead copies `t` into a pinned slot right where it is
+    produced in stream order (call it straight after the forward, before `backward()`), followed by an
+    event; `pop()` waits for the oldest slot's event only -- long complete by the time the next step has
+    been enqueued -- and returns the value(s) as Python floats."""
+
+    def __init__(self, device, depth=4, numel=1):
+        self.device = torch.device(device)
+        self._host = [torch.zeros(numel, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self._events = [torch.cuda.Event() for _ in range(depth)]
+        self._head = self._tail = self._inflight = 0
+        self.depth, self.numel = depth, numel
+
+    def __len__(self):
+        return self._inflight
+
+    def push(self, t):
+        if self._inflight >= self.depth:
+            raise RuntimeError("HostScalarReader: all %d slots are in flight" % self.depth)
+        slot = self._head
+        self._host[slot].copy_(t.detach().reshape(-1), non_blocking=True)
+        self._events[slot].record(torch.cuda.current_stream(self.device))
+        self._head = (slot + 1) % self.depth
+        self._inflight += 1
+
+    def pop(self):
+        if self._inflight == 0:
+            raise RuntimeError("HostScalarReader: nothing was pushed")
+        slot = self._tail
+        self._events[slot].synchronize()
+        self._tail = (slot + 1) % self.depth
+        self._inflight -= 1
+        h = self._host[slot]
+        return float(h[0]) if self.numel == 1 else [float(v) for v in h]
+
+
 class GraphedChamferStep:
     """One Chamfer training step -- H2D of both clouds from pinned host memory, nndistance forward
     with the fused loss sums, the backward scatter for loss = mean(dist1) + mean(dist2), and the
