@@ -302,6 +302,14 @@ int pp_microbench(int which, int iters, float *ms, double *work, int device);
 int pp_timing_collect(const char *name, double *total_ms, int *count);
 
 /*
+ * Asynchronous copy between host and device memory on `stream` (cudaMemcpyAsync; direction inferred from the
+ * pointers).  The host side of the input pipeline (pipeline.HostPrefetcher / HostScalarReader) calls this
+ * instead of tensor.copy_ under a stream context: a few microseconds of host time per call instead of 10-20.
+ * Host buffers should be pinned, otherwise the call is synchronous.
+ */
+int pp_memcpy_async(void *dst, const void *src, size_t bytes, int device, void *stream);
+
+/*
  * With pp_set_option("knn_stats", 1) the ordered-sweep KNN path counts the (query block, point
  * tile) pairs it actually evaluated (this synchronises the stream).  Returns the counts of the
  * last such call: visited and total.  The rest were skipped by exact bounding-box pruning.

@@ -177,3 +177,18 @@ def nmdistance_forward_backward_uniform(xyz1, xyz2, dist1, dist2, idx1, idx2, su
                                            flags, dev.index, stream)
     _C.check(rc, "pp_chamfer_fwd_bwd_uniform")
     return 1
+
+
+def _fwd_bwd_uniform_raw(dev, B, N, M, xyz1, xyz2, fbase, ibase, gw, g1, g2):
+    """Host-lean form of nmdistance_forward_backward_uniform for callers that allocated every output
+    themselves (network.model_loss): `fbase` / `ibase` are the addresses of one float buffer laid out
+    dist1 (B*N) | dist2 (B*M) | sums (2) and one int32 buffer idx1 | idx2.  No per-call validation, no
+    tensor views: ~20 us less host time per step, which is what a 0.1 ms GPU step is bounded by."""
+    stream = _C.raw_stream(dev)
+    ws, flags = _scratch(dev, B, N, M, None, False, stream)
+    vp = _C._vp
+    rc = _C.lib.pp_chamfer_fwd_bwd_uniform(vp(xyz1.data_ptr()), vp(xyz2.data_ptr()), vp(gw.data_ptr()), B, N, M,
+                                           vp(fbase), vp(fbase + 4 * B * N), vp(ibase), vp(ibase + 4 * B * N),
+                                           vp(fbase + 4 * B * (N + M)), vp(g1.data_ptr()), vp(g2.data_ptr()),
+                                           vp(ws.data_ptr()), ws.numel(), flags, dev.index, stream)
+    _C.check(rc, "pp_chamfer_fwd_bwd_uniform")

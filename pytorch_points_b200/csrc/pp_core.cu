@@ -251,6 +251,15 @@ extern "C" int pp_timing_collect(const char *name, double *total_ms, int *count)
     return PP_OK;
 }
 
+extern "C" int pp_memcpy_async(void *dst, const void *src, size_t bytes, int device, void *stream) {
+    PP_REQUIRE(dst && src, "memcpy_async: null pointer");
+    if (bytes == 0) return PP_OK;
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    PP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return PP_OK;
+}
+
 extern "C" int pp_microbench(int which, int iters, float *ms, double *work, int device) {
     PP_REQUIRE(ms && work && iters > 0, "microbench: bad arguments");
     DeviceGuard guard(device);
