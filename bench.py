@@ -550,12 +550,12 @@ def main():
     pipe_pairs = mix_pairs / (mix_ms * 1e-3)
     achieved = flops_per_launch / (fwd_ms * 1e-3) / 1e12
     # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload -- used only
-    # if it was taken from the kernel source that is running now (hash of csrc/chamfer.cu + chamfer_sweep.cu)
+    # if it was taken from the kernel source that is running now (hash of csrc/chamfer.cu + chamfer_sweep.cu + tc_common.cuh)
     traffic, traffic_note = None, "no ncu capture committed for this workload"
     try:
         import hashlib
         sha = hashlib.sha256(b"".join(open(os.path.join(ROOT, "pytorch_points_b200", "csrc", f), "rb").read()
-                                      for f in ("chamfer.cu", "chamfer_sweep.cu"))).hexdigest()[:16]
+                                      for f in ("chamfer.cu", "chamfer_sweep.cu", "tc_common.cuh"))).hexdigest()[:16]
         ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get(args.workload)
         if ent and world > 1:
             traffic_note = "the committed capture is of the single-GPU launch (256 clouds); not reported for a sharded batch"

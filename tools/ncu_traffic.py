@@ -1,11 +1,11 @@
 """profiles/ncu_summary.json: DRAM bytes per launch of the dominant Chamfer kernel, read by bench.py for
 `roofline.traffic`.  Stamped with the kernel name, the capture and the hash of the kernel sources it was taken
-from -- bench.py refuses the entry when csrc/chamfer.cu or csrc/chamfer_sweep.cu has changed since.
+from -- bench.py refuses the entry when csrc/chamfer.cu, chamfer_sweep.cu or tc_common.cuh has changed since.
     python tools/ncu_traffic.py <workload> <capture name under gpurun_out/> [<workload> <capture> ...]"""
 import csv, hashlib, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sha = hashlib.sha256(b"".join(open(os.path.join(ROOT, "pytorch_points_b200", "csrc", f), "rb").read()
-                              for f in ("chamfer.cu", "chamfer_sweep.cu"))).hexdigest()[:16]
+                              for f in ("chamfer.cu", "chamfer_sweep.cu", "tc_common.cuh"))).hexdigest()[:16]
 path = os.path.join(ROOT, "profiles", "ncu_summary.json")
 out = {}
 args = sys.argv[1:]
