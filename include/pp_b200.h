@@ -302,6 +302,12 @@ int pp_microbench(int which, int iters, float *ms, double *work, int device);
 int pp_timing_collect(const char *name, double *total_ms, int *count);
 
 /*
+ * out[0] = a[0] * b[0] + a[1] * b[1] on the device (one thread): the scalar loss from the two fused sums and
+ * their weights, so that the autograd node's forward needs no library reduction for two numbers.
+ */
+int pp_dot2(const float *a, const float *b, float *out, int device, void *stream);
+
+/*
  * Asynchronous copy between host and device memory on `stream` (cudaMemcpyAsync; direction inferred from the
  * pointers).  The host side of the input pipeline (pipeline.HostPrefetcher / HostScalarReader) calls this
  * instead of tensor.copy_ under a stream context: a few microseconds of host time per call instead of 10-20.

@@ -53,6 +53,7 @@ SIGNATURES = {
     "pp_three_interpolate_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
     "pp_microbench": (_i, [_i, _i, ctypes.POINTER(_f), ctypes.POINTER(ctypes.c_double), _i]),
     "pp_set_option": (_i, [ctypes.c_char_p, _i]),
+    "pp_dot2": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pp_memcpy_async": (_i, [_vp, _vp, _sz, _i, _vp]),
     "pp_timing_collect": (_i, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i)]),
 }

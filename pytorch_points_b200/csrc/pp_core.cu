@@ -251,6 +251,23 @@ extern "C" int pp_timing_collect(const char *name, double *total_ms, int *count)
     return PP_OK;
 }
 
+namespace pp {
+namespace {
+__global__ void dot2_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out) {
+    pdl_wait();
+    out[0] = __fmaf_rn(a[1], b[1], __fmul_rn(a[0], b[0]));
+}
+}  // namespace
+}  // namespace pp
+
+extern "C" int pp_dot2(const float *a, const float *b, float *out, int device, void *stream) {
+    PP_REQUIRE(a && b && out, "dot2: null pointer");
+    DeviceGuard guard(device);
+    PP_CUDA(guard.err);
+    PP_CUDA(launch_pdl(pp::dot2_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, a, b, out));
+    return PP_OK;
+}
+
 extern "C" int pp_memcpy_async(void *dst, const void *src, size_t bytes, int device, void *stream) {
     PP_REQUIRE(dst && src, "memcpy_async: null pointer");
     if (bytes == 0) return PP_OK;
