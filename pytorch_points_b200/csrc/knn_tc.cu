@@ -725,7 +725,8 @@ int knn_tc_launch(const float *query, const float *points, int B, int M, int N, 
         unsigned long long hs[4];
         PP_CUDA(cudaMemcpy(hs, S.counter, sizeof(hs), cudaMemcpyDeviceToHost));
         const double nq = (double)B * M;
-        fprintf(stderr, "knn_tc stats: per query %.1f flagged granules, %.1f candidates, %.3f cuts\n", hs[1] / nq, hs[2] / nq,
+        if (get_option("knn_stats", 0) >= 2)
+            fprintf(stderr, "knn_tc stats: per query %.1f flagged granules, %.1f candidates, %.3f cuts\n", hs[1] / nq, hs[2] / nq,
                 hs[3] / nq);
         g_knn_tiles_visited = v;  // here in units of 128 x 128 (query tile, reference block) pairs
         g_knn_tiles_total = (double)B * L.qtiles * L.rblk;

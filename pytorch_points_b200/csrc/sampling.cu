@@ -460,43 +460,62 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
 }
 
 // ===========================================================================
-// three_interpolate forward / backward (_ext/interpolate_gpu.cu:77-97,120-142): flat
-// one-element-per-thread kernels.  Forward rounding order = what nvcc makes of
-// w0*p0 + w1*p1 + w2*p2:  fma(w2,p2, fma(w0,p0, rn(w1*p1)))  -- middle product first, the same
-// pattern as the 3-term distances (verified bit for bit against the reference kernel).
+// three_interpolate forward / backward (_ext/interpolate_gpu.cu:77-97,120-142).  The reference runs one
+// thread per output element (index arithmetic, three index and three weight reads for every channel).
+// Here a thread owns a point: its three indices and weights are read once (a warp reads 384 contiguous
+// bytes of each), then it walks TI_CH channels -- three gathers from a channel row that sits in L1
+// (m floats), one coalesced store per channel.  HBM-bound on the (B,C,n) output.
+// Forward rounding order = what nvcc makes of w0*p0 + w1*p1 + w2*p2:  fma(w2,p2, fma(w0,p0, rn(w1*p1)))
+// -- middle product first, the same pattern as the 3-term distances (verified bit for bit against the
+// reference kernel).
 // ===========================================================================
+constexpr int TI_CH = 16;  // channels per thread
+
 __global__ void __launch_bounds__(256)
 three_interpolate_fwd_kernel(const float *__restrict__ points, const int *__restrict__ idx,
-                             const float *__restrict__ weight, int C, int M, int N, long long total,
-                             float *__restrict__ out) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int i = (int)(t % N);
-    const long long bc = t / N;  // b*C + c
-    const int b = (int)(bc / C);
+                             const float *__restrict__ weight, int C, int M, int N, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int b = blockIdx.z, c0 = blockIdx.y * TI_CH;
     const int *id = idx + ((size_t)b * N + i) * 3;
     const float *w = weight + ((size_t)b * N + i) * 3;
-    const float *p = points + bc * M;
-    out[t] = __fmaf_rn(__ldg(w + 2), __ldg(p + __ldg(id + 2)),
-                       __fmaf_rn(__ldg(w), __ldg(p + __ldg(id)), __fmul_rn(__ldg(w + 1), __ldg(p + __ldg(id + 1)))));
+    const int i0 = __ldg(id), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+    const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const float *p = points + ((size_t)b * C + c0) * M;
+    float *o = out + ((size_t)b * C + c0) * N + i;
+    const int nc = min(TI_CH, C - c0);
+    if (nc == TI_CH) {
+#pragma unroll
+        for (int c = 0; c < TI_CH; c++)
+            __stcs(o + (size_t)c * N, __fmaf_rn(w2, __ldg(p + (size_t)c * M + i2),
+                                                __fmaf_rn(w0, __ldg(p + (size_t)c * M + i0), __fmul_rn(w1, __ldg(p + (size_t)c * M + i1)))));
+    } else {
+        for (int c = 0; c < nc; c++)
+            o[(size_t)c * N] = __fmaf_rn(w2, __ldg(p + (size_t)c * M + i2),
+                                         __fmaf_rn(w0, __ldg(p + (size_t)c * M + i0), __fmul_rn(w1, __ldg(p + (size_t)c * M + i1))));
+    }
 }
 
 __global__ void __launch_bounds__(256)
 three_interpolate_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx,
-                             const float *__restrict__ weight, int C, int M, int N, long long total,
-                             float *__restrict__ grad_points) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int i = (int)(t % N);
-    const long long bc = t / N;
-    const int b = (int)(bc / C);
+                             const float *__restrict__ weight, int C, int M, int N, float *__restrict__ grad_points) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int b = blockIdx.z, c0 = blockIdx.y * TI_CH;
     const int *id = idx + ((size_t)b * N + i) * 3;
     const float *w = weight + ((size_t)b * N + i) * 3;
-    float *g = grad_points + bc * M;
-    const float go = __ldg(grad_out + t);
-    atomicAdd(g + __ldg(id), __fmul_rn(go, __ldg(w)));
-    atomicAdd(g + __ldg(id + 1), __fmul_rn(go, __ldg(w + 1)));
-    atomicAdd(g + __ldg(id + 2), __fmul_rn(go, __ldg(w + 2)));
+    const int i0 = __ldg(id), i1 = __ldg(id + 1), i2 = __ldg(id + 2);
+    const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    float *g = grad_points + ((size_t)b * C + c0) * M;
+    const float *go = grad_out + ((size_t)b * C + c0) * N + i;
+    const int nc = min(TI_CH, C - c0);
+#pragma unroll 4
+    for (int c = 0; c < nc; c++) {
+        const float v = __ldg(go + (size_t)c * N);
+        atomicAdd(g + (size_t)c * M + i0, __fmul_rn(v, w0));
+        atomicAdd(g + (size_t)c * M + i1, __fmul_rn(v, w1));
+        atomicAdd(g + (size_t)c * M + i2, __fmul_rn(v, w2));
+    }
 }
 
 template <int P, int C>
@@ -742,7 +761,11 @@ extern "C" int pp_three_interpolate_fwd(const float *points, const int32_t *idx,
     PP_REQUIRE(points && idx && weight && out && M > 0, "three_interpolate_fwd: null pointer or empty source");
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
-    three_interpolate_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(points, idx, weight, C, M, N, total, out);
+    PP_REQUIRE(B <= 65535 && ceil_div(C, TI_CH) <= 65535, "three_interpolate_fwd: B or C too large");
+    {
+        KernelTimer timer("three_interpolate", (cudaStream_t)stream);
+        three_interpolate_fwd_kernel<<<dim3(ceil_div(N, 256), ceil_div(C, TI_CH), B), 256, 0, (cudaStream_t)stream>>>(points, idx, weight, C, M, N, out);
+    }
     PP_LAUNCH_CHECK();
     return PP_OK;
 }
@@ -755,7 +778,8 @@ extern "C" int pp_three_interpolate_bwd(const float *grad_out, const int32_t *id
     PP_REQUIRE(grad_out && idx && weight && grad_points && M > 0, "three_interpolate_bwd: null pointer or empty target");
     DeviceGuard guard(device);
     PP_CUDA(guard.err);
-    three_interpolate_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, weight, C, M, N, total, grad_points);
+    PP_REQUIRE(B <= 65535 && ceil_div(C, TI_CH) <= 65535, "three_interpolate_bwd: B or C too large");
+    three_interpolate_bwd_kernel<<<dim3(ceil_div(N, 256), ceil_div(C, TI_CH), B), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, weight, C, M, N, grad_points);
     PP_LAUNCH_CHECK();
     return PP_OK;
 }

@@ -96,7 +96,7 @@ for B, N, k, mk in big:
     _C.set_option("timing", 1); sampling.knn(k, p, p); torch.cuda.synchronize()
     st = {n: _C.timing_collect(n)[0] for n in ("knn_sort", "knn_prep", "knn_seed", "knn", "knn_select")}
     _C.set_option("timing", 0)
-    _C.set_option("knn_stats", 1); sampling.knn(k, p, p); v, tot = _C.knn_stats(); _C.set_option("knn_stats", 0)
+    _C.set_option("knn_stats", 2); sampling.knn(k, p, p); v, tot = _C.knn_stats(); _C.set_option("knn_stats", 0)
     _C.set_option("knn_tc", -1)
     print("k%d B%d N%d %s: equal=%s  ordered sweep %.3f ms | tensor path %.3f ms  (%s)  blocks visited %.1f%%" % (
         k, B, N, mk.__name__, ok, ms0, ms1, " ".join("%s %.3f" % (n, v_) for n, v_ in st.items()), 100 * v / max(tot, 1)), flush=True)
