@@ -839,10 +839,16 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
     ms_f, ms_o = timeit(sa_fused, iters=5, warm=2), timeit(sa_ops, iters=5, warm=2)
     ms_g = timeit(lambda: grouper(x, ctr, f64))
     ms_go = timeit(lambda: grouper_ops(x, ctr, f64))
+    # point-major staging: the features copied once per level to (B,N,C), every scale gathers full lines
+    ms_stage = timeit(lambda: ppn.stage_features(f64))
+    f64_pm = ppn.stage_features(f64)
+    ms_gpm = timeit(lambda: grouper(x, ctr, f64, features_pm=f64_pm))
     out_bytes = 4.0 * B * (3 + 64) * m * 32
     out["sa_stage_B16_N16384_m1024_r0.2_ns32_C64"] = {
         "fused_ms": ms_f, "op_by_op_ms": ms_o, "query_and_group_fused_ms": ms_g,
         "query_and_group_op_by_op_ms": ms_go, "query_and_group_output_GBps": out_bytes / (ms_g * 1e-3) / 1e9,
+        "stage_features_ms": ms_stage, "query_and_group_staged_ms": ms_gpm,
+        "query_and_group_staged_output_GBps": out_bytes / (ms_gpm * 1e-3) / 1e9,
         "note": "op_by_op = the reference's kernel sequence (FPS, gather, ball_query, 2x group_points, "
                 "subtract, cat) on this repo's single kernels"}
     # feature propagation: three_nn of all 16384 points against the 1024
