@@ -904,13 +904,15 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
               "evaluated_pairs_per_s_in_flagging_kernel": float(B) * N * N * vis_tc / max(tot_tc, 1.0) / max(stages["knn"] * 1e-3, 1e-9),
               "note": "tcgen05.mma flagging pass over Morton-ordered 128x128 blocks + exact seed / resolution kernels "
                       "(knn_tc = 1); same bits as the ordered sweep"}
-        if (B, N) == (32, 8192):  # where the tensor path is the automatic choice: k = 32
+        # where the tensor path is the automatic choice: lists wider than 16 -- K = k + 1 = 17 is what the
+        # snapshot's DenseEdgeConv asks for (network/layers.py:52 with k = 16)
+        for kk in ((17, 32) if (B, N) == (32, 8192) else (17,)):
             _C.set_option("knn_tc", 0)
-            ms32_sweep = timeit(lambda: sampling.knn(32, p, p), iters=3, warm=1)
+            ms_sweep = timeit(lambda: sampling.knn(kk, p, p), iters=3, warm=1)
             _C.set_option("knn_tc", -1)
-            ms32 = timeit(lambda: sampling.knn(32, p, p), iters=3, warm=1)
-            tc["k32_ms_per_step_automatic_choice"] = ms32
-            tc["k32_ms_per_step_ordered_sweep"] = ms32_sweep
+            ms_auto = timeit(lambda: sampling.knn(kk, p, p), iters=3, warm=1)
+            tc["k%d_ms_per_step_automatic_choice" % kk] = ms_auto
+            tc["k%d_ms_per_step_ordered_sweep" % kk] = ms_sweep
         out["knn_k16_B%d_N%d" % (B, N)] = {
             "ms_per_step": ms, "point_pairs_per_s": float(B) * N * N / (ms * 1e-3), "sweep_kernel_ms": kms,
             "algorithmic_tflops": 8.0 * B * N * N / (ms * 1e-3) / 1e12,

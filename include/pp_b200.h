@@ -345,7 +345,8 @@ int pp_knn_stats(double *tiles_visited, double *tiles_total);
  *   "fps_cluster" (0)            0 = automatic, else the cluster width 1 / 2 / 4 / 8
  *   "fps_stream" (0)             force the streaming fallback kernel
  *   "knn_morton" (-1)            -1 = automatic, 0 / 1 = never / always use the ordered sweep
- *   "knn_tc" (-1)                -1 = automatic (16 < k <= 32 from N = 2048), 0 / 1 = never / always use the
+ *   "knn_tc" (-1)                -1 = automatic (from N = 2048: 16 < k <= 32, and k <= 16 on jobs of up to 65536
+ *                                queries with clouds of up to 16384 points), 0 / 1 = never / always use the
  *                                tensor-core path (tcgen05 flagging pass + exact resolution; c == 3, k <= 32,
  *                                N <= 262144); timers "knn_sort", "knn_prep", "knn_seed", "knn", "knn_select"
  *   "knn_prune" (1), "knn_estimate" (1), "knn_fused_prep" (1)

@@ -382,10 +382,16 @@ static bool knn_use_tc(int B, int M, int N, int c, int k) {
     if (c != 3 || !knn_tc_supported(B, M, N, k)) return false;
     const int opt = get_option("knn_tc", -1);
     if (opt >= 0) return opt != 0;
-    // measured on B200 (tools/knn_tc_check.py, profiles/r02_knn_tc.txt): on par with the ordered sweep for
-    // k <= 16 (0.49 vs 0.48 ms at B = 32, N = 8192), ahead for wider lists (k = 32: 0.90 vs 1.06 ms), whose
-    // per-candidate insertion the exact pass replaces by one rank count per query
-    return k > 16 && N >= 2048 && get_option("knn_morton", -1) < 0;
+    // measured on B200 (tools/knn_tc_check.py, profiles/r02_knn_tc.txt):
+    //  * lists wider than 16 (K = k + 1 = 17, 20, 21 are what the snapshot's callers ask for): ahead everywhere,
+    //    0.54 vs 0.76 ms at K = 17, B = 32, N = 8192; 1.27 vs 1.82 ms at B = 4, N = 131072 -- the ordered sweep's
+    //    per-candidate insertion switches to full-warp lists there, the exact pass only ranks a few more keys;
+    //  * k <= 16: ahead on small jobs (up to ~65536 queries per call, clouds up to 16384 points: 0.125 vs 0.156 ms
+    //    at B = 2, N = 2048; 0.19 vs 0.22 at B = 4, N = 8192), on par or slightly behind on large ones
+    //    (0.50 vs 0.47 ms at B = 32, N = 8192), where the ordered sweep stays.
+    if (get_option("knn_morton", -1) >= 0 || N < 2048) return false;
+    if (k > 16) return true;
+    return N <= 16384 && (long long)B * M <= 65536;
 }
 
 extern "C" size_t pp_knn_workspace_bytes(int B, int M, int N, int c, int k) {

@@ -541,13 +541,28 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
     const unsigned *fl_warp = flags + ((size_t)b * qtiles + tile) * words * CS_RB + w * 32;
     const float *tau_warp = tau0 + (size_t)b * qtiles * CS_RB + (size_t)tile * CS_RB + w * 32;
 
+    // what a query needs first is requested one query ahead: threshold, coordinates, first flag word, output row
+    float nx_tau = -1.f, nx_x = 0.f, nx_y = 0.f, nx_z = 0.f;
+    unsigned nx_word = 0u;
+    int nx_orig = 0;
+    auto request = [&](int qi) {
+        if (qi < q_count) {
+            const float *q = sq + ((size_t)b * M + q_first + qi) * 3;
+            nx_tau = __ldg(tau_warp + qi);
+            nx_x = __ldg(q); nx_y = __ldg(q + 1); nx_z = __ldg(q + 2);
+            nx_word = nwords > 0 ? __ldg(fl_warp + qi) : 0u;
+            nx_orig = __ldg(sqi + (size_t)b * M + q_first + qi);
+        }
+    };
+    request(0);
     for (int qi = 0; qi < q_count; qi++) {
-        float tau = __ldg(tau_warp + qi);
-        const float *q = sq + ((size_t)b * M + q_first + qi) * 3;
-        const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+        float tau = nx_tau;
+        const float qx = nx_x, qy = nx_y, qz = nx_z;
+        const int orig = nx_orig;
+        unsigned word = nx_word;
+        request(qi + 1);
         int cnt = 0;
         if (!(tau < 0.f)) {
-            unsigned word = __ldg(fl_warp + qi);
             for (int wd = 0; wd < nwords; wd++) {
                 const unsigned next = wd + 1 < nwords ? __ldg(fl_warp + (size_t)(wd + 1) * CS_RB + qi) : 0u;
                 const unsigned short *v8 = sVis + wd * 8;
@@ -566,7 +581,7 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
 #pragma unroll
                     for (int u = 0; u < 4; u++) r[u] = __ldg(refs + off[u]);
                     n_gran += (unsigned)have[0] + have[1] + have[2] + have[3];
-                    if (cnt >= KT_SEL_CAP - 128) {  // room for four granules and the ranking loop's pad (rare)
+                    if (cnt >= KT_SEL_CAP - 136) {  // room for four granules and the ranking loop's pad (rare)
                         n_cut++;
                         // every key counts the keys below it; those ranked below k move to their rank
                         for (int i = lane; i < cnt; i += 32) {
@@ -592,10 +607,9 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
                 word = next;
             }
         }
-        if (lane == 0) buf[cnt] = ~0ull;  // pads the last pair of the ranking loop (cnt < KT_SEL_CAP)
+        if (lane < 8) buf[cnt + lane] = ~0ull;  // pads the last group of the ranking loop (cnt <= KT_SEL_CAP - 8)
         __syncwarp();
         n_cand += cnt;
-        const int orig = __ldg(sqi + (size_t)b * M + q_first + qi);
         float *od = dist + ((size_t)b * M + orig) * k;
         int *oi = idx + ((size_t)b * M + orig) * k;
         // rank = number of keys below mine (keys are distinct: every reference appears once); two keys per LDS.128
@@ -603,10 +617,12 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
             const int i = base + lane;
             const unsigned long long mine = i < cnt ? buf[i] : 0ull;
             int rank = 0;
-#pragma unroll 2
-            for (int j = 0; j < cnt; j += 2) {
-                const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(buf + j);
-                rank += (kk.x < mine ? 1 : 0) + (kk.y < mine ? 1 : 0);
+            for (int j = 0; j < cnt; j += 8) {  // eight keys per trip, four LDS.128
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(buf + j + u);
+                    rank += (kk.x < mine ? 1 : 0) + (kk.y < mine ? 1 : 0);
+                }
             }
             if (i < cnt && rank < k) {
                 od[rank] = __uint_as_float((unsigned)(mine >> 32));
@@ -681,12 +697,18 @@ int knn_tc_launch(const float *query, const float *points, int B, int M, int N, 
     {
         KernelTimer timer("knn_seed", st);
         const dim3 grid(L.qtiles, B);
-        if (k <= 8)
-            kt_seed_kernel<8><<<grid, CS_RB, 0, st>>>(S.sq, S.qk, S.pk, ref4, M, N, L.qtiles, L.rblk, k, self ? 1 : 0, tau0, tilerec);
-        else if (k <= 16)
-            kt_seed_kernel<16><<<grid, CS_RB, 0, st>>>(S.sq, S.qk, S.pk, ref4, M, N, L.qtiles, L.rblk, k, self ? 1 : 0, tau0, tilerec);
-        else
-            kt_seed_kernel<32><<<grid, CS_RB, 0, st>>>(S.sq, S.qk, S.pk, ref4, M, N, L.qtiles, L.rblk, k, self ? 1 : 0, tau0, tilerec);
+        // the K smallest window distances live in registers: the narrowest list that holds k (the insertion
+        // chain is 2 K FMNMX and it is what the kernel spends its time on)
+#define KT_SEED(KK) kt_seed_kernel<KK><<<grid, CS_RB, 0, st>>>(S.sq, S.qk, S.pk, ref4, M, N, L.qtiles, L.rblk, k, self ? 1 : 0, tau0, tilerec)
+        if (k <= 4) KT_SEED(4);
+        else if (k <= 8) KT_SEED(8);
+        else if (k <= 12) KT_SEED(12);
+        else if (k <= 16) KT_SEED(16);
+        else if (k <= 20) KT_SEED(20);
+        else if (k <= 24) KT_SEED(24);
+        else if (k <= 28) KT_SEED(28);
+        else KT_SEED(32);
+#undef KT_SEED
         PP_LAUNCH_CHECK();
     }
     {

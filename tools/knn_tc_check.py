@@ -83,6 +83,10 @@ big = [(32, 8192, 16, uniform_cloud), (32, 8192, 16, sphere_cloud), (4, 131072, 
 if len(sys.argv) > 1 and sys.argv[1] == "regimes":
     big = [(32, 8192, 4, uniform_cloud), (32, 8192, 8, uniform_cloud), (32, 8192, 32, uniform_cloud), (64, 4096, 16, uniform_cloud),
            (128, 2048, 16, uniform_cloud), (8, 32768, 16, uniform_cloud), (1, 262144, 16, uniform_cloud), (32, 2500, 16, sphere_cloud)]
+if len(sys.argv) > 1 and sys.argv[1] == "ks":
+    big = [(32, 8192, kk, uniform_cloud) for kk in (9, 12, 17, 20, 24, 28)] + [(4, 131072, 17, uniform_cloud), (16, 2048, 17, uniform_cloud)]
+if len(sys.argv) > 1 and sys.argv[1] == "small":
+    big = [(B_, N_, 16, uniform_cloud) for (B_, N_) in ((1, 2048), (4, 2048), (8, 2048), (16, 2048), (32, 2048), (1, 4096), (4, 4096), (8, 4096), (16, 4096), (1, 8192), (2, 8192), (4, 8192), (8, 8192), (16, 8192), (1, 16384), (4, 16384), (1, 65536))]
 if quick:
     big = big[:1]
 for B, N, k, mk in big:
