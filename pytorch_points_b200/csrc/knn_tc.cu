@@ -57,7 +57,7 @@ struct KtArgs {
     const float *qnorm;        // (B, qtiles * 128) |q|^2 of the centred queries
     const float *tau0;         // (B, qtiles * 128) seed thresholds (-1: no query)
     const float4 *blockbox;    // (B, rblk, 2) boxes of the reference blocks
-    const float *tilerec;      // (B, qtiles, 8) query box lo/hi, largest TAU0
+    const float *tilerec;      // (B, qtiles, 4 warps, 8): box lo/hi and largest TAU0 of each warp's 32 queries
     const unsigned *r2bits;    // (B) bits of R^2
     unsigned short *vis;       // (B, qtiles, rblk) visited blocks of a tile, ascending
     int *viscnt;               // (B, qtiles)
@@ -85,7 +85,7 @@ KtLayout kt_layout(int B, int M, int N) {
     L.ref4 = o;     o += up(16 * rrows);
     L.blockbox = o; o += up(32 * (size_t)B * L.rblk);
     L.tau0 = o;     o += up(4 * qrows);
-    L.tilerec = o;  o += up(32 * (size_t)B * L.qtiles);
+    L.tilerec = o;  o += up(128 * (size_t)B * L.qtiles);
     L.vis = o;      o += up(2 * (size_t)B * L.qtiles * L.rblk);
     L.viscnt = o;   o += up(4 * (size_t)B * L.qtiles);
     L.flags = o;    o += up(4 * (size_t)B * L.qtiles * L.words * CS_RB);
@@ -211,7 +211,6 @@ kt_seed_kernel(const float *__restrict__ sq, const unsigned long long *__restric
                int rblk, int k, int self, float *__restrict__ tau0, float *__restrict__ tilerec) {
     __shared__ __align__(16) float sX[KT_WIN], sY[KT_WIN], sZ[KT_WIN];
     __shared__ int s_home;
-    __shared__ float s_red[CS_RB / 32][7];
     const int b = blockIdx.y, tile = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int i_q = tile * CS_RB + (int)threadIdx.x;
@@ -297,7 +296,7 @@ kt_seed_kernel(const float *__restrict__ sq, const unsigned long long *__restric
         if (s == k - 1) t0 = l[s];
     if (!ok) t0 = -1.f;
     tau0[(size_t)b * qtiles * CS_RB + i_q] = t0;
-    // the tile's query box and largest threshold
+    // box and largest threshold of every warp's 32 queries (Morton neighbours: much tighter than the tile's box)
     float red[7] = {ok ? qx : PP_INF, ok ? qy : PP_INF, ok ? qz : PP_INF, ok ? qx : -PP_INF, ok ? qy : -PP_INF,
                     ok ? qz : -PP_INF, t0};
 #pragma unroll
@@ -307,15 +306,13 @@ kt_seed_kernel(const float *__restrict__ sq, const unsigned long long *__restric
             const float other = __shfl_xor_sync(FULL_MASK, red[c], o);
             red[c] = c < 3 ? fminf(red[c], other) : fmaxf(red[c], other);
         }
-        if (lane == 0) s_red[w][c] = red[c];
     }
-    __syncthreads();
-    if (threadIdx.x < 7) {
-        const int c = threadIdx.x;
-        float v = s_red[0][c];
+    if (lane < 7) {
+        float v = red[0];
 #pragma unroll
-        for (int u = 1; u < CS_RB / 32; u++) v = c < 3 ? fminf(v, s_red[u][c]) : fmaxf(v, s_red[u][c]);
-        tilerec[((size_t)b * qtiles + tile) * 8 + c] = v;
+        for (int c = 1; c < 7; c++)
+            if (lane == c) v = red[c];
+        tilerec[(((size_t)b * qtiles + tile) * (CS_RB / 32) + w) * 8 + lane] = v;
     }
 }
 
@@ -354,10 +351,15 @@ kt_rowpass_kernel(const KtArgs a) {
     }
     // ---- which reference blocks can hold a neighbour of one of this tile's queries?
     {
-        const float *rec = a.tilerec + ((size_t)b * a.qtiles + tile) * 8;
-        const float qlo[3] = {__ldg(rec), __ldg(rec + 1), __ldg(rec + 2)};
-        const float qhi[3] = {__ldg(rec + 3), __ldg(rec + 4), __ldg(rec + 5)};
-        const float taumax = __ldg(rec + 6);
+        // a block is visited when one of the four 32-query groups of the tile cannot rule it out
+        const float *rec = a.tilerec + ((size_t)b * a.qtiles + tile) * (CS_RB / 32) * 8;
+        float qlo[CS_RB / 32][3], qhi[CS_RB / 32][3], taumax[CS_RB / 32];
+#pragma unroll
+        for (int v = 0; v < CS_RB / 32; v++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) { qlo[v][c] = __ldg(rec + v * 8 + c); qhi[v][c] = __ldg(rec + v * 8 + 3 + c); }
+            taumax[v] = __ldg(rec + v * 8 + 6);
+        }
         const float4 *boxes = a.blockbox + (size_t)b * a.rblk * 2;
         const int ngroups = ceil_div(a.rblk, 32);
         for (int g = w; g < ngroups; g += KT_THREADS / 32) {
@@ -366,15 +368,18 @@ kt_rowpass_kernel(const KtArgs a) {
             if (blk < a.rblk) {
                 const float4 b0 = __ldg(boxes + blk * 2), b1 = __ldg(boxes + blk * 2 + 1);
                 const float blo[3] = {b0.x, b0.y, b0.z}, bhi[3] = {b0.w, b1.x, b1.y};
-                float gap2 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float gsep = fmaxf(0.f, fmaxf(blo[c] - qhi[c], qlo[c] - bhi[c]));
-                    gap2 = fmaf(gsep, gsep, gap2);
+                for (int v = 0; v < CS_RB / 32; v++) {
+                    float gap2 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float gsep = fmaxf(0.f, fmaxf(blo[c] - qhi[v][c], qlo[v][c] - bhi[c]));
+                        gap2 = fmaf(gsep, gsep, gap2);
+                    }
+                    // skipped only when provably too far (margin: the rounded chain can undershoot the real
+                    // distance by a few ulp); NaN compares false -> visited
+                    need = need || !(gap2 * 0.9999f > taumax[v] && gap2 > 1e-30f);
                 }
-                // skipped only when provably too far (margin: the rounded chain can undershoot the real
-                // distance by a few ulp); NaN compares false -> visited
-                need = !(gap2 * 0.9999f > taumax && gap2 > 1e-30f);
             }
             const unsigned m = __ballot_sync(FULL_MASK, need);
             if (lane == 0) sSurvive[g] = m;
