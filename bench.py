@@ -843,12 +843,33 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
     ms_stage = timeit(lambda: ppn.stage_features(f64))
     f64_pm = ppn.stage_features(f64)
     ms_gpm = timeit(lambda: grouper(x, ctr, f64, features_pm=f64_pm))
+    # the calls above are host bound at this size (a Python autograd Function + a 140 MB allocation per call):
+    # the kernels themselves, from the library's CUDA events
+    _C.set_option("timing", 1)
+    kern = {}
+    for name_, fn_ in (("query_and_group_kernel_ms", lambda: grouper(x, ctr, f64)),
+                       ("query_and_group_staged_kernel_ms", lambda: grouper(x, ctr, f64, features_pm=f64_pm))):
+        _C.timing_collect("query_group")
+        for _ in range(5):
+            fn_()
+        torch.cuda.synchronize()
+        tot_, cnt_ = _C.timing_collect("query_group")
+        kern[name_] = tot_ / max(cnt_, 1)
+    _C.timing_collect("channels_to_points")
+    for _ in range(5):
+        ppn.stage_features(f64)
+    torch.cuda.synchronize()
+    tot_, cnt_ = _C.timing_collect("channels_to_points")
+    kern["stage_features_kernel_ms"] = tot_ / max(cnt_, 1)
+    _C.set_option("timing", 0)
     out_bytes = 4.0 * B * (3 + 64) * m * 32
     out["sa_stage_B16_N16384_m1024_r0.2_ns32_C64"] = {
         "fused_ms": ms_f, "op_by_op_ms": ms_o, "query_and_group_fused_ms": ms_g,
         "query_and_group_op_by_op_ms": ms_go, "query_and_group_output_GBps": out_bytes / (ms_g * 1e-3) / 1e9,
         "stage_features_ms": ms_stage, "query_and_group_staged_ms": ms_gpm,
         "query_and_group_staged_output_GBps": out_bytes / (ms_gpm * 1e-3) / 1e9,
+        **kern,
+        "query_and_group_staged_kernel_output_GBps": out_bytes / (max(kern["query_and_group_staged_kernel_ms"], 1e-9) * 1e-3) / 1e9,
         "note": "op_by_op = the reference's kernel sequence (FPS, gather, ball_query, 2x group_points, "
                 "subtract, cat) on this repo's single kernels"}
     # feature propagation: three_nn of all 16384 points against the 1024
