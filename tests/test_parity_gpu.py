@@ -217,6 +217,42 @@ def test_graphed_chamfer_step_and_prefetcher(pp):
     assert torch.equal(x0.cpu(), pairs[0][0]) and torch.equal(y1.cpu(), pairs[1][1])
 
 
+def test_host_scalar_reader_in_the_autograd_loop(pp):
+    """pipeline.HostScalarReader: every step's loss arrives on the host (one step behind, in order) with the
+    value loss.item() would have given, while prefetcher, autograd loss and backward keep running; the
+    non-contiguous / wrong-dtype input path and the bounds are checked too."""
+    from pytorch_points_b200.dist import sharded_chamfer_loss
+    from pytorch_points_b200.pipeline import HostPrefetcher, HostScalarReader
+    pairs = [(uniform_cloud(4, 700, 180 + i).pin_memory(), uniform_cloud(4, 650, 190 + i).pin_memory()) for i in range(3)]
+    pf, rd = HostPrefetcher("cuda", depth=2), HostScalarReader("cuda", depth=2)
+    pf.prefetch(pairs[0])
+    got, want = [], []
+    for it in range(6):
+        xd, yd = pf.get()
+        x, y = xd.detach().requires_grad_(True), yd.detach().requires_grad_(True)
+        loss = sharded_chamfer_loss(x, y, total_batch=4)
+        rd.push(loss)
+        loss.backward()
+        want.append(float(loss.detach().cpu()))
+        pf.release()
+        pf.prefetch(pairs[(it + 1) % 3])
+        if len(rd) > 1:
+            got.append(rd.pop())
+    while len(rd):
+        got.append(rd.pop())
+    assert got == want
+    # reference value of the first step
+    d1, d2, _, _ = pp.nndistance(dev(pairs[0][0]), dev(pairs[0][1]))
+    assert abs(got[0] - (d1.mean() + d2.mean()).item()) <= 1e-6 * abs(got[0])
+    with pytest.raises(RuntimeError):
+        rd.pop()
+    rd2 = HostScalarReader("cuda:0", depth=1, numel=2)
+    rd2.push(torch.tensor([[1.5], [2.5]], dtype=torch.float64, device="cuda").t())  # reshaped, cast, made contiguous
+    with pytest.raises(RuntimeError):
+        rd2.push(torch.zeros(2, device="cuda"))
+    assert rd2.pop() == [1.5, 2.5]
+
+
 def test_graphed_chamfer_step_pipelined(pp):
     """submit()/loss(): two steps in flight; each ticket returns the loss of ITS step even though the
     pinned host buffers are rewritten with new clouds as soon as their copy has been consumed."""
