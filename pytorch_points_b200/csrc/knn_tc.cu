@@ -512,13 +512,16 @@ kt_rowpass_kernel(const KtArgs a) {
 // ---- exact pass ------------------------------------------------------------------------------------------
 // grid (qtiles, B), 128 threads.  A warp takes 32 queries of the tile, one after the other with all 32 lanes.
 // Everything that steers the loop is warp-uniform (the query's flag words are read by all lanes at once):
-//   * up to four flagged granules per trip: lane = reference (independent coalesced 512-byte reads in flight),
+//   * up to two flagged granules per trip: lane = reference (independent coalesced 512-byte reads in flight),
 //     the references with d <= TAU0 are compacted (ballot + prefix count) into the warp's candidate buffer as
 //     keys (distance bits << 32 | original index);
 //   * finally every candidate counts the keys below its own -- that rank is its output slot.
 // A buffer about to overflow (degenerate data: hundreds of equal distances) is cut back to its k smallest
 // keys and the threshold drops to the k-th of them.
 constexpr int KT_SEL_CAP = 256;   // candidate keys per warp (two buffers)
+// flagged granules per trip of the exact pass: a query's ~5 granules are spread over ~4 flag words, so wider trips
+// mostly carry idle slots (measured: 4 slots 0.230 ms, 2 slots 0.213, 1 slot 0.230 at B = 32, N = 8192, k = 16)
+constexpr int KT_SEL_SLOTS = 2;
 
 __global__ void __launch_bounds__(CS_RB)
 kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, const float4 *__restrict__ ref4,
@@ -572,20 +575,21 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
                 const unsigned next = wd + 1 < nwords ? __ldg(fl_warp + (size_t)(wd + 1) * CS_RB + qi) : 0u;
                 const unsigned short *v8 = sVis + wd * 8;
                 while (word) {  // warp-uniform
-                    // up to four flagged granules per trip
-                    unsigned off[4];
-                    bool have[4];
+                    // up to KT_SEL_SLOTS flagged granules per trip
+                    unsigned off[KT_SEL_SLOTS];
+                    bool have[KT_SEL_SLOTS];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < KT_SEL_SLOTS; u++) {
                         have[u] = word != 0u;
                         const int bit = have[u] ? __ffs(word) - 1 : 0;
                         word &= word - 1u;  // (0 stays 0)
                         off[u] = (unsigned)v8[bit >> 2] * CS_RB + (bit & 3) * KT_GR;
                     }
-                    float4 r[4];
+                    float4 r[KT_SEL_SLOTS];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) r[u] = __ldg(refs + off[u]);
-                    n_gran += (unsigned)have[0] + have[1] + have[2] + have[3];
+                    for (int u = 0; u < KT_SEL_SLOTS; u++) r[u] = __ldg(refs + off[u]);
+                    #pragma unroll
+                    for (int u = 0; u < KT_SEL_SLOTS; u++) n_gran += have[u] ? 1u : 0u;
                     if (cnt >= KT_SEL_CAP - 136) {  // room for four granules and the ranking loop's pad (rare)
                         n_cut++;
                         // every key counts the keys below it; those ranked below k move to their rank
@@ -601,7 +605,7 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
                         if (cnt == k) tau = __uint_as_float((unsigned)(buf[k - 1] >> 32));
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < KT_SEL_SLOTS; u++) {
                         const float d = sqdist_xyz(r[u].x, r[u].y, r[u].z, qx, qy, qz);
                         const bool pass = have[u] && d <= tau && d < PP_INF;
                         const unsigned m = __ballot_sync(FULL_MASK, pass);
