@@ -212,7 +212,8 @@ int pp_channels_to_points(const float *in, int B, int C, int N, float *out, int 
 
 /* --------------------------------------------------------------------- knn */
 
-/* Scratch bytes pp_knn needs. */
+/* Scratch bytes pp_knn needs for the path it would choose with the options in force now (pp_set_option):
+ * query it after setting them.  pp_knn returns PP_ENOSPC for a workspace that is too small. */
 size_t pp_knn_workspace_bytes(int B, int M, int N, int c, int k);
 
 /*

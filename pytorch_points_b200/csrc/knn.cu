@@ -397,10 +397,10 @@ static bool knn_use_tc(int B, int M, int N, int c, int k) {
 extern "C" size_t pp_knn_workspace_bytes(int B, int M, int N, int c, int k) {
     if (B <= 0 || M <= 0 || N <= 0) return 0;
     if (c != 3 || k > 32) return 0;
-    // upper bound over the paths the options can select
-    const size_t a = knn_morton_workspace_bytes(B, M, N);
-    const size_t t = knn_tc_supported(B, M, N, k) ? knn_tc_workspace_bytes(B, M, N) : 0;
-    return a > t ? a : t;
+    // what the path pp_knn would choose right now needs (the choice depends on the options in force: query
+    // the size after setting them; pp_knn refuses a workspace that is too small, it never overruns it)
+    if (knn_use_tc(B, M, N, c, k)) return knn_tc_workspace_bytes(B, M, N);
+    return knn_morton_workspace_bytes(B, M, N);
 }
 
 extern "C" int pp_knn(const float *query, const float *points, int B, int M, int N, int c, int k,
