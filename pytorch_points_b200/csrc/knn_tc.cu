@@ -592,6 +592,7 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
                     for (int u = 0; u < KT_SEL_SLOTS; u++) n_gran += have[u] ? 1u : 0u;
                     if (cnt >= KT_SEL_CAP - 136) {  // room for four granules and the ranking loop's pad (rare)
                         n_cut++;
+                        __syncwarp();  // the keys other lanes wrote in the previous trips are read below
                         // every key counts the keys below it; those ranked below k move to their rank
                         for (int i = lane; i < cnt; i += 32) {
                             const unsigned long long mine = buf[i];
