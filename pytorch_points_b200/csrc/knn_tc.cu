@@ -518,6 +518,17 @@ kt_rowpass_kernel(const KtArgs a) {
 //   * finally every candidate counts the keys below its own -- that rank is its output slot.
 // A buffer about to overflow (degenerate data: hundreds of equal distances) is cut back to its k smallest
 // keys and the threshold drops to the k-th of them.
+// rank += (a < b) on 64-bit keys: two compares and one predicated add
+__device__ __forceinline__ void kt_count_less(int &rank, unsigned long long a, unsigned long long b) {
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.lt.u64 p, %1, %2;\n\t"
+        "@p add.s32 %0, %0, 1;\n\t"
+        "}"
+        : "+r"(rank)
+        : "l"(a), "l"(b));
+}
+
 constexpr int KT_SEL_CAP = 256;   // candidate keys per warp (two buffers)
 // flagged granules per trip of the exact pass: a query's ~5 granules are spread over ~4 flag words, so wider trips
 // mostly carry idle slots (measured: 4 slots 0.230 ms, 2 slots 0.213, 1 slot 0.230 at B = 32, N = 8192, k = 16)
@@ -571,8 +582,10 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
         request(qi + 1);
         int cnt = 0;
         if (!(tau < 0.f)) {
+            const unsigned *fw = fl_warp + qi;
             for (int wd = 0; wd < nwords; wd++) {
-                const unsigned next = wd + 1 < nwords ? __ldg(fl_warp + (size_t)(wd + 1) * CS_RB + qi) : 0u;
+                fw += CS_RB;
+                const unsigned next = wd + 1 < nwords ? __ldg(fw) : 0u;
                 const unsigned short *v8 = sVis + wd * 8;
                 while (word) {  // warp-uniform
                     // up to KT_SEL_SLOTS flagged granules per trip
@@ -631,7 +644,8 @@ kt_select_kernel(const float *__restrict__ sq, const int *__restrict__ sqi, cons
 #pragma unroll
                 for (int u = 0; u < 8; u += 2) {
                     const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(buf + j + u);
-                    rank += (kk.x < mine ? 1 : 0) + (kk.y < mine ? 1 : 0);
+                    kt_count_less(rank, kk.x, mine);
+                    kt_count_less(rank, kk.y, mine);
                 }
             }
             if (i < cnt && rank < k) {
