@@ -735,6 +735,24 @@ def test_knn_tensor_core_path_matches_oracle(pp, oracle_mod, name, B, M, N, k):
     assert np.array_equal(np32(idx), ei) and np.array_equal(np32(dist), ed)
 
 
+def test_knn_points_adaptor_at_the_callers_list_width(pp, oracle_mod):
+    """`ops.knn_points(x, x, K=k+1, return_nn=True)` with k = 16 (network/layers.py:52) and K = nn_size = 20
+    (geo_operations.py:112): lists wider than 16 take the tensor-core path automatically -- same bits as the
+    oracle, self dropped by the caller's slice."""
+    x = uniform_cloud(2, 4096, 321)
+    for K in (17, 20):
+        ed, ei = oracle_mod.knn(K, np32(x), np32(x))
+        d, i, nn = pp.knn_points(dev(x), dev(x), K=K, return_nn=True)
+        assert i.dtype == torch.int64
+        assert np.array_equal(np32(i), ei.astype(np.int64)) and np.array_equal(np32(d), ed)
+        assert np.array_equal(np32(i[:, :, 0]), np.broadcast_to(np.arange(4096), (2, 4096)))  # self first
+        assert np.array_equal(np32(nn), np.take_along_axis(np32(x)[:, None], ei[..., None].astype(np.int64), 2))
+    q = uniform_cloud(2, 1500, 322)
+    ed, ei = oracle_mod.knn(17, np32(q), np32(x))
+    d, i = pp.knn_points(dev(q), dev(x), K=17)[:2]
+    assert np.array_equal(np32(i), ei.astype(np.int64)) and np.array_equal(np32(d), ed)
+
+
 def test_knn_tensor_core_path_nonfinite_points(pp):
     """Non-finite points are never neighbours and a non-finite query gets (inf, -1): same as the ordered sweep."""
     from pytorch_points_b200 import _C
