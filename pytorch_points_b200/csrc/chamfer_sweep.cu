@@ -47,6 +47,7 @@
 //                         the rate the same loads reach alone.
 //   cs_finalize_kernel    exact resolution: the recorded granule, or for ambiguous points the blocks of the mask
 //                         (dist / idx, loss sums, fused backward).
+#include <algorithm>
 #include <atomic>
 
 #include "pp_common.cuh"
@@ -84,6 +85,7 @@ struct CsArgs {
     const unsigned *r2part;  // (B, CS_R2_SLOTS) bits of the preparation CTAs' largest centred squared norms
     unsigned *taubits;       // (B) bits of TAU, written by the sweep for the resolving kernel
     float *sums;             // [sum(dist1), sum(dist2)] or null
+    unsigned *qctr;          // work-item counter of the persistent sweep (zeroed by the preparation kernel)
     const float *gw;         // fused backward weights or null
     int B;
 };
@@ -98,7 +100,7 @@ CsLayout cs_layout(int B, int N, int M) {
     const int n[2] = {N, M};
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o = 0;
-    L.ctrl = o; o += up(4 * (size_t)B * (CS_R2_SLOTS + 1));  // r2part[B][CS_R2_SLOTS], taubits[B]
+    L.ctrl = o; o += up(4 * ((size_t)B * (CS_R2_SLOTS + 1) + 1));  // r2part[B][CS_R2_SLOTS], taubits[B], item counter
     for (int s = 0; s < 2; s++) {
         L.blk[s] = ceil_div(n[s], CS_RB);
         const size_t rows = (size_t)B * L.blk[s] * CS_RB;
@@ -131,8 +133,9 @@ cs_prep_kernel(const float *__restrict__ xyz1, const float *__restrict__ xyz2, i
                float *__restrict__ nm1, unsigned long long *__restrict__ key0, unsigned long long *__restrict__ key1,
                unsigned *__restrict__ sec0, unsigned *__restrict__ sec1, unsigned long long *__restrict__ msk0,
                unsigned long long *__restrict__ msk1, unsigned *__restrict__ r2part, float *__restrict__ g1,
-               float *__restrict__ g2) {
+               float *__restrict__ g2, unsigned *__restrict__ qctr) {
     pdl_launch_dependents();
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *qctr = 0u;
     const int b = blockIdx.y, s = blockIdx.z;
     const int lane = threadIdx.x & 31;
     __shared__ float s_c[3];
@@ -380,6 +383,225 @@ cs_rowpass_tc_kernel(const CsArgs args) {
     if (w == TC_EPI) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+// ---- the same pass as a persistent kernel with a work queue --------------------------------------------------
+// One CTA per accumulator pair (two per SM) takes work items (direction, cloud, query tile, chunk) off a global
+// counter.  What a fresh CTA pays per tile -- launch, tensor-memory allocation behind the CTA that just left,
+// barrier set-up, the first operand copies with nothing to overlap them, the last accumulator drained with the
+// tensor pipe idle -- is paid once per CTA: the copy issuer fetches the next item and runs ahead into it (the
+// query tile is double buffered, the reference ring never drains), the MMA issuer follows, and the epilogue warps
+// only store one item's results and clear their registers between two accumulators.  The item number travels
+// with the query tile's slot (written before the slot's full barrier is armed); -1 ends the kernel.  Barrier
+// parities follow from use counters that all roles advance identically.
+constexpr int TCP_SMEM = (2 + TC_STAGES) * TC_TILE_BYTES;
+
+struct CsItem { int dir, b, tile, chunk; };
+__device__ __forceinline__ CsItem cs_item(const CsArgs &args, int wi, int items0) {
+    CsItem it;
+    it.dir = wi >= items0 ? 1 : 0;
+    const CsDir &D = args.d[it.dir];
+    const int local = wi - (it.dir ? items0 : 0);
+    const int per_cloud = D.tiles * D.nchunks;
+    it.b = local / per_cloud;
+    const int rem = local - it.b * per_cloud;
+    it.tile = rem / D.nchunks;
+    it.chunk = rem - it.tile * D.nchunks;
+    return it;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+cs_rowpass_tc_persistent_kernel(const CsArgs args, int items0, int items_total) {
+    extern __shared__ __align__(128) unsigned char cs_dyn_smem[];  // 2 A tiles | TC_STAGES B tiles
+    unsigned char (*sA)[TC_TILE_BYTES] = reinterpret_cast<unsigned char (*)[TC_TILE_BYTES]>(cs_dyn_smem);
+    unsigned char (*sB)[TC_TILE_BYTES] = reinterpret_cast<unsigned char (*)[TC_TILE_BYTES]>(cs_dyn_smem + 2 * TC_TILE_BYTES);
+    // a_full[2] | a_empty[2] | b_full[S] | b_empty[S] | t_full[2] | t_empty[2]
+    __shared__ __align__(8) unsigned long long sBar[4 + 2 * TC_STAGES + 4];
+    __shared__ unsigned sTmem;
+    __shared__ int sItem[2];
+
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned bar_af = smem_u32(sBar), bar_ae = smem_u32(sBar + 2);
+    const unsigned bar_bf = smem_u32(sBar + 4), bar_be = smem_u32(sBar + 4 + TC_STAGES);
+    const unsigned bar_tf = smem_u32(sBar + 4 + 2 * TC_STAGES), bar_te = smem_u32(sBar + 6 + 2 * TC_STAGES);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            mbar_init(bar_af + 8 * i, 1);
+            mbar_init(bar_ae + 8 * i, 1 + TC_EPI);  // the item's MMAs are through AND every epilogue warp has read the item number
+        }
+#pragma unroll
+        for (int i = 0; i < TC_STAGES; i++) { mbar_init(bar_bf + 8 * i, 1); mbar_init(bar_be + 8 * i, 1); }
+#pragma unroll
+        for (int i = 0; i < 2; i++) { mbar_init(bar_tf + 8 * i, 1); mbar_init(bar_te + 8 * i, TC_EPI); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (w == TC_EPI) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&sTmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = sTmem;
+    pdl_wait();  // the prepared operands, R^2, the reset keys and the cleared item counter are complete and visible
+
+    if (w == TC_EPI) {
+        if (lane == 0) {  // ---- copy issuer: takes the items off the queue
+            unsigned used = 0u, uses = 0u;  // per stage: used before / parity of its use count
+            for (int ai = 0;; ai++) {
+                const int slot = ai & 1;
+                // the slot's previous item (ai - 2) is through: completion number (ai >> 1) - 1 of its empty barrier
+                if (ai >= 2) mbar_wait(bar_ae + 8 * slot, (unsigned)((ai >> 1) - 1) & 1u);
+                const int wi = (int)atomicAdd(args.qctr, 1u);
+                if (wi >= items_total) {
+                    sItem[slot] = -1;
+                    mbar_arrive(bar_af + 8 * slot);
+                    break;
+                }
+                sItem[slot] = wi;
+                const CsItem it = cs_item(args, wi, items0);
+                const CsDir &D = args.d[it.dir];
+                const int blk0 = it.chunk * D.chunk_blocks;
+                const int nblk = min(D.rblk, blk0 + D.chunk_blocks) - blk0;
+                mbar_expect_tx(bar_af + 8 * slot, TC_TILE_BYTES);
+                bulk_g2s(smem_u32(sA[slot]), D.aform + ((size_t)it.b * D.tiles + it.tile) * (TC_TILE_BYTES / 4), TC_TILE_BYTES,
+                         bar_af + 8 * slot);
+                const float *src = D.bform + ((size_t)it.b * D.rblk + blk0) * (TC_TILE_BYTES / 4);
+                for (int i = 0; i < nblk; i++) {
+                    const int st = i % TC_STAGES;
+                    if ((used >> st) & 1u) mbar_wait(bar_be + 8 * st, ((uses >> st) & 1u) ^ 1u);
+                    used |= 1u << st;
+                    uses ^= 1u << st;
+                    mbar_expect_tx(bar_bf + 8 * st, TC_TILE_BYTES);
+                    bulk_g2s(smem_u32(sB[st]), src + (size_t)i * (TC_TILE_BYTES / 4), TC_TILE_BYTES, bar_bf + 8 * st);
+                }
+            }
+        }
+    } else if (w == TC_EPI + 1) {
+        if (lane == 0) {  // ---- MMA issuer
+            constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+            const unsigned long long bdesc0 = tc_smem_desc(smem_u32(sB[0]));
+            // parity of the next completion to wait for, per stage and per accumulator: registers with constant
+            // indices in the unrolled loop.  The accumulators start out "drained" (pre-arrival of the epilogue warps).
+            unsigned pf[TC_STAGES], pt[2] = {0u, 0u};
+#pragma unroll
+            for (int u = 0; u < TC_STAGES; u++) pf[u] = 0u;
+            int ai = 0;
+            for (;; ai++) {
+                const int slot = ai & 1;
+                mbar_wait(bar_af + 8 * slot, (unsigned)(ai >> 1) & 1u);
+                const int wi = sItem[slot];
+                if (wi < 0) break;
+                const CsItem it = cs_item(args, wi, items0);
+                const CsDir &D = args.d[it.dir];
+                const int blk0 = it.chunk * D.chunk_blocks;
+                const int nblk = min(D.rblk, blk0 + D.chunk_blocks) - blk0;
+                const unsigned long long adesc = tc_smem_desc(smem_u32(sA[slot]));
+                for (int i0 = 0; i0 < nblk; i0 += TC_STAGES) {
+#pragma unroll
+                    for (int u = 0; u < TC_STAGES; u++) {
+                        if (i0 + u >= nblk) break;
+                        const int acc = u & 1;
+                        mbar_wait(bar_bf + 8 * u, pf[u]);
+                        pf[u] ^= 1u;
+                        mbar_wait(bar_te + 8 * acc, pt[acc]);
+                        pt[acc] ^= 1u;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const unsigned long long bdesc = bdesc0 + (unsigned long long)(u * (TC_TILE_BYTES >> 4));
+                        const unsigned d = tmem + (unsigned)acc * 128u;
+                        tc_mma_tf32(d, adesc, bdesc, idesc, 0u);
+                        tc_mma_tf32(d, adesc + (2 * 2048 >> 4), bdesc + (2 * 2048 >> 4), idesc, 1u);
+                        tc_commit(bar_be + 8 * u);
+                        tc_commit(bar_tf + 8 * acc);
+                    }
+                }
+                tc_commit(bar_ae + 8 * slot);
+            }
+            // nothing of this CTA may still be in flight towards its shared memory when it exits
+            if (ai > 0) mbar_wait(bar_ae + 8 * ((ai - 1) & 1), (unsigned)((ai - 1) >> 1) & 1u);
+        }
+    } else {
+        // ---- epilogue warps: thread = query = TMEM lane
+        if (lane == 0) { mbar_arrive(bar_te); mbar_arrive(bar_te + 8); }  // both accumulators start out drained
+        unsigned tfp[2] = {0u, 0u};  // parity of the next full-barrier completion to wait for, per accumulator
+        for (int ai = 0;; ai++) {
+            const int slot = ai & 1;
+            mbar_wait(bar_af + 8 * slot, (unsigned)(ai >> 1) & 1u);
+            const int wi = sItem[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_ae + 8 * slot);  // this warp has the item number
+            if (wi < 0) break;
+            const CsItem it = cs_item(args, wi, items0);
+            const CsDir &D = args.d[it.dir];
+            const int b = it.b;
+            const int blk0 = it.chunk * D.chunk_blocks;
+            const int nblk = min(D.rblk, blk0 + D.chunk_blocks) - blk0;
+            const int i_q = it.tile * CS_RB + (int)threadIdx.x;
+            const unsigned rb = __reduce_max_sync(FULL_MASK, max(__ldcg(args.r2part + (size_t)b * CS_R2_SLOTS + lane),
+                                                                 __ldcg(args.r2part + (size_t)b * CS_R2_SLOTS + 32 + lane)));
+            const float tau = __uint_as_float(rb) * CS_TAU_PER_R2;
+            if (it.dir == 0 && it.tile == 0 && it.chunk == 0 && threadIdx.x == 0) args.taubits[b] = __float_as_uint(tau);
+            float best = PP_INF, second = PP_INF;
+            int gran = 0;
+            unsigned long long mask = 0ull;
+#pragma unroll 2
+            for (int i = 0; i < nblk; i++) {  // (unrolled by two: the accumulator index is a constant of each copy)
+                const int acc = i & 1;
+                mbar_wait(bar_tf + 8 * acc, tfp[acc]);
+                tfp[acc] ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned t0 = tmem + ((unsigned)(w * 32) << 16) + (unsigned)acc * 128u;
+                unsigned raw[TC_GRAN_PER_WARP][32];
+#pragma unroll
+                for (int gi = 0; gi < TC_GRAN_PER_WARP; gi++) tc_ld32_issue(t0 + gi * CS_GR, raw[gi]);
+#pragma unroll
+                for (int gi = 0; gi < TC_GRAN_PER_WARP; gi++) tc_ld_wait(raw[gi]);
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_te + 8 * acc);
+                float bm = PP_INF;
+#pragma unroll
+                for (int gi = 0; gi < TC_GRAN_PER_WARP; gi++) {
+                    float v[32];
+#pragma unroll
+                    for (int k = 0; k < 32; k++) v[k] = __uint_as_float(raw[gi][k]);
+                    float m0 = fmin3(v[0], v[1], v[2]), m1 = fmin3(v[3], v[4], v[5]);
+                    float m2 = fmin3(v[6], v[7], v[8]), m3 = fmin3(v[9], v[10], v[11]);
+                    m0 = fmin3(m0, v[12], v[13]); m1 = fmin3(m1, v[14], v[15]);
+                    m2 = fmin3(m2, v[16], v[17]); m3 = fmin3(m3, v[18], v[19]);
+                    m0 = fmin3(m0, v[20], v[21]); m1 = fmin3(m1, v[22], v[23]);
+                    m2 = fmin3(m2, v[24], v[25]); m3 = fmin3(m3, v[26], v[27]);
+                    m0 = fmin3(m0, v[28], v[29]); m1 = fmin3(m1, v[30], v[31]);
+                    const float gm = fminf(fmin3(m0, m1, m2), m3);
+                    const int gid = (blk0 + i) * (CS_RB / CS_GR) + gi;
+                    second = fminf(second, fmaxf(best, gm));
+                    if (gm < best) gran = gid;
+                    best = fminf(best, gm);
+                    bm = fminf(bm, gm);
+                }
+                if (bm <= __fadd_rn(best, tau)) mask |= 1ull << ((blk0 + i) >> D.mask_shift);
+            }
+            if (i_q < D.nq) {
+                const float qq = __fadd_rn(__ldg(D.norm + (size_t)b * D.tiles * CS_RB + i_q), tau);
+                const unsigned long long key = ((unsigned long long)__float_as_uint(__fadd_rn(best, qq)) << 32) | (unsigned)gran;
+                const unsigned sb = __float_as_uint(__fadd_rn(second, qq));
+                const size_t t = (size_t)b * D.nq + i_q;
+                if (D.nchunks == 1) {
+                    D.key[t] = key; D.sec[t] = sb; D.mask[t] = mask;
+                } else {
+                    const unsigned long long old = atomicMin(D.key + t, key);
+                    atomicMin(D.sec + t, min((unsigned)((old > key ? old : key) >> 32), sb));
+                    atomicOr(D.mask + t, mask);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == TC_EPI) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 // ---- exact resolution ------------------------------------------------------------------------------
 // One launch for both directions: blocks [0, blocks0) take the points of cloud 1 (dist1 / idx1), the
 // rest those of cloud 2.  A warp takes 32 points, one after the other with all 32 lanes:
@@ -581,6 +803,7 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
     unsigned *r2part = (unsigned *)(ws + L.ctrl);
     CsArgs A;
     A.r2part = r2part; A.taubits = r2part + (size_t)B * CS_R2_SLOTS; A.sums = sums; A.gw = gw; A.B = B;
+    A.qctr = A.taubits + B;
     const int n[2] = {N, M};
     const float *xyz[2] = {xyz1, xyz2};
     float *dist[2] = {dist1, dist2};
@@ -627,7 +850,7 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
             (float *)(ws + L.bform[1]), (float *)(ws + L.norm[0]), (float *)(ws + L.norm[1]),
             (unsigned long long *)(ws + L.key[0]), (unsigned long long *)(ws + L.key[1]), (unsigned *)(ws + L.sec[0]),
             (unsigned *)(ws + L.sec[1]), (unsigned long long *)(ws + L.mask[0]), (unsigned long long *)(ws + L.mask[1]),
-            r2part, g[0], g[1]);
+            r2part, g[0], g[1], A.qctr);
         PP_LAUNCH_CHECK();
     }
     {
@@ -640,7 +863,25 @@ int chamfer_sweep_launch(const float *xyz1, const float *xyz2, int B, int N, int
             PP_CUDA(cudaFuncSetAttribute(cs_rowpass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (dev >= 0 && dev < 64) opted_in[dev].store(true, std::memory_order_release);
         }
-        PP_CUDA(launch_pdl(cs_rowpass_tc_kernel, dim3(grid_x, B, 2), dim3(TC_THREADS), smem, st, A));
+        // Persistent form with a work queue: measured 4-5 % faster on clouds of up to ~4096 points (20-32 blocks per
+        // tile: the per-CTA set-up it removes matters there), 1 % slower at 8192 (64 blocks per tile: the hardware's
+        // CTA turnover is already hidden behind the other CTA of the SM) -- profiles/r02_chamfer_tc_pipeline_experiments.txt
+        const int persistent_opt = get_option("chamfer_persistent", -1);
+        if (persistent_opt >= 0 ? persistent_opt != 0 : std::max(L.blk[0], L.blk[1]) <= 32) {
+            static std::atomic<bool> opted_in_p[64];
+            if (dev < 0 || dev >= 64 || !opted_in_p[dev].load(std::memory_order_acquire)) {
+                PP_CUDA(cudaFuncSetAttribute(cs_rowpass_tc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM));
+                if (dev >= 0 && dev < 64) opted_in_p[dev].store(true, std::memory_order_release);
+            }
+            const long long items0 = (long long)B * A.d[0].tiles * A.d[0].nchunks;
+            const long long items = items0 + (long long)B * A.d[1].tiles * A.d[1].nchunks;
+            PP_REQUIRE(items < (1ll << 30), "chamfer: too many tiles");
+            const int grid = (int)std::min<long long>(items, 2ll * NUM_SMS_B200);
+            PP_CUDA(launch_pdl(cs_rowpass_tc_persistent_kernel, dim3(grid), dim3(TC_THREADS), (size_t)TCP_SMEM, st, A, (int)items0,
+                               (int)items));
+        } else {
+            PP_CUDA(launch_pdl(cs_rowpass_tc_kernel, dim3(grid_x, B, 2), dim3(TC_THREADS), smem, st, A));
+        }
         PP_LAUNCH_CHECK();
     }
     {

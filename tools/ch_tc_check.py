@@ -34,7 +34,9 @@ for name, a, b in cases:
     a, b = a.cuda().contiguous(), b.cuda().contiguous()
     want = run(a, b, 1 if a.shape[1] > 4096 else 32)
     for rep in range(2):
+        _C.set_option("chamfer_persistent", rep)
         got = run(a, b, 51)
+        _C.set_option("chamfer_persistent", 0)
         nd = [int((x != y).sum()) for x, y in zip(got[:4], want[:4])]
         if any(nd) or not torch.allclose(got[4], want[4], rtol=1e-4):
             bad += 1
@@ -51,8 +53,9 @@ for B, N in [(32, 2500), (32, 4096), (32, 8192), (256, 8192)]:
     i1 = torch.empty(B, N, dtype=torch.int32, device="cuda"); i2 = torch.empty(B, N, dtype=torch.int32, device="cuda")
     gw = torch.full((2,), 1.0 / (B * N), device="cuda"); g1, g2 = torch.empty_like(a), torch.empty_like(b)
     sums = torch.zeros(2, device="cuda")
-    for v in (1, 51):
+    for v, pers in ((1, 0), (51, 0), (51, 1)):
         _C.set_option("chamfer_variant", v)
+        _C.set_option("chamfer_persistent", pers)
         fn = lambda: losses.nmdistance_forward_backward_uniform(a, b, d1, d2, i1, i2, sums, gw, g1, g2)
         for _ in range(3): fn()
         torch.cuda.synchronize(); ts = []
@@ -69,5 +72,5 @@ for B, N in [(32, 2500), (32, 4096), (32, 8192), (256, 8192)]:
             tot, cnt = _C.timing_collect(k)
             if cnt: parts.append("%s %.4f" % (k, tot / cnt))
         _C.set_option("timing", 0)
-        print("B%d N%d variant %d: fused step %.4f ms (%.3e pairs/s) | %s" % (B, N, v, ms, B * N * N / ms * 1e3, ", ".join(parts)), flush=True)
+        print("B%d N%d variant %d persistent %d: fused step %.4f ms (%.3e pairs/s) | %s" % (B, N, v, pers, ms, B * N * N / ms * 1e3, ", ".join(parts)), flush=True)
     _C.set_option("chamfer_variant", 0)
