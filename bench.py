@@ -721,9 +721,11 @@ def run_extras(dev, _C, peak_tflops, pipe_pairs):
             else:
                 losses.nmdistance_forward(a, b, d1, d2, i1, i2, sums=sums)
                 losses.nmdistance_backward_uniform(a, b, g1, g2, gw, i1, i2)
+        ms = timeit(chamfer_step)  # the step as it runs (programmatic dependent launch between its kernels)
+        # the forward kernel alone: a separate pass with the library's CUDA events (launches fully serialised there)
         _C.set_option("timing", 1)
         _C.timing_collect("chamfer_fwd")
-        ms = timeit(chamfer_step)
+        timeit(chamfer_step, iters=10, warm=0)
         tot, cnt = _C.timing_collect("chamfer_fwd")
         _C.set_option("timing", 0)
         kms = tot / max(cnt, 1)

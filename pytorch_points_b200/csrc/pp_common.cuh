@@ -113,7 +113,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = get_option("pdl", 1) ? 1 : 0;
+    // with per-kernel timing on, kernels are launched fully serialised: CUDA events around a kernel that was allowed
+    // to become resident during its predecessor do not bracket that kernel alone
+    cfg.numAttrs = (get_option("pdl", 1) && !get_option("timing", 0)) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
