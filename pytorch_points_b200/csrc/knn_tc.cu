@@ -16,18 +16,19 @@
 //                         every 128-reference block.
 //   3. kt_seed_kernel     CTA = 128 queries.  Every query's exact k-th smallest distance inside a
 //                         window of 256 references around the tile's place on the curve: an upper
-//                         bound TAU0 of its true k-th distance.  Also the tile's query box and the
-//                         largest TAU0 of the tile.
-//   4. kt_rowpass_kernel  CTA = 128 queries (TMEM lane = query) x the reference blocks whose box is
-//                         not provably farther than the tile's largest TAU0 (exact box test).  The
+//                         bound TAU0 of its true k-th distance.  Also the box and the largest TAU0 of
+//                         each of the tile's four 32-query groups.
+//   4. kt_rowpass_kernel  CTA = 128 queries (TMEM lane = query) x the reference blocks that one of the
+//                         four groups cannot rule out (box farther than its largest TAU0: exact test).  The
 //                         accumulator holds e = |r|^2 - 2 q.r for 128 x 128 pairs; a thread reduces
 //                         every 32 of its values to their minimum and flags the 32-reference granule
 //                         when that minimum is within the approximation's error bound of TAU0 - |q|^2.
 //                         Output: 4 flag bits per (query, visited block).  No selection, no atomics.
-//   5. kt_select_kernel   thread = query: walks its flagged granules, evaluates the exact chain, keeps
-//                         every reference with d <= TAU0 (at least k exist: those of the window) in a
-//                         per-thread column of shared memory, and finally orders the k smallest
-//                         (distance bits << 32 | original index) keys.
+//   5. kt_select_kernel   a warp takes 32 queries one after the other: lane = reference of a flagged
+//                         granule (exact chain), the references with d <= TAU0 (at least k exist: those
+//                         of the window) are compacted into the warp's buffer as keys (distance bits << 32
+//                         | original index), and every candidate counts the keys below its own: that
+//                         rank is its output slot.
 // Why it is exact: the approximation error of e + |q|^2 against the exact chain is below
 // EPS = 128 u R^2; a reference with d <= TAU0 therefore has e <= TAU0 - |q|^2 + EPS and
 // its granule is flagged (the kernel adds 2.5 EPS); a block is skipped only when its box is provably
