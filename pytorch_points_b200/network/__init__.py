@@ -9,6 +9,6 @@ from .geo_operations import (FurthestPointSampling, FurthestPointSampleGather, f
 from .operations import (stage_features, GatherFunction, gather_points, BallQuery, ball_query, GroupingOperation,  # noqa: F401
                          grouping_operation, QueryAndGroup, QueryAndGroupFunction, query_and_group, group_knn,
                          knn_points)
-from .pointnet2_utils import ThreeNN, three_nn, ThreeInterpolate, three_interpolate, GroupAll  # noqa: F401
+from .pointnet2_utils import ThreeNN, three_nn, ThreeInterpolate, three_interpolate, propagate_features, GroupAll  # noqa: F401
 from .layers import Conv2d, SharedMLP, DenseEdgeConv, SampledDenseEdgeConv  # noqa: F401
 from .pointnet2_modules import PointnetSAModule, PointnetSAModuleMSG, PointnetFPModule  # noqa: F401

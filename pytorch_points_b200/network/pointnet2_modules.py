@@ -133,8 +133,6 @@ class PointnetFPModule(nn.Module):
         if known is None:  # nothing to interpolate from: broadcast the single global descriptor
             spread = known_feats.expand(known_feats.shape[0], known_feats.shape[1], unknown.shape[1])
         else:
-            dist, idx = pointnet2_utils.three_nn(unknown, known)
-            inv = (dist + 1e-8).reciprocal()
-            spread = pointnet2_utils.three_interpolate(known_feats, idx, inv / inv.sum(dim=2, keepdim=True))
+            spread = pointnet2_utils.propagate_features(unknown, known, known_feats)
         stacked = spread if unknow_feats is None else torch.cat([spread, unknow_feats], dim=1)
         return self.mlp(stacked.unsqueeze(-1)).squeeze(-1)

@@ -1,9 +1,10 @@
 """PointNet++ feature-propagation helpers.
 
-Drop-in for `pytorch_points.network.pointnet2_utils.ThreeNN` / `three_nn` and
-`ThreeInterpolate` / `three_interpolate` (network/pointnet2_utils.py:11-88) -- SURVEY.md "next"
-row N3.  `QueryAndGroup` lives in `operations.py` (the reference keeps a duplicate here,
-pointnet2_utils.py:91-124; it is re-exported for import compatibility)."""
+Same public surface as `pytorch_points.network.pointnet2_utils` (`ThreeNN` / `three_nn`, `ThreeInterpolate` /
+`three_interpolate`, `GroupAll`; network/pointnet2_utils.py:11-88,127-150) -- SURVEY.md "next" row N3 -- on this
+repo's kernels, plus `propagate_features`, the whole interpolation step of a feature-propagation level in one
+call.  `QueryAndGroup` lives in `operations.py` (the reference keeps a duplicate in its pointnet2_utils; it is
+re-exported here for import compatibility)."""
 import torch
 
 from .._ext import sampling
@@ -11,23 +12,17 @@ from .operations import QueryAndGroup, ball_query, grouping_operation  # noqa: F
 
 
 class ThreeNN(torch.autograd.Function):
+    """(unknown (B, n, 3), known (B, m, 3)) -> (L2 distances to the three nearest known points, ascending
+    (B, n, 3); their indices (B, n, 3) int32).  Not differentiable, like the reference's."""
 
     @staticmethod
     def forward(ctx, unknown, known):
-        """unknown (B, N, 3), known (B, M, 3) -> (dist (B, N, 3) L2 distances to the three nearest
-        known points, ascending; idx (B, N, 3) int32)."""
-        assert unknown.is_contiguous()
-        assert known.is_contiguous()
-        B, N, _ = unknown.size()
-        m = known.size(1)
-        dist2 = torch.empty(B, N, 3, dtype=torch.float32, device=unknown.device)
-        idx = torch.empty(B, N, 3, dtype=torch.int32, device=unknown.device)
-        sampling.three_nn_wrapper(B, N, m, unknown, known, dist2, idx)
+        dist2, idx = sampling.three_nn(unknown.contiguous(), known.contiguous())
         ctx.mark_non_differentiable(idx)
-        return torch.sqrt(dist2), idx
+        return dist2.sqrt_(), idx  # the kernel returns squared distances in a buffer of our own
 
     @staticmethod
-    def backward(ctx, a=None, b=None):
+    def backward(ctx, *unused):
         return None, None
 
 
@@ -35,46 +30,56 @@ three_nn = ThreeNN.apply  # type: ignore
 
 
 class ThreeInterpolate(torch.autograd.Function):
+    """(features (B, C, m), idx (B, n, 3) int32, weight (B, n, 3)) -> (B, C, n): for every target point the weighted
+    sum of its three source columns.  The gradient flows to `features` only (scatter-add through `idx`)."""
 
     @staticmethod
     def forward(ctx, features, idx, weight):
-        """features (B, C, M), idx (B, n, 3), weight (B, n, 3) -> (B, C, n) weighted sum of the three
-        gathered feature columns."""
-        assert features.is_contiguous()
-        assert idx.is_contiguous()
-        assert weight.is_contiguous()
-        B, c, m = features.size()
-        n = idx.size(1)
-        ctx.three_interpolate_for_backward = (idx, weight, m)
-        output = torch.empty(B, c, n, dtype=torch.float32, device=features.device)
-        sampling.three_interpolate_wrapper(B, c, m, n, features, idx, weight, output)
-        return output
+        features, idx, weight = features.contiguous(), idx.contiguous(), weight.contiguous()
+        batch, channels, m = features.shape
+        n = idx.shape[1]
+        out = features.new_empty(batch, channels, n)
+        sampling.three_interpolate_wrapper(batch, channels, m, n, features, idx, weight, out)
+        ctx.save_for_backward(idx, weight)
+        ctx.sources = m
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, weight, m = ctx.three_interpolate_for_backward
-        B, c, n = grad_out.size()
-        grad_features = torch.zeros(B, c, m, dtype=torch.float32, device=grad_out.device)
-        sampling.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight, grad_features)
+        idx, weight = ctx.saved_tensors
+        batch, channels, n = grad_out.shape
+        grad_features = grad_out.new_zeros(batch, channels, ctx.sources)
+        sampling.three_interpolate_grad_wrapper(batch, channels, n, ctx.sources, grad_out.contiguous(), idx, weight,
+                                                grad_features)
         return grad_features, None, None
 
 
 three_interpolate = ThreeInterpolate.apply  # type: ignore
 
 
+def propagate_features(unknown, known, known_feats, eps=1e-8):
+    """Inverse-distance interpolation of `known_feats` (B, C, m) from the `known` points (B, m, 3) onto the `unknown`
+    points (B, n, 3) -> (B, C, n): the three nearest sources of every target, weights 1 / (distance + eps)
+    normalised to one -- the interpolation step of `PointnetFPModule.forward`
+    (network/pointnet2_modules.py:137-144) as one call."""
+    dist, idx = three_nn(unknown, known)
+    inv = 1.0 / (dist + eps)
+    return three_interpolate(known_feats, idx, inv / inv.sum(dim=2, keepdim=True))
+
+
 class GroupAll(torch.nn.Module):
-    """Groups the whole cloud into one set (network/pointnet2_utils.py:127-150)."""
+    """The whole cloud as ONE group: (xyz (B, N, 3), new_xyz ignored, features (B, C, N) | None) ->
+    (B, 3 * use_xyz + C, 1, N) (same result as network/pointnet2_utils.py:127-150)."""
 
     def __init__(self, use_xyz: bool = True):
         super().__init__()
         self.use_xyz = use_xyz
 
     def forward(self, xyz, new_xyz, features=None):
-        """xyz (B, N, 3), new_xyz ignored, features (B, C, N) -> (B, C + 3, 1, N)."""
-        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
-        if features is None:
-            return grouped_xyz
-        grouped_features = features.unsqueeze(2)
-        if self.use_xyz:
-            return torch.cat([grouped_xyz, grouped_features], dim=1)
-        return grouped_features
+        parts = []
+        if features is None or self.use_xyz:
+            parts.append(xyz.transpose(1, 2))
+        if features is not None:
+            parts.append(features)
+        grouped = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        return grouped.unsqueeze(2)
