@@ -6,58 +6,73 @@ edge-convolution layers that call the KNN / FPS / gather operators.
 (`conv`, `norm`, `act`, `layer{i}`) so state dicts interchange.  They are plain torch.nn
 plumbing around the hot-path operators; the rest of the reference's layer zoo is out of scope
 (SURVEY.md section 8)."""
-from typing import List
+from typing import List, Optional
 
+import torch
 import torch.nn as nn
+
+# what the `normalization` / `activation` keywords of the reference's layers select (network/layers.py:9-21)
+_NORMS = {
+    "batch": lambda ch, momentum: nn.BatchNorm2d(ch, affine=True, eps=0.001, momentum=momentum),
+    "instance": lambda ch, momentum: nn.InstanceNorm2d(ch, affine=True, eps=0.001, momentum=momentum),
+}
+_ACTIVATIONS = {
+    "relu": nn.ReLU,
+    "elu": lambda: nn.ELU(alpha=1.0),
+    "lrelu": lambda: nn.LeakyReLU(0.1),
+    "tanh": nn.Tanh,
+}
+
+
+def _pick(table, key, what):
+    if key not in table:
+        raise ValueError("%s %r is not one of %s" % (what, key, sorted(table)))
+    return table[key]
 
 
 class Conv2d(nn.Module):
-    """2-D convolution followed by optional normalization and activation."""
+    """Convolution -> optional normalization (`norm`) -> optional activation (`act`); the convolution carries a
+    bias only when nothing normalizes its output.  Keywords and sub-module names as in the reference."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True,
-                 activation=None, normalization=None, momentum=0.01, conv_params={}):
+                 activation: Optional[str] = None, normalization: Optional[str] = None, momentum=0.01, conv_params=None):
         super().__init__()
-        self.activation = activation
-        self.normalization = normalization
-        bias = not normalization and bias
+        self.activation, self.normalization = activation, normalization
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding,
-                              bias=bias, **conv_params)
-        if normalization is not None:
-            if normalization == "batch":
-                self.norm = nn.BatchNorm2d(out_channels, affine=True, eps=0.001, momentum=momentum)
-            elif normalization == "instance":
-                self.norm = nn.InstanceNorm2d(out_channels, affine=True, eps=0.001, momentum=momentum)
-            else:
-                raise ValueError("only \"batch/instance\" normalization permitted.")
-        if activation is not None:
-            if activation == "relu":
-                self.act = nn.ReLU()
-            elif activation == "elu":
-                self.act = nn.ELU(alpha=1.0)
-            elif activation == "lrelu":
-                self.act = nn.LeakyReLU(0.1)
-            elif activation == "tanh":
-                self.act = nn.Tanh()
-            else:
-                raise ValueError("only \"relu/elu/lrelu/tanh\" implemented")
+                              bias=bool(bias) and not normalization, **(conv_params or {}))
+        self.norm = None if normalization is None else _pick(_NORMS, normalization, "normalization")(out_channels, momentum)
+        self.act = None if activation is None else _pick(_ACTIVATIONS, activation, "activation")()
 
     def forward(self, x, epoch=None):
-        x = self.conv(x)
-        if self.normalization is not None:
-            x = self.norm(x)
-        if self.activation is not None:
-            x = self.act(x)
+        for stage in (self.conv, self.norm, self.act):
+            if stage is not None:
+                x = stage(x)
         return x
 
 
 class SharedMLP(nn.Sequential):
-    """A stack of 1x1 `Conv2d` blocks applied to every (point, sample) position."""
+    """1x1 `Conv2d` blocks `layer0`, `layer1`, ... with widths `args[0] -> args[1] -> ...`, applied to every
+    (point, sample) position."""
 
     def __init__(self, args: List[int], activation: str = None, normalization: str = None, **kwargs):
         super().__init__()
-        for i in range(len(args) - 1):
-            self.add_module("layer{}".format(i),
-                            Conv2d(args[i], args[i + 1], 1, normalization=normalization, activation=activation))
+        for i, (c_in, c_out) in enumerate(zip(args[:-1], args[1:])):
+            self.add_module("layer%d" % i, Conv2d(c_in, c_out, 1, normalization=normalization, activation=activation))
+
+
+def _dense_stack(mlps, edge, carry):
+    """The densely connected part shared by both edge convolutions: the first MLP sees the edge features and is
+    concatenated with `carry` (the centre features repeated over the k neighbours); every later MLP sees everything
+    produced so far and is stacked in front of it; ReLU after all but the last; finally the maximum over the
+    neighbours.  -> (B, C', S)"""
+    last = len(mlps) - 1
+    y = edge
+    for i, mlp in enumerate(mlps):
+        out = mlp(y)
+        if i != last or i == 0:
+            out = nn.functional.relu_(out)
+        y = torch.cat([out, carry if i == 0 else y], dim=1)
+    return y.max(dim=-1)[0]
 
 
 class DenseEdgeConv(nn.Module):
@@ -78,7 +93,6 @@ class DenseEdgeConv(nn.Module):
         """x (B, C, N) -> edge features [x_i, x_j - x_i] (B, 2C, N, k) over the k nearest
         neighbours j of i (the point itself excluded), and their indices (B, N, k)."""
         from .operations import knn_points
-        import torch
         pts = x.transpose(1, 2).contiguous()  # (B, N, C)
         if idx is None:
             _, idx, nn_pts = knn_points(pts, pts, K=k + 1, return_nn=True)  # (B, N, k+1[, C])
@@ -92,18 +106,9 @@ class DenseEdgeConv(nn.Module):
 
     def forward(self, x, idx=None):
         """x (B, C, N) -> (features (B, C', N), knn idx (B, N, k))."""
-        import torch
-        for i, mlp in enumerate(self.mlps):
-            if i == 0:
-                y, idx = self.get_local_graph(x, k=self.k, idx=idx)
-                x = x.unsqueeze(-1).repeat(1, 1, 1, self.k)
-                y = torch.cat([nn.functional.relu_(mlp(y)), x], dim=1)
-            elif i == (self.n - 1):
-                y = torch.cat([mlp(y), y], dim=1)
-            else:
-                y = torch.cat([nn.functional.relu_(mlp(y)), y], dim=1)
-        y, _ = torch.max(y, dim=-1)
-        return y, idx
+        edge, idx = self.get_local_graph(x, k=self.k, idx=idx)
+        carry = x.unsqueeze(-1).expand(-1, -1, -1, self.k)
+        return _dense_stack(self.mlps, edge, carry), idx
 
 
 class SampledDenseEdgeConv(DenseEdgeConv):
@@ -121,7 +126,6 @@ class SampledDenseEdgeConv(DenseEdgeConv):
         """query (B, C, S) centres, x (B, C, N) all points -> edge features [q_i, x_j - q_i]
         (B, 2C, S, k) over the k nearest neighbours j of centre i in feature space (the nearest
         one, i itself, excluded) and their indices (B, S, k)."""
-        import torch
         from . import operations as ops
         pts = x.transpose(1, 2).contiguous()  # (B, N, C)
         if idx is None:
@@ -139,7 +143,6 @@ class SampledDenseEdgeConv(DenseEdgeConv):
     def forward(self, x, nsample, xyz):
         """x (B, C, N) features, xyz (B, 3, N) coordinates ->
         (features (B, C', nsample), sampled_xyz (B, 3, nsample), sampled_idx (B, nsample))."""
-        import torch
         from . import geo_operations as geo
         from . import operations as ops
         if nsample == 1:
@@ -152,14 +155,6 @@ class SampledDenseEdgeConv(DenseEdgeConv):
         else:
             sampled_idx, sampled_xyz = geo.furthest_point_sample(xyz, nsample, NCHW=True)
         sampled_x = ops.gather_points(x.contiguous(), sampled_idx)  # (B, C, nsample)
-        for i, mlp in enumerate(self.mlps):
-            if i == 0:
-                y, _ = self.get_local_graph(sampled_x, x, k=self.k)
-                centre = sampled_x.unsqueeze(-1).expand(-1, -1, -1, self.k)
-                y = torch.cat([nn.functional.relu_(mlp(y)), centre], dim=1)
-            elif i == (self.n - 1):
-                y = torch.cat([mlp(y), y], dim=1)
-            else:
-                y = torch.cat([nn.functional.relu_(mlp(y)), y], dim=1)
-        y, _ = torch.max(y, dim=-1)
-        return y, sampled_xyz, sampled_idx
+        edge, _ = self.get_local_graph(sampled_x, x, k=self.k)
+        carry = sampled_x.unsqueeze(-1).expand(-1, -1, -1, self.k)
+        return _dense_stack(self.mlps, edge, carry), sampled_xyz, sampled_idx

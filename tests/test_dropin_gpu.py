@@ -250,3 +250,40 @@ def test_reference_knn_callers_on_the_plugin_knn(both):
     conv = ours.layers.DenseEdgeConv(3, 12, n=3, k=k).cuda()
     with pytest.raises(RuntimeError, match="expanded size"):
         conv(pts.transpose(1, 2).contiguous())
+
+
+def test_own_layers_and_fp_helpers_interchange_with_the_reference(both):
+    """This repo's own `network.layers.Conv2d` / `SharedMLP` and `network.pointnet2_utils` (written independently of
+    the reference's files) take the reference modules' state dicts and give the same numbers as the reference's own
+    classes running over the plugin: keyword meaning, sub-module names and the feature-propagation arithmetic."""
+    ours, _ = both
+    from pytorch_points_b200 import network as mine
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6, 40, 5, generator=g).cuda()
+    for act, norm in (("relu", "batch"), ("lrelu", "instance"), ("tanh", None), (None, None), ("elu", "batch")):
+        ref_mlp = ours.layers.SharedMLP([6, 16, 9], activation=act, normalization=norm).cuda().eval()
+        own_mlp = mine.layers.SharedMLP([6, 16, 9], activation=act, normalization=norm).cuda().eval()
+        assert sorted(own_mlp.state_dict()) == sorted(ref_mlp.state_dict())
+        own_mlp.load_state_dict(ref_mlp.state_dict())
+        assert torch.equal(own_mlp(x), ref_mlp(x)), (act, norm)
+    with pytest.raises(ValueError):
+        mine.layers.Conv2d(3, 4, 1, normalization="layer")
+    # three_nn / three_interpolate / GroupAll / the one-call interpolation step
+    unknown, known = uniform_cloud(2, 900, 41).cuda(), uniform_cloud(2, 64, 42).cuda()
+    feats = torch.randn(2, 7, 64, generator=g).cuda().requires_grad_(True)
+    feats_r = feats.detach().clone().requires_grad_(True)
+    d_r, i_r = ours.pointnet2_utils.three_nn(unknown, known)
+    d_o, i_o = mine.three_nn(unknown, known)
+    assert torch.equal(d_r, d_o) and torch.equal(i_r, i_o)
+    w = 1.0 / (d_r + 1e-8)
+    w = w / w.sum(dim=2, keepdim=True)
+    out_r = ours.pointnet2_utils.three_interpolate(feats_r, i_r, w)
+    out_o = mine.propagate_features(unknown, known, feats)
+    assert torch.equal(out_r, out_o)
+    out_r.sum().backward(); out_o.sum().backward()
+    _sync()
+    _grad_close(feats.grad, feats_r.grad, "propagate_features gradient")
+    xyz, f = uniform_cloud(2, 50, 43).cuda(), torch.randn(2, 4, 50, generator=g).cuda()
+    for use_xyz in (True, False):
+        assert torch.equal(mine.GroupAll(use_xyz)(xyz, None, f), ours.pointnet2_utils.GroupAll(use_xyz)(xyz, None, f))
+        assert torch.equal(mine.GroupAll(use_xyz)(xyz, None), ours.pointnet2_utils.GroupAll(use_xyz)(xyz, None))
