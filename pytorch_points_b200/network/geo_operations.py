@@ -8,77 +8,73 @@ from .._ext import sampling
 from .operations import gather_points
 
 
+def _sample(xyz, npoint, seed, with_points):
+    """One farthest-point-sampling call on a contiguous (B, N, 3) cloud: the index buffer and the running minimum
+    distances (started at 1e10, like the reference's `temp`) are allocated here; with `with_points` the kernel
+    also writes the winners' coordinates (they are in its hands every round)."""
+    batch, n = xyz.shape[0], xyz.shape[1]
+    idx = xyz.new_empty((batch, npoint), dtype=torch.int32)
+    nearest = xyz.new_full((batch, n), 1e10, dtype=torch.float32)
+    if not with_points:
+        sampling.furthest_sampling(npoint, seed, xyz, nearest, idx)
+        return idx, None
+    picked = xyz.new_empty((batch, npoint, 3), dtype=torch.float32)
+    sampling.furthest_sampling_gather(npoint, seed, xyz, nearest, idx, picked)
+    return idx, picked
+
+
 class FurthestPointSampling(torch.autograd.Function):
+    """xyz (B, N, 3) -> idx (B, npoint) int32 with idx[:, 0] == seedIdx; every next sample is the point farthest
+    from the set selected so far (the reference's tie-break).  Same signature as the reference's Function
+    (network/geo_operations.py:11-40); not differentiable."""
 
     @staticmethod
     def forward(ctx, xyz, npoint, seedIdx):
-        """xyz (B, N, 3) -> idx (B, npoint) int32; idx[:, 0] == seedIdx.  Each next sample is the
-        point with the largest distance to the already selected set (reference tie-break)."""
-        B, N, _ = xyz.size()
-        idx = torch.empty([B, npoint], dtype=torch.int32, device=xyz.device)
-        temp = torch.full([B, N], 1e10, dtype=torch.float32, device=xyz.device)
-        sampling.furthest_sampling(npoint, seedIdx, xyz, temp, idx)
+        idx, _ = _sample(xyz, npoint, seedIdx, False)
         ctx.mark_non_differentiable(idx)
         return idx
 
     @staticmethod
-    def backward(ctx, grad_idx=None):
+    def backward(ctx, *unused):
         return None, None, None
 
 
-__furthest_point_sample = FurthestPointSampling.apply  # type: ignore
-
-
 class FurthestPointSampleGather(torch.autograd.Function):
-    """FPS with the gather of the sampled coordinates fused into the sampling kernel."""
+    """FPS with the gather of the sampled coordinates fused into the sampling kernel:
+    xyz (B, N, 3) contiguous -> (idx (B, npoint) int32, new_xyz (B, npoint, 3)); the gradient of `new_xyz` is
+    scattered back onto the sampled points."""
 
     @staticmethod
     def forward(ctx, xyz, npoint, seedIdx):
-        """xyz (B, N, 3) contiguous -> (idx (B, npoint) int32, new_xyz (B, npoint, 3))."""
-        B, N, _ = xyz.size()
-        idx = torch.empty([B, npoint], dtype=torch.int32, device=xyz.device)
-        new_xyz = torch.empty([B, npoint, 3], dtype=torch.float32, device=xyz.device)
-        temp = torch.full([B, N], 1e10, dtype=torch.float32, device=xyz.device)
-        sampling.furthest_sampling_gather(npoint, seedIdx, xyz, temp, idx, new_xyz)
+        idx, picked = _sample(xyz, npoint, seedIdx, True)
         ctx.save_for_backward(idx)
-        ctx.N = N
+        ctx.cloud_size = xyz.shape[1]
         ctx.mark_non_differentiable(idx)
-        return idx, new_xyz
+        return idx, picked
 
     @staticmethod
     def backward(ctx, grad_idx, grad_new_xyz):
         # same scatter as GatherFunction.backward on the (B, 3, N) view (network/operations.py:68-85)
-        idx, = ctx.saved_tensors
-        B, npoint = idx.size()
-        g = torch.zeros(B, 3, ctx.N, dtype=torch.float32, device=grad_new_xyz.device)
-        sampling.gather_backward(B, 3, ctx.N, npoint, grad_new_xyz.transpose(1, 2).contiguous(), idx, g)
-        return g.transpose(1, 2).contiguous(), None, None
-
-
-__furthest_point_sample_gather = FurthestPointSampleGather.apply  # type: ignore
+        (idx,) = ctx.saved_tensors
+        batch, npoint = idx.shape
+        grad = grad_new_xyz.new_zeros(batch, 3, ctx.cloud_size)
+        sampling.gather_backward(batch, 3, ctx.cloud_size, npoint, grad_new_xyz.transpose(1, 2).contiguous(), idx, grad)
+        return grad.transpose(1, 2).contiguous(), None, None
 
 
 def furthest_point_sample(xyz, npoint, NCHW=True, seedIdx=0):
-    """xyz (B, 3, N) if NCHW else (B, N, 3) -> (idx (B, npoint) int32,
-    sampled points (B, 3, npoint) if NCHW else (B, npoint, 3))."""
-    assert xyz.dim() == 3, "input for furthest sampling must be a 3D-tensor, but xyz.size() is {}".format(xyz.size())
-    if NCHW:
-        xyz = xyz.transpose(2, 1).contiguous()
-    else:
-        xyz = xyz.contiguous()
-    assert xyz.size(2) == 3, "furthest sampling is implemented for 3D points"
-    # the reference gathers the samples with a second kernel and two transposes
-    # (geo_operations.py:60-63); the sampling kernel already holds each winner's coordinates
-    idx, sampled_pc = __furthest_point_sample_gather(xyz, npoint, seedIdx)
-    if NCHW:
-        sampled_pc = sampled_pc.transpose(2, 1).contiguous()
-    return idx, sampled_pc
+    """xyz (B, 3, N) if NCHW else (B, N, 3) -> (idx (B, npoint) int32, sampled points in the layout of the input).
+    The reference gathers the samples with a second kernel and two transposes (geo_operations.py:60-63); here the
+    sampling kernel writes them."""
+    if xyz.dim() != 3:
+        raise AssertionError("input for furthest sampling must be a 3D-tensor, but xyz.size() is {}".format(xyz.size()))
+    cloud = (xyz.transpose(1, 2) if NCHW else xyz).contiguous()
+    if cloud.shape[2] != 3:
+        raise AssertionError("furthest sampling is implemented for 3D points")
+    idx, picked = FurthestPointSampleGather.apply(cloud, npoint, seedIdx)
+    return idx, (picked.transpose(1, 2).contiguous() if NCHW else picked)
 
 
-# ---------------------------------------------------------------------------
-# k-NN based geometry helpers (SURVEY.md next row N4): the reference's versions call
-# pytorch3d.ops.knn_points (network/geo_operations.py:88-152); these run on this repo's KNN.
-# ---------------------------------------------------------------------------
 def _gather_neighbours(points, idx):
     """points (B, N, C), idx (B, M, K) -> (B, M, K, C)."""
     B, M, K = idx.shape
