@@ -12,60 +12,65 @@ from .._ext import sampling
 
 
 class GatherFunction(torch.autograd.Function):
+    """features (B, C, N), idx (B, npoint) -> the selected columns (B, C, npoint); the gradient is scattered back
+    onto the selected columns.  Same signature as the reference's Function (network/operations.py:38-85)."""
+
     @staticmethod
     def forward(ctx, features, idx):
-        """features (B, C, N), idx (B, npoint) -> (B, C, npoint)."""
         features = features.contiguous()
-        idx = idx.contiguous().to(dtype=torch.int32)
-        B, npoint = idx.size()
-        _, C, N = features.size()
-        output = torch.empty(B, C, npoint, dtype=features.dtype, device=features.device)
-        sampling.gather_forward(B, C, N, npoint, features, idx, output)
+        idx = idx.to(torch.int32).contiguous()
+        (batch, channels, n), npoint = features.shape, idx.shape[1]
+        picked = features.new_empty(batch, channels, npoint)
+        sampling.gather_forward(batch, channels, n, npoint, features, idx, picked)
         ctx.save_for_backward(idx)
-        ctx.C = C
-        ctx.N = N
-        return output
+        ctx.source_shape = (batch, channels, n)
+        return picked
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, = ctx.saved_tensors
-        B, npoint = idx.size()
-        grad_features = torch.zeros(B, ctx.C, ctx.N, dtype=grad_out.dtype, device=grad_out.device)
-        sampling.gather_backward(B, ctx.C, ctx.N, npoint, grad_out.contiguous(), idx, grad_features)
-        return grad_features, None
+        (idx,) = ctx.saved_tensors
+        batch, channels, n = ctx.source_shape
+        grad = grad_out.new_zeros(batch, channels, n)
+        sampling.gather_backward(batch, channels, n, idx.shape[1], grad_out.contiguous(), idx, grad)
+        return grad, None
 
 
 gather_points = GatherFunction.apply  # type: ignore
 
 
 class BallQuery(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, radius, nsample, xyz, new_xyz):
-        """radius, nsample, xyz (B, N, 3), new_xyz (B, npoint, 3) -> idx (B, npoint, nsample) int32."""
-        idx = sampling.ball_query(new_xyz, xyz, radius, nsample)
-        ctx.mark_non_differentiable(idx)
-        return idx
+    """(radius, nsample, xyz (B, N, 3), new_xyz (B, npoint, 3)) -> idx (B, npoint, nsample) int32: the first
+    `nsample` points of `xyz` (in index order) within `radius` of each centre, padded with the first hit.
+    Argument order of the reference's Function (network/operations.py:88-114); not differentiable."""
 
     @staticmethod
-    def backward(ctx, a=None):
-        return None, None, None, None
+    def forward(ctx, radius, nsample, xyz, new_xyz):
+        members = sampling.ball_query(new_xyz, xyz, radius, nsample)
+        ctx.mark_non_differentiable(members)
+        return members
+
+    @staticmethod
+    def backward(ctx, *unused):
+        return (None,) * 4
 
 
 ball_query = BallQuery.apply  # type: ignore
 
 
 class GroupingOperation(torch.autograd.Function):
+    """features (B, C, N), idx (B, npoint, nsample) -> (B, C, npoint, nsample); the gradient is scatter-added
+    through `idx` (network/operations.py:117-163)."""
+
     @staticmethod
     def forward(ctx, features, idx):
-        """features (B, C, N), idx (B, npoint, nsample) -> (B, C, npoint, nsample)."""
-        _, _, N = features.size()
-        ctx.for_backwards = (idx, N)
+        ctx.save_for_backward(idx)
+        ctx.sources = features.shape[2]
         return sampling.group_points(features, idx)
 
     @staticmethod
     def backward(ctx, grad_out):
-        idx, N = ctx.for_backwards
-        return sampling.group_points_grad(grad_out.contiguous(), idx, N), None
+        (idx,) = ctx.saved_tensors
+        return sampling.group_points_grad(grad_out.contiguous(), idx, ctx.sources), None
 
 
 grouping_operation = GroupingOperation.apply  # type: ignore
