@@ -15,34 +15,47 @@ from .. import _C
 from .._ext import losses
 
 
+def _pair(xyz1, xyz2):
+    """Both clouds contiguous, shapes and dtypes checked once for all three Functions below."""
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.dtype != xyz2.dtype:
+        raise AssertionError("nndistance: two (B, n, c) clouds of one dtype expected, got %s %s and %s %s"
+                             % (tuple(xyz1.shape), xyz1.dtype, tuple(xyz2.shape), xyz2.dtype))
+    return xyz1.contiguous(), xyz2.contiguous()
+
+
+def _nn_outputs(xyz1, xyz2):
+    """The four outputs of a Chamfer forward, each a tensor of its own on the clouds' device: squared
+    distances (B, n) / (B, m) and int32 neighbour indices."""
+    batch, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    return (xyz1.new_empty(batch, n), xyz1.new_empty(batch, m),
+            xyz1.new_empty((batch, n), dtype=torch.int32), xyz1.new_empty((batch, m), dtype=torch.int32))
+
+
+def _nn_backward(saved, graddist1, graddist2):
+    """d loss / d clouds from the per-point upstream gradients and the saved neighbour indices (the kernel
+    overwrites its outputs: no zero fill)."""
+    xyz1, xyz2, idx1, idx2 = saved
+    grads = torch.empty_like(xyz1), torch.empty_like(xyz2)
+    losses.nmdistance_backward(xyz1, xyz2, grads[0], grads[1], graddist1.contiguous(), graddist2.contiguous(), idx1, idx2)
+    return grads
+
+
 class NmDistanceFunction(torch.autograd.Function):
-    """3D point set to 3D point set distance (both directions in one pass)."""
+    """Point set to point set nearest-neighbour distances, both directions:
+    (xyz1 (B, n, 3), xyz2 (B, m, 3)) -> (dist1, dist2, idx1, idx2)."""
 
     @staticmethod
     def forward(ctx, xyz1, xyz2):
-        xyz1 = xyz1.contiguous()
-        xyz2 = xyz2.contiguous()
-        assert xyz1.dim() == 3 and xyz2.dim() == 3
-        assert xyz1.dtype == xyz2.dtype
-        B, n, _ = xyz1.size()
-        _, m, _ = xyz2.size()
-        dist1 = torch.empty(B, n, dtype=xyz1.dtype, device=xyz1.device)
-        dist2 = torch.empty(B, m, dtype=xyz1.dtype, device=xyz1.device)
-        idx1 = torch.empty(B, n, dtype=torch.int32, device=xyz1.device)
-        idx2 = torch.empty(B, m, dtype=torch.int32, device=xyz1.device)
-        losses.nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2)
-        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
-        ctx.mark_non_differentiable(idx1, idx2)
-        return dist1, dist2, idx1, idx2
+        xyz1, xyz2 = _pair(xyz1, xyz2)
+        out = _nn_outputs(xyz1, xyz2)
+        losses.nmdistance_forward(xyz1, xyz2, *out)
+        ctx.save_for_backward(xyz1, xyz2, out[2], out[3])
+        ctx.mark_non_differentiable(out[2], out[3])
+        return out
 
     @staticmethod
-    def backward(ctx, graddist1, graddist2, gradNone1, gradNone2):
-        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        gradxyz1 = torch.empty_like(xyz1)
-        gradxyz2 = torch.empty_like(xyz2)
-        losses.nmdistance_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1.contiguous(),
-                                   graddist2.contiguous(), idx1, idx2)
-        return gradxyz1, gradxyz2
+    def backward(ctx, graddist1, graddist2, *unused):
+        return _nn_backward(ctx.saved_tensors, graddist1, graddist2)
 
 
 nndistance = NmDistanceFunction.apply  # type: ignore
@@ -54,30 +67,16 @@ class LabeledNmdistanceFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz1, xyz2, label1, label2):
-        xyz1 = xyz1.contiguous()
-        xyz2 = xyz2.contiguous()
-        assert xyz1.dtype == xyz2.dtype
-        B, n, _ = xyz1.size()
-        _, m, _ = xyz2.size()
-        label1 = label1.to(dtype=xyz1.dtype)
-        label2 = label2.to(dtype=xyz1.dtype)
-        dist1 = torch.empty(B, n, dtype=xyz1.dtype, device=xyz1.device)
-        dist2 = torch.empty(B, m, dtype=xyz1.dtype, device=xyz1.device)
-        idx1 = torch.empty(B, n, dtype=torch.int32, device=xyz1.device)
-        idx2 = torch.empty(B, m, dtype=torch.int32, device=xyz1.device)
-        losses.labeled_nmdistance_forward(xyz1, xyz2, label1, label2, dist1, dist2, idx1, idx2)
-        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
-        ctx.mark_non_differentiable(idx1, idx2)
-        return dist1, dist2, idx1, idx2
+        xyz1, xyz2 = _pair(xyz1, xyz2)
+        out = _nn_outputs(xyz1, xyz2)
+        losses.labeled_nmdistance_forward(xyz1, xyz2, label1.to(dtype=xyz1.dtype), label2.to(dtype=xyz1.dtype), *out)
+        ctx.save_for_backward(xyz1, xyz2, out[2], out[3])
+        ctx.mark_non_differentiable(out[2], out[3])
+        return out
 
     @staticmethod
-    def backward(ctx, graddist1, graddist2, gradNone1, gradNone2):
-        xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        gradxyz1 = torch.empty_like(xyz1)
-        gradxyz2 = torch.empty_like(xyz2)
-        losses.nmdistance_backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1.contiguous(),
-                                   graddist2.contiguous(), idx1, idx2)
-        return gradxyz1, gradxyz2, None, None
+    def backward(ctx, graddist1, graddist2, *unused):
+        return _nn_backward(ctx.saved_tensors, graddist1, graddist2) + (None, None)
 
 
 labeled_nndistance = LabeledNmdistanceFunction.apply  # type: ignore
@@ -91,27 +90,19 @@ class ChamferSumsFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz1, xyz2):
-        xyz1 = xyz1.contiguous()
-        xyz2 = xyz2.contiguous()
-        B, n, _ = xyz1.size()
-        _, m, _ = xyz2.size()
-        dev = xyz1.device
-        dist1 = torch.empty(B, n, dtype=xyz1.dtype, device=dev)
-        dist2 = torch.empty(B, m, dtype=xyz1.dtype, device=dev)
-        idx1 = torch.empty(B, n, dtype=torch.int32, device=dev)
-        idx2 = torch.empty(B, m, dtype=torch.int32, device=dev)
-        sums = torch.empty(2, dtype=xyz1.dtype, device=dev)
-        losses.nmdistance_forward(xyz1, xyz2, dist1, dist2, idx1, idx2, sums=sums)
-        ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+        xyz1, xyz2 = _pair(xyz1, xyz2)
+        out = _nn_outputs(xyz1, xyz2)
+        sums = xyz1.new_empty(2)
+        losses.nmdistance_forward(xyz1, xyz2, *out, sums=sums)
+        ctx.save_for_backward(xyz1, xyz2, out[2], out[3])
         return sums
 
     @staticmethod
     def backward(ctx, gsums):
         xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
-        gradxyz1 = torch.empty_like(xyz1)
-        gradxyz2 = torch.empty_like(xyz2)
-        losses.nmdistance_backward_uniform(xyz1, xyz2, gradxyz1, gradxyz2, gsums.contiguous(), idx1, idx2)
-        return gradxyz1, gradxyz2
+        grads = torch.empty_like(xyz1), torch.empty_like(xyz2)
+        losses.nmdistance_backward_uniform(xyz1, xyz2, grads[0], grads[1], gsums.contiguous(), idx1, idx2)
+        return grads
 
 
 chamfer_sums = ChamferSumsFunction.apply  # type: ignore
