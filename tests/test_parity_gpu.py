@@ -695,6 +695,7 @@ KNN_TC_CASES = [
     ("duplicates", 2, 2048, 2048, 16), ("lattice", 2, 1500, 1500, 16), ("offset", 2, 2048, 2048, 16),
     ("tiny", 2, 2048, 2048, 16), ("fewpoints", 2, 300, 40, 32), ("k1", 2, 2048, 2048, 1), ("k32", 1, 4096, 4096, 32),
     ("allequal", 1, 600, 600, 16), ("clusters", 2, 4096, 4096, 16), ("above16k", 1, 300, 16500, 8),
+    ("onequery", 1, 1, 2048, 3), ("oddtile", 1, 129, 4000, 17), ("kequalsn", 2, 50, 24, 24), ("manyclouds", 40, 130, 260, 5),
 ]
 
 
